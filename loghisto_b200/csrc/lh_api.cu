@@ -1,0 +1,874 @@
+// lh_api.cu -- C ABI (include/loghisto_b200.h) over the sm_100a kernels.
+//
+// Host-side bookkeeping only: double-buffered bucket/counter arrays, stream
+// and event ordering between ingest and snapshot, the pinned staging ring,
+// kernel-variant dispatch.  No bucket arithmetic happens on the CPU.
+#include "../../include/loghisto_b200.h"
+#include "lh_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace lh;
+
+namespace {
+
+struct WriterEvent { cudaStream_t stream; cudaEvent_t ev; };
+
+struct Buffer {
+    unsigned long long *d_buckets = nullptr;   // [H][65536]
+    unsigned long long *d_counters = nullptr;  // [C]
+    cudaEvent_t cleared = nullptr;             // zeroing finished
+    std::vector<WriterEvent> writers;          // last ingest per stream
+};
+
+enum SlotState { SLOT_FREE = 0, SLOT_ACQUIRED = 1, SLOT_INFLIGHT = 2 };
+struct Slot {
+    void *h = nullptr; void *d = nullptr;
+    cudaEvent_t done = nullptr;
+    int state = SLOT_FREE;
+    uint64_t seq = 0;
+};
+
+struct K1Variant {
+    const char *name;
+    void (*launch)(int grid, size_t smem, cudaStream_t s, const double *v32, size_t nvec,
+                   const double *head, int nhead, const double *tail, int ntail, unsigned long long *counts);
+    const void *func;
+    int threads;
+    size_t smem;
+    int blocks_per_sm;   // filled at create
+};
+
+template <int THREADS, int UNROLL, int COPIES, int MINB, bool WIDE>
+void launch_ldg(int grid, size_t smem, cudaStream_t s, const double *v32, size_t nvec, const double *head, int nhead,
+                const double *tail, int ntail, unsigned long long *counts) {
+    k_ingest_single_ldg<THREADS, UNROLL, COPIES, MINB, WIDE><<<grid, THREADS, smem, s>>>(v32, nvec, head, nhead, tail, ntail, counts);
+}
+template <int CW, int STAGES, int STAGE_BYTES, int COPIES, int MINB>
+void launch_bulk(int grid, size_t smem, cudaStream_t s, const double *v32, size_t nvec, const double *head, int nhead,
+                 const double *tail, int ntail, unsigned long long *counts) {
+    k_ingest_single_bulk<CW, STAGES, STAGE_BYTES, COPIES, MINB><<<grid, (CW + 1) * 32, smem, s>>>(v32, nvec, head, nhead, tail, ntail, counts);
+}
+
+constexpr size_t hist_bytes(int copies) { return (size_t)copies * LH_SUBHIST_ALLOC * 4; }
+constexpr size_t bulk_smem(int stages, int stage_bytes, int copies) {
+    return (size_t)stages * stage_bytes + (size_t)stages * 16 + hist_bytes(copies);
+}
+
+#define LDG_VARIANT(T, U, C, M, W) \
+    { "ldg" #W "_t" #T "_u" #U "_c" #C "_b" #M, launch_ldg<T, U, C, M, W == 256>, (const void *)k_ingest_single_ldg<T, U, C, M, W == 256>, T, hist_bytes(C), 0 }
+#define BULK_VARIANT(W, S, B, C, M) \
+    { "bulk_w" #W "_s" #S "_" #B "_c" #C "_b" #M, launch_bulk<W, S, B, C, M>, (const void *)k_ingest_single_bulk<W, S, B, C, M>, (W + 1) * 32, bulk_smem(S, B, C), 0 }
+
+K1Variant g_k1_variants[] = {
+    LDG_VARIANT(512, 2, 1, 2, 256),     // 0
+    LDG_VARIANT(512, 2, 2, 2, 256),     // 1
+    LDG_VARIANT(256, 2, 1, 4, 256),     // 2
+    LDG_VARIANT(512, 2, 1, 2, 128),     // 3
+    LDG_VARIANT(512, 1, 1, 2, 256),     // 4
+    BULK_VARIANT(16, 4, 32768, 1, 1),   // 5
+    BULK_VARIANT(16, 4, 32768, 2, 1),   // 6
+    BULK_VARIANT(8, 4, 16384, 1, 2),    // 7
+    BULK_VARIANT(8, 3, 32768, 1, 2),    // 8
+    BULK_VARIANT(16, 3, 65536, 1, 1),   // 9
+    BULK_VARIANT(4, 4, 8192, 1, 4),     // 10
+};
+constexpr int kNumK1Variants = (int)(sizeof(g_k1_variants) / sizeof(g_k1_variants[0]));
+constexpr int kDefaultK1Variant = 0;
+
+}  // namespace
+
+struct lh_ctx {
+    lh_config cfg{};
+    int device = 0;
+    int sm_count = 0;
+    uint32_t H = 0, C = 0;
+    Buffer buf[2];
+    int active = 0;
+    bool frozen = false;
+    bool nnz_valid = false;
+    cudaStream_t ingest_stream = nullptr, snap_stream = nullptr;
+    double *d_decomp = nullptr;
+    unsigned long long *d_dropped = nullptr;
+    // reduce / export scratch
+    double *d_ps = nullptr;
+    unsigned long long *d_r_count = nullptr;
+    double *d_r_sum = nullptr, *d_r_avg = nullptr, *d_r_pvals = nullptr;
+    int *d_r_pkeys = nullptr;
+    uint32_t *d_nnz = nullptr, *d_offsets = nullptr;
+    short *d_x_keys = nullptr; unsigned long long *d_x_counts = nullptr; size_t x_cap = 0;
+    // pinned host mirrors
+    void *h_scratch = nullptr; size_t h_scratch_bytes = 0;
+    uint32_t *h_offsets = nullptr;
+    short *h_x_keys = nullptr; unsigned long long *h_x_counts = nullptr; size_t hx_cap = 0;
+    unsigned long long *h_counter_deltas = nullptr;
+    // staging ring
+    std::vector<Slot> slots;
+    uint64_t slot_seq = 0;
+    size_t staging_bytes = 0;
+    // tuning
+    int k1_variant = kDefaultK1Variant;
+    int k1_grid_mult = 1;
+    int keyed_blocks_per_sm = 8;
+    K1Variant k1[kNumK1Variants];
+    // timing of the most recent ingest kernel
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    bool timing_valid = false;
+    // stats
+    lh_stats stats{};
+    std::mutex mu;
+    std::string last_error;
+};
+
+namespace {
+
+lh_status fail(lh_ctx *ctx, lh_status st, const char *what, cudaError_t e = cudaSuccess) {
+    if (ctx) {
+        char buf[512];
+        if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+        else snprintf(buf, sizeof buf, "%s", what);
+        ctx->last_error = buf;
+    }
+    return st;
+}
+
+#define LH_CUDA(ctx, call)                                                      \
+    do {                                                                        \
+        cudaError_t _e = (call);                                                \
+        if (_e != cudaSuccess) return fail((ctx), LH_ERR_CUDA, #call, _e);      \
+    } while (0)
+
+// order `s` after the zeroing of buffer b, and remember `s` as a writer of b
+lh_status before_write(lh_ctx *ctx, int b, cudaStream_t s) {
+    LH_CUDA(ctx, cudaStreamWaitEvent(s, ctx->buf[b].cleared, 0));
+    return LH_OK;
+}
+lh_status after_write(lh_ctx *ctx, int b, cudaStream_t s) {
+    for (auto &w : ctx->buf[b].writers)
+        if (w.stream == s) { LH_CUDA(ctx, cudaEventRecord(w.ev, s)); return LH_OK; }
+    WriterEvent w{s, nullptr};
+    LH_CUDA(ctx, cudaEventCreateWithFlags(&w.ev, cudaEventDisableTiming));
+    LH_CUDA(ctx, cudaEventRecord(w.ev, s));
+    ctx->buf[b].writers.push_back(w);
+    return LH_OK;
+}
+
+cudaStream_t pick_stream(lh_ctx *ctx, void *stream) { return stream ? (cudaStream_t)stream : ctx->ingest_stream; }
+
+int grid_1d(lh_ctx *ctx, size_t n, int threads, int per_thread, int blocks_per_sm) {
+    size_t need = (n + (size_t)threads * per_thread - 1) / ((size_t)threads * per_thread);
+    size_t cap = (size_t)ctx->sm_count * blocks_per_sm;
+    return (int)std::max<size_t>(1, std::min(need, cap));
+}
+
+// ---- K1 dispatch (locked) ----
+lh_status launch_single(lh_ctx *ctx, uint32_t hid, const double *d_values, size_t n, cudaStream_t s) {
+    if (hid >= ctx->H) return fail(ctx, LH_ERR_RANGE, "histogram_id >= max_histograms");
+    if (((uintptr_t)d_values & 7u) != 0) return fail(ctx, LH_ERR_INVALID, "d_values must be 8-byte aligned");
+    const int b = ctx->active;
+    lh_status st = before_write(ctx, b, s);
+    if (st != LH_OK) return st;
+    unsigned long long *counts = ctx->buf[b].d_buckets + (size_t)hid * 65536u;
+    const K1Variant &kv = ctx->k1[ctx->k1_variant];
+    // a CTA's uint32 sub-histogram must not overflow: bound samples per launch
+    const size_t kMaxPerLaunch = (size_t)1 << 36;
+    size_t done = 0;
+    LH_CUDA(ctx, cudaEventRecord(ctx->ev_t0, s));
+    while (done < n) {
+        size_t m = std::min(n - done, kMaxPerLaunch);
+        const double *p = d_values + done;
+        // peel up to 3 samples so the body is 32-byte aligned (256-bit loads, 16-byte bulk copies)
+        int nhead = (int)(((32u - ((uintptr_t)p & 31u)) & 31u) / 8u);
+        if ((size_t)nhead > m) nhead = (int)m;
+        const double *head = p;
+        const double *body = p + nhead;
+        size_t nvec = (m - nhead) >> 2;
+        const double *tail = body + nvec * 4;
+        int ntail = (int)(m - nhead - nvec * 4);
+        size_t consumed = m;
+        int grid = ctx->sm_count * kv.blocks_per_sm * ctx->k1_grid_mult;
+        kv.launch(grid, kv.smem, s, body, nvec, head, nhead, tail, ntail, counts);
+        LH_CUDA(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches++;
+        done += consumed;
+    }
+    LH_CUDA(ctx, cudaEventRecord(ctx->ev_t1, s));
+    ctx->timing_valid = true;
+    ctx->stats.samples += n;
+    return after_write(ctx, b, s);
+}
+
+template <typename IdT, typename ValT>
+lh_status launch_keyed(lh_ctx *ctx, const IdT *d_ids, const ValT *d_vals, size_t n, cudaStream_t s) {
+    const int b = ctx->active;
+    lh_status st = before_write(ctx, b, s);
+    if (st != LH_OK) return st;
+    LH_CUDA(ctx, cudaEventRecord(ctx->ev_t0, s));
+    if (n) {
+        constexpr int T = 256, U = 4;
+        int grid = grid_1d(ctx, n, T, U, ctx->keyed_blocks_per_sm);
+        k_ingest_keyed<IdT, ValT, T, U><<<grid, T, 0, s>>>(d_ids, d_vals, n, ctx->buf[b].d_buckets, ctx->H, ctx->d_dropped);
+        LH_CUDA(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches++;
+    }
+    LH_CUDA(ctx, cudaEventRecord(ctx->ev_t1, s));
+    ctx->timing_valid = true;
+    ctx->stats.samples += n;
+    return after_write(ctx, b, s);
+}
+
+template <typename IdT>
+lh_status launch_counter(lh_ctx *ctx, const IdT *d_ids, const uint64_t *d_amounts, size_t n, cudaStream_t s) {
+    const int b = ctx->active;
+    lh_status st = before_write(ctx, b, s);
+    if (st != LH_OK) return st;
+    LH_CUDA(ctx, cudaEventRecord(ctx->ev_t0, s));
+    if (n) {
+        constexpr int T = 256;
+        int grid = grid_1d(ctx, n, T, 4, 8);
+        k_counter_add<IdT, T><<<grid, T, 0, s>>>(d_ids, reinterpret_cast<const unsigned long long *>(d_amounts), n,
+                                                 ctx->buf[b].d_counters, ctx->C, ctx->d_dropped);
+        LH_CUDA(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches++;
+    }
+    LH_CUDA(ctx, cudaEventRecord(ctx->ev_t1, s));
+    ctx->timing_valid = true;
+    ctx->stats.counter_ops += n;
+    return after_write(ctx, b, s);
+}
+
+// ---- staging ring (locked) ----
+lh_status slot_wait_free(lh_ctx *ctx, int *out) {
+    // prefer a free slot; otherwise wait for the oldest in-flight one
+    int best = -1;
+    for (size_t i = 0; i < ctx->slots.size(); i++)
+        if (ctx->slots[i].state == SLOT_FREE) { *out = (int)i; return LH_OK; }
+    for (size_t i = 0; i < ctx->slots.size(); i++)
+        if (ctx->slots[i].state == SLOT_INFLIGHT && (best < 0 || ctx->slots[i].seq < ctx->slots[best].seq)) best = (int)i;
+    if (best < 0) return fail(ctx, LH_ERR_STATE, "every staging slot is acquired and none is in flight");
+    LH_CUDA(ctx, cudaEventSynchronize(ctx->slots[best].done));
+    ctx->slots[best].state = SLOT_FREE;
+    *out = best;
+    return LH_OK;
+}
+
+lh_status ensure_host_scratch(lh_ctx *ctx, size_t bytes) {
+    if (ctx->h_scratch_bytes >= bytes) return LH_OK;
+    if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+    ctx->h_scratch = nullptr; ctx->h_scratch_bytes = 0;
+    LH_CUDA(ctx, cudaMallocHost(&ctx->h_scratch, bytes));
+    ctx->h_scratch_bytes = bytes;
+    return LH_OK;
+}
+
+bool is_pinned_or_managed(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+// =========================================================== lifecycle
+extern "C" uint32_t lh_abi_version(void) { return LH_ABI_VERSION; }
+
+extern "C" const char *lh_strerror(lh_status st) {
+    switch (st) {
+    case LH_OK: return "ok";
+    case LH_ERR_INVALID: return "invalid argument";
+    case LH_ERR_CUDA: return "CUDA runtime error";
+    case LH_ERR_NOMEM: return "out of memory";
+    case LH_ERR_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
+    case LH_ERR_STATE: return "call out of order";
+    case LH_ERR_RANGE: return "id or size out of range";
+    default: return "unknown status";
+    }
+}
+
+extern "C" const char *lh_last_error(const lh_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+extern "C" lh_status lh_create(const lh_config *cfg, lh_ctx **out) {
+    if (!cfg || !out || cfg->struct_size != sizeof(lh_config) || cfg->max_histograms == 0 || cfg->max_counters == 0)
+        return LH_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return LH_ERR_NO_DEVICE; }
+    if (cfg->device < 0 || cfg->device >= ndev) return LH_ERR_NO_DEVICE;
+    lh_ctx *ctx = new (std::nothrow) lh_ctx();
+    if (!ctx) return LH_ERR_NOMEM;
+    ctx->cfg = *cfg;
+    ctx->device = cfg->device;
+    ctx->H = cfg->max_histograms;
+    ctx->C = cfg->max_counters;
+    ctx->staging_bytes = cfg->staging_bytes ? (size_t)cfg->staging_bytes : ((size_t)32 << 20);
+    ctx->staging_bytes = (ctx->staging_bytes + 255) & ~(size_t)255;
+    const uint32_t nslots = cfg->staging_slots ? cfg->staging_slots : 3;
+
+#define LH_CREATE_CUDA(call)                                                            \
+    do {                                                                                \
+        cudaError_t _e = (call);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            fprintf(stderr, "loghisto_b200: lh_create: %s failed: %s\n", #call, cudaGetErrorString(_e)); \
+            lh_destroy(ctx);                                                            \
+            return _e == cudaErrorMemoryAllocation ? LH_ERR_NOMEM : LH_ERR_CUDA;        \
+        }                                                                               \
+    } while (0)
+
+    LH_CREATE_CUDA(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    LH_CREATE_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+    if (prop.major < 10) {
+        fprintf(stderr, "loghisto_b200: device %d is sm_%d%d; this library is built for sm_100a only\n", ctx->device, prop.major, prop.minor);
+        lh_destroy(ctx);
+        return LH_ERR_NO_DEVICE;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    LH_CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->ingest_stream, cudaStreamNonBlocking));
+    LH_CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->snap_stream, cudaStreamNonBlocking));
+    LH_CREATE_CUDA(cudaEventCreate(&ctx->ev_t0));
+    LH_CREATE_CUDA(cudaEventCreate(&ctx->ev_t1));
+
+    const size_t bucket_bytes = (size_t)ctx->H * 65536u * 8u, counter_bytes = (size_t)ctx->C * 8u;
+    for (int b = 0; b < 2; b++) {
+        LH_CREATE_CUDA(cudaMalloc(&ctx->buf[b].d_buckets, bucket_bytes));
+        LH_CREATE_CUDA(cudaMalloc(&ctx->buf[b].d_counters, counter_bytes));
+        LH_CREATE_CUDA(cudaMemsetAsync(ctx->buf[b].d_buckets, 0, bucket_bytes, ctx->snap_stream));
+        LH_CREATE_CUDA(cudaMemsetAsync(ctx->buf[b].d_counters, 0, counter_bytes, ctx->snap_stream));
+        LH_CREATE_CUDA(cudaEventCreateWithFlags(&ctx->buf[b].cleared, cudaEventDisableTiming));
+        LH_CREATE_CUDA(cudaEventRecord(ctx->buf[b].cleared, ctx->snap_stream));
+    }
+    LH_CREATE_CUDA(cudaMalloc(&ctx->d_decomp, 65536 * sizeof(double)));
+    k_fill_decompress<<<65536 / 256, 256, 0, ctx->snap_stream>>>(ctx->d_decomp);
+    LH_CREATE_CUDA(cudaGetLastError());
+    LH_CREATE_CUDA(cudaMalloc(&ctx->d_dropped, 8));
+    LH_CREATE_CUDA(cudaMemsetAsync(ctx->d_dropped, 0, 8, ctx->snap_stream));
+    LH_CREATE_CUDA(cudaMalloc(&ctx->d_ps, LH_MAX_PERCENTILES * sizeof(double)));
+    LH_CREATE_CUDA(cudaMalloc(&ctx->d_r_count, (size_t)ctx->H * 8));
+    LH_CREATE_CUDA(cudaMalloc(&ctx->d_r_sum, (size_t)ctx->H * 8));
+    LH_CREATE_CUDA(cudaMalloc(&ctx->d_r_avg, (size_t)ctx->H * 8));
+    LH_CREATE_CUDA(cudaMalloc(&ctx->d_r_pkeys, (size_t)ctx->H * LH_MAX_PERCENTILES * 4));
+    LH_CREATE_CUDA(cudaMalloc(&ctx->d_r_pvals, (size_t)ctx->H * LH_MAX_PERCENTILES * 8));
+    LH_CREATE_CUDA(cudaMalloc(&ctx->d_nnz, (size_t)ctx->H * 4));
+    LH_CREATE_CUDA(cudaMalloc(&ctx->d_offsets, ((size_t)ctx->H + 1) * 4));
+    LH_CREATE_CUDA(cudaMallocHost(&ctx->h_offsets, ((size_t)ctx->H + 1) * 4));
+    LH_CREATE_CUDA(cudaMallocHost(&ctx->h_counter_deltas, counter_bytes));
+
+    ctx->slots.resize(nslots);
+    for (auto &sl : ctx->slots) {
+        LH_CREATE_CUDA(cudaMallocHost(&sl.h, ctx->staging_bytes));
+        LH_CREATE_CUDA(cudaMalloc(&sl.d, ctx->staging_bytes));
+        LH_CREATE_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    }
+
+    for (int i = 0; i < kNumK1Variants; i++) {
+        ctx->k1[i] = g_k1_variants[i];
+        LH_CREATE_CUDA(cudaFuncSetAttribute(ctx->k1[i].func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->k1[i].smem));
+        int nb = 0;
+        LH_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ctx->k1[i].func, ctx->k1[i].threads, ctx->k1[i].smem));
+        ctx->k1[i].blocks_per_sm = std::max(nb, 1);
+    }
+    LH_CREATE_CUDA(cudaStreamSynchronize(ctx->snap_stream));
+#undef LH_CREATE_CUDA
+    *out = ctx;
+    return LH_OK;
+}
+
+extern "C" lh_status lh_destroy(lh_ctx *ctx) {
+    if (!ctx) return LH_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int b = 0; b < 2; b++) {
+        cudaFree(ctx->buf[b].d_buckets); cudaFree(ctx->buf[b].d_counters);
+        if (ctx->buf[b].cleared) cudaEventDestroy(ctx->buf[b].cleared);
+        for (auto &w : ctx->buf[b].writers) cudaEventDestroy(w.ev);
+    }
+    cudaFree(ctx->d_decomp); cudaFree(ctx->d_dropped); cudaFree(ctx->d_ps);
+    cudaFree(ctx->d_r_count); cudaFree(ctx->d_r_sum); cudaFree(ctx->d_r_avg);
+    cudaFree(ctx->d_r_pkeys); cudaFree(ctx->d_r_pvals); cudaFree(ctx->d_nnz); cudaFree(ctx->d_offsets);
+    cudaFree(ctx->d_x_keys); cudaFree(ctx->d_x_counts);
+    if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+    if (ctx->h_offsets) cudaFreeHost(ctx->h_offsets);
+    if (ctx->h_x_keys) cudaFreeHost(ctx->h_x_keys);
+    if (ctx->h_x_counts) cudaFreeHost(ctx->h_x_counts);
+    if (ctx->h_counter_deltas) cudaFreeHost(ctx->h_counter_deltas);
+    for (auto &sl : ctx->slots) {
+        if (sl.h) cudaFreeHost(sl.h);
+        cudaFree(sl.d);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
+    if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+    if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+    if (ctx->ingest_stream) cudaStreamDestroy(ctx->ingest_stream);
+    if (ctx->snap_stream) cudaStreamDestroy(ctx->snap_stream);
+    cudaGetLastError();
+    delete ctx;
+    return LH_OK;
+}
+
+// =========================================================== ingest (device)
+#define LH_ENTER(ctx)                                   \
+    if (!(ctx)) return LH_ERR_INVALID;                  \
+    std::lock_guard<std::mutex> _lk((ctx)->mu);         \
+    LH_CUDA((ctx), cudaSetDevice((ctx)->device))
+
+extern "C" lh_status lh_ingest_f64(lh_ctx *ctx, uint32_t hid, const double *d_values, size_t n, void *stream) {
+    LH_ENTER(ctx);
+    if (n && !d_values) return fail(ctx, LH_ERR_INVALID, "d_values is NULL");
+    if (n == 0) return LH_OK;
+    return launch_single(ctx, hid, d_values, n, pick_stream(ctx, stream));
+}
+extern "C" lh_status lh_ingest_keyed_f64_u16(lh_ctx *ctx, const uint16_t *d_ids, const double *d_values, size_t n, void *stream) {
+    LH_ENTER(ctx);
+    if (n && (!d_ids || !d_values)) return fail(ctx, LH_ERR_INVALID, "NULL input");
+    return launch_keyed<unsigned short, double>(ctx, d_ids, d_values, n, pick_stream(ctx, stream));
+}
+extern "C" lh_status lh_ingest_keyed_f64_u32(lh_ctx *ctx, const uint32_t *d_ids, const double *d_values, size_t n, void *stream) {
+    LH_ENTER(ctx);
+    if (n && (!d_ids || !d_values)) return fail(ctx, LH_ERR_INVALID, "NULL input");
+    return launch_keyed<unsigned int, double>(ctx, d_ids, d_values, n, pick_stream(ctx, stream));
+}
+extern "C" lh_status lh_ingest_keyed_i64ns_u16(lh_ctx *ctx, const uint16_t *d_ids, const int64_t *d_nanos, size_t n, void *stream) {
+    LH_ENTER(ctx);
+    if (n && (!d_ids || !d_nanos)) return fail(ctx, LH_ERR_INVALID, "NULL input");
+    return launch_keyed<unsigned short, long long>(ctx, d_ids, reinterpret_cast<const long long *>(d_nanos), n, pick_stream(ctx, stream));
+}
+extern "C" lh_status lh_counter_add_u16(lh_ctx *ctx, const uint16_t *d_ids, const uint64_t *d_amounts, size_t n, void *stream) {
+    LH_ENTER(ctx);
+    if (n && (!d_ids || !d_amounts)) return fail(ctx, LH_ERR_INVALID, "NULL input");
+    return launch_counter<unsigned short>(ctx, d_ids, d_amounts, n, pick_stream(ctx, stream));
+}
+extern "C" lh_status lh_counter_add_u32(lh_ctx *ctx, const uint32_t *d_ids, const uint64_t *d_amounts, size_t n, void *stream) {
+    LH_ENTER(ctx);
+    if (n && (!d_ids || !d_amounts)) return fail(ctx, LH_ERR_INVALID, "NULL input");
+    return launch_counter<unsigned int>(ctx, d_ids, d_amounts, n, pick_stream(ctx, stream));
+}
+
+// =========================================================== ingest (host)
+// Chunks of staging_bytes go through the slot ring: (memcpy into pinned if the
+// source is pageable) -> async H2D -> kernel, all on the ingest stream.
+namespace {
+enum HostKind { HK_SINGLE, HK_KEYED_U16, HK_COUNTER_U16 };
+
+lh_status ingest_host(lh_ctx *ctx, HostKind kind, uint32_t hid, const void *h_a /* 8-byte items */,
+                      const uint16_t *h_ids, size_t n) {
+    const bool pinned = is_pinned_or_managed(h_a) && (!h_ids || is_pinned_or_managed(h_ids));
+    const size_t item = (kind == HK_SINGLE) ? 8 : 10;
+    size_t per = ctx->staging_bytes / item;
+    per &= ~(size_t)15;   // keeps the ids region 16-byte aligned
+    if (per == 0) return fail(ctx, LH_ERR_INVALID, "staging_bytes too small");
+    cudaStream_t s = ctx->ingest_stream;
+    size_t done = 0;
+    while (done < n) {
+        size_t m = std::min(per, n - done);
+        int si;
+        lh_status st = slot_wait_free(ctx, &si);
+        if (st != LH_OK) return st;
+        Slot &sl = ctx->slots[si];
+        const char *src_a = (const char *)h_a + done * 8;
+        char *d_a = (char *)sl.d;
+        char *d_i = (char *)sl.d + per * 8;
+        if (pinned) {
+            LH_CUDA(ctx, cudaMemcpyAsync(d_a, src_a, m * 8, cudaMemcpyHostToDevice, s));
+            if (h_ids) LH_CUDA(ctx, cudaMemcpyAsync(d_i, h_ids + done, m * 2, cudaMemcpyHostToDevice, s));
+        } else {
+            memcpy(sl.h, src_a, m * 8);
+            LH_CUDA(ctx, cudaMemcpyAsync(d_a, sl.h, m * 8, cudaMemcpyHostToDevice, s));
+            if (h_ids) {
+                memcpy((char *)sl.h + per * 8, h_ids + done, m * 2);
+                LH_CUDA(ctx, cudaMemcpyAsync(d_i, (char *)sl.h + per * 8, m * 2, cudaMemcpyHostToDevice, s));
+            }
+        }
+        ctx->stats.h2d_bytes += m * item;
+        if (kind == HK_SINGLE) st = launch_single(ctx, hid, (const double *)d_a, m, s);
+        else if (kind == HK_KEYED_U16) st = launch_keyed<unsigned short, double>(ctx, (const unsigned short *)d_i, (const double *)d_a, m, s);
+        else st = launch_counter<unsigned short>(ctx, (const unsigned short *)d_i, (const uint64_t *)d_a, m, s);
+        if (st != LH_OK) return st;
+        LH_CUDA(ctx, cudaEventRecord(sl.done, s));
+        sl.state = SLOT_INFLIGHT;
+        sl.seq = ++ctx->slot_seq;
+        done += m;
+    }
+    if (pinned) {
+        // the caller may reuse its buffers on return: the async copies must have read them
+        LH_CUDA(ctx, cudaStreamSynchronize(s));
+        for (auto &sl : ctx->slots) if (sl.state == SLOT_INFLIGHT) sl.state = SLOT_FREE;
+    }
+    return LH_OK;
+}
+}  // namespace
+
+extern "C" lh_status lh_ingest_f64_host(lh_ctx *ctx, uint32_t hid, const double *h_values, size_t n) {
+    LH_ENTER(ctx);
+    if (n && !h_values) return fail(ctx, LH_ERR_INVALID, "h_values is NULL");
+    if (hid >= ctx->H) return fail(ctx, LH_ERR_RANGE, "histogram_id >= max_histograms");
+    return ingest_host(ctx, HK_SINGLE, hid, h_values, nullptr, n);
+}
+extern "C" lh_status lh_ingest_keyed_f64_u16_host(lh_ctx *ctx, const uint16_t *h_ids, const double *h_values, size_t n) {
+    LH_ENTER(ctx);
+    if (n && (!h_ids || !h_values)) return fail(ctx, LH_ERR_INVALID, "NULL input");
+    return ingest_host(ctx, HK_KEYED_U16, 0, h_values, h_ids, n);
+}
+extern "C" lh_status lh_counter_add_u16_host(lh_ctx *ctx, const uint16_t *h_ids, const uint64_t *h_amounts, size_t n) {
+    LH_ENTER(ctx);
+    if (n && (!h_ids || !h_amounts)) return fail(ctx, LH_ERR_INVALID, "NULL input");
+    return ingest_host(ctx, HK_COUNTER_U16, 0, h_amounts, h_ids, n);
+}
+
+// =========================================================== staging ring
+extern "C" lh_status lh_staging_acquire(lh_ctx *ctx, lh_staging *out) {
+    LH_ENTER(ctx);
+    if (!out) return fail(ctx, LH_ERR_INVALID, "out is NULL");
+    int si;
+    lh_status st = slot_wait_free(ctx, &si);
+    if (st != LH_OK) return st;
+    ctx->slots[si].state = SLOT_ACQUIRED;
+    out->host = ctx->slots[si].h;
+    out->bytes = ctx->staging_bytes;
+    out->slot = (uint32_t)si;
+    out->reserved = 0;
+    return LH_OK;
+}
+
+namespace {
+lh_status staging_commit(lh_ctx *ctx, const lh_staging *sg, HostKind kind, uint32_t hid, size_t n, uint64_t ids_offset) {
+    if (!sg || sg->slot >= ctx->slots.size()) return fail(ctx, LH_ERR_INVALID, "bad staging handle");
+    Slot &sl = ctx->slots[sg->slot];
+    if (sl.state != SLOT_ACQUIRED) return fail(ctx, LH_ERR_STATE, "staging slot was not acquired");
+    const size_t item_bytes = n * 8;
+    if (kind == HK_SINGLE) {
+        if (item_bytes > ctx->staging_bytes) return fail(ctx, LH_ERR_RANGE, "n exceeds the staging slot");
+    } else {
+        if ((ids_offset & 15u) || ids_offset < item_bytes || ids_offset + n * 2 > ctx->staging_bytes)
+            return fail(ctx, LH_ERR_RANGE, "ids_offset / n do not fit the staging slot");
+    }
+    cudaStream_t s = ctx->ingest_stream;
+    lh_status st = LH_OK;
+    if (n) {
+        LH_CUDA(ctx, cudaMemcpyAsync(sl.d, sl.h, item_bytes, cudaMemcpyHostToDevice, s));
+        ctx->stats.h2d_bytes += item_bytes;
+        if (kind != HK_SINGLE) {
+            LH_CUDA(ctx, cudaMemcpyAsync((char *)sl.d + ids_offset, (char *)sl.h + ids_offset, n * 2, cudaMemcpyHostToDevice, s));
+            ctx->stats.h2d_bytes += n * 2;
+        }
+        if (kind == HK_SINGLE) st = launch_single(ctx, hid, (const double *)sl.d, n, s);
+        else if (kind == HK_KEYED_U16) st = launch_keyed<unsigned short, double>(ctx, (const unsigned short *)((char *)sl.d + ids_offset), (const double *)sl.d, n, s);
+        else st = launch_counter<unsigned short>(ctx, (const unsigned short *)((char *)sl.d + ids_offset), (const uint64_t *)sl.d, n, s);
+    }
+    LH_CUDA(ctx, cudaEventRecord(sl.done, s));
+    sl.state = SLOT_INFLIGHT;
+    sl.seq = ++ctx->slot_seq;
+    return st;
+}
+}  // namespace
+
+extern "C" lh_status lh_staging_commit_f64(lh_ctx *ctx, const lh_staging *s, uint32_t hid, size_t n) {
+    LH_ENTER(ctx);
+    if (hid >= ctx->H) return fail(ctx, LH_ERR_RANGE, "histogram_id >= max_histograms");
+    return staging_commit(ctx, s, HK_SINGLE, hid, n, 0);
+}
+extern "C" lh_status lh_staging_commit_keyed_f64_u16(lh_ctx *ctx, const lh_staging *s, size_t n, uint64_t ids_offset) {
+    LH_ENTER(ctx);
+    return staging_commit(ctx, s, HK_KEYED_U16, 0, n, ids_offset);
+}
+extern "C" lh_status lh_staging_commit_counter_u16(lh_ctx *ctx, const lh_staging *s, size_t n, uint64_t ids_offset) {
+    LH_ENTER(ctx);
+    return staging_commit(ctx, s, HK_COUNTER_U16, 0, n, ids_offset);
+}
+extern "C" lh_status lh_staging_abandon(lh_ctx *ctx, const lh_staging *s) {
+    LH_ENTER(ctx);
+    if (!s || s->slot >= ctx->slots.size()) return fail(ctx, LH_ERR_INVALID, "bad staging handle");
+    if (ctx->slots[s->slot].state != SLOT_ACQUIRED) return fail(ctx, LH_ERR_STATE, "staging slot was not acquired");
+    ctx->slots[s->slot].state = SLOT_FREE;
+    return LH_OK;
+}
+
+// =========================================================== snapshot
+extern "C" lh_status lh_snapshot_begin(lh_ctx *ctx) {
+    LH_ENTER(ctx);
+    if (ctx->frozen) return fail(ctx, LH_ERR_STATE, "previous snapshot not ended");
+    const int f = ctx->active;
+    // order the snapshot stream after every ingest launch that wrote the buffer being frozen
+    for (auto &w : ctx->buf[f].writers) LH_CUDA(ctx, cudaStreamWaitEvent(ctx->snap_stream, w.ev, 0));
+    ctx->active ^= 1;
+    ctx->frozen = true;
+    ctx->nnz_valid = false;
+    ctx->stats.snapshots++;
+    return LH_OK;
+}
+
+extern "C" lh_status lh_snapshot_device(lh_ctx *ctx, lh_device_view *out) {
+    LH_ENTER(ctx);
+    if (!out) return fail(ctx, LH_ERR_INVALID, "out is NULL");
+    if (!ctx->frozen) return fail(ctx, LH_ERR_STATE, "no snapshot in progress");
+    const int f = ctx->active ^ 1;
+    out->d_buckets = reinterpret_cast<uint64_t *>(ctx->buf[f].d_buckets);
+    out->d_counters = reinterpret_cast<uint64_t *>(ctx->buf[f].d_counters);
+    out->n_bucket_words = (uint64_t)ctx->H * 65536u;
+    out->n_counter_words = ctx->C;
+    out->stream = ctx->snap_stream;
+    return LH_OK;
+}
+
+namespace {
+lh_status run_reduce(lh_ctx *ctx, const double *ps, uint32_t np) {
+    const int f = ctx->active ^ 1;
+    if (np) LH_CUDA(ctx, cudaMemcpyAsync(ctx->d_ps, ps, np * sizeof(double), cudaMemcpyHostToDevice, ctx->snap_stream));
+    k_reduce<<<ctx->H, K3_THREADS, 0, ctx->snap_stream>>>(ctx->buf[f].d_buckets, ctx->d_decomp, ctx->d_ps, (int)np,
+                                                          ctx->d_r_count, ctx->d_r_sum, ctx->d_r_avg, ctx->d_r_pkeys,
+                                                          ctx->d_r_pvals, ctx->d_nnz);
+    LH_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    ctx->nnz_valid = true;
+    return LH_OK;
+}
+}  // namespace
+
+extern "C" lh_status lh_snapshot_reduce(lh_ctx *ctx, const double *percentiles, uint32_t np, uint64_t *counts,
+                                        double *sums, double *avgs, int32_t *pkeys, double *pvals) {
+    LH_ENTER(ctx);
+    if (!ctx->frozen) return fail(ctx, LH_ERR_STATE, "no snapshot in progress");
+    if (np > LH_MAX_PERCENTILES || (np && !percentiles)) return fail(ctx, LH_ERR_INVALID, "bad percentile array");
+    lh_status st = run_reduce(ctx, percentiles, np);
+    if (st != LH_OK) return st;
+    const size_t H = ctx->H;
+    const size_t bytes = H * 8 * 3 + H * np * 12;
+    st = ensure_host_scratch(ctx, bytes + 64);
+    if (st != LH_OK) return st;
+    char *p = (char *)ctx->h_scratch;
+    unsigned long long *hc = (unsigned long long *)p; p += H * 8;
+    double *hs = (double *)p; p += H * 8;
+    double *ha = (double *)p; p += H * 8;
+    double *hv = (double *)p; p += H * np * 8;
+    int *hk = (int *)p;
+    cudaStream_t s = ctx->snap_stream;
+    LH_CUDA(ctx, cudaMemcpyAsync(hc, ctx->d_r_count, H * 8, cudaMemcpyDeviceToHost, s));
+    LH_CUDA(ctx, cudaMemcpyAsync(hs, ctx->d_r_sum, H * 8, cudaMemcpyDeviceToHost, s));
+    LH_CUDA(ctx, cudaMemcpyAsync(ha, ctx->d_r_avg, H * 8, cudaMemcpyDeviceToHost, s));
+    if (np) {
+        LH_CUDA(ctx, cudaMemcpyAsync(hv, ctx->d_r_pvals, H * np * 8, cudaMemcpyDeviceToHost, s));
+        LH_CUDA(ctx, cudaMemcpyAsync(hk, ctx->d_r_pkeys, H * np * 4, cudaMemcpyDeviceToHost, s));
+    }
+    LH_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->stats.d2h_bytes += bytes;
+    if (counts) memcpy(counts, hc, H * 8);
+    if (sums) memcpy(sums, hs, H * 8);
+    if (avgs) memcpy(avgs, ha, H * 8);
+    if (pvals && np) memcpy(pvals, hv, H * np * 8);
+    if (pkeys && np) memcpy(pkeys, hk, H * np * 4);
+    return LH_OK;
+}
+
+extern "C" lh_status lh_snapshot_export(lh_ctx *ctx, lh_sparse *out) {
+    LH_ENTER(ctx);
+    if (!out) return fail(ctx, LH_ERR_INVALID, "out is NULL");
+    if (!ctx->frozen) return fail(ctx, LH_ERR_STATE, "no snapshot in progress");
+    const int f = ctx->active ^ 1;
+    cudaStream_t s = ctx->snap_stream;
+    if (!ctx->nnz_valid) { lh_status st = run_reduce(ctx, nullptr, 0); if (st != LH_OK) return st; }
+    k_scan_nnz<<<1, 1024, 0, s>>>(ctx->d_nnz, ctx->H, ctx->d_offsets);
+    LH_CUDA(ctx, cudaGetLastError());
+    LH_CUDA(ctx, cudaMemcpyAsync(ctx->h_offsets, ctx->d_offsets, ((size_t)ctx->H + 1) * 4, cudaMemcpyDeviceToHost, s));
+    LH_CUDA(ctx, cudaMemcpyAsync(ctx->h_counter_deltas, ctx->buf[f].d_counters, (size_t)ctx->C * 8, cudaMemcpyDeviceToHost, s));
+    LH_CUDA(ctx, cudaStreamSynchronize(s));
+    const size_t total = ctx->h_offsets[ctx->H];
+    if (total > ctx->x_cap) {
+        size_t cap = std::max<size_t>(total, 4096) * 2;
+        cudaFree(ctx->d_x_keys); cudaFree(ctx->d_x_counts);
+        if (ctx->h_x_keys) cudaFreeHost(ctx->h_x_keys);
+        if (ctx->h_x_counts) cudaFreeHost(ctx->h_x_counts);
+        ctx->d_x_keys = nullptr; ctx->d_x_counts = nullptr; ctx->h_x_keys = nullptr; ctx->h_x_counts = nullptr; ctx->x_cap = 0;
+        LH_CUDA(ctx, cudaMalloc(&ctx->d_x_keys, cap * 2));
+        LH_CUDA(ctx, cudaMalloc(&ctx->d_x_counts, cap * 8));
+        LH_CUDA(ctx, cudaMallocHost(&ctx->h_x_keys, cap * 2));
+        LH_CUDA(ctx, cudaMallocHost(&ctx->h_x_counts, cap * 8));
+        ctx->x_cap = cap;
+    }
+    if (total) {
+        k_export<<<ctx->H, K3_THREADS, 0, s>>>(ctx->buf[f].d_buckets, ctx->d_offsets, ctx->d_x_keys, ctx->d_x_counts);
+        LH_CUDA(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches += 2;
+        LH_CUDA(ctx, cudaMemcpyAsync(ctx->h_x_keys, ctx->d_x_keys, total * 2, cudaMemcpyDeviceToHost, s));
+        LH_CUDA(ctx, cudaMemcpyAsync(ctx->h_x_counts, ctx->d_x_counts, total * 8, cudaMemcpyDeviceToHost, s));
+        LH_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    ctx->stats.d2h_bytes += total * 10 + ((size_t)ctx->H + 1) * 4 + (size_t)ctx->C * 8;
+    out->offsets = ctx->h_offsets;
+    out->keys = ctx->h_x_keys;
+    out->counts = reinterpret_cast<const uint64_t *>(ctx->h_x_counts);
+    out->counter_deltas = reinterpret_cast<const uint64_t *>(ctx->h_counter_deltas);
+    out->total_entries = total;
+    return LH_OK;
+}
+
+extern "C" lh_status lh_snapshot_copy_histogram(lh_ctx *ctx, uint32_t hid, uint64_t *h_out) {
+    LH_ENTER(ctx);
+    if (!ctx->frozen) return fail(ctx, LH_ERR_STATE, "no snapshot in progress");
+    if (hid >= ctx->H) return fail(ctx, LH_ERR_RANGE, "histogram_id >= max_histograms");
+    if (!h_out) return fail(ctx, LH_ERR_INVALID, "h_out is NULL");
+    const int f = ctx->active ^ 1;
+    LH_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->buf[f].d_buckets + (size_t)hid * 65536u, 65536 * 8, cudaMemcpyDeviceToHost, ctx->snap_stream));
+    LH_CUDA(ctx, cudaStreamSynchronize(ctx->snap_stream));
+    ctx->stats.d2h_bytes += 65536 * 8;
+    return LH_OK;
+}
+
+extern "C" lh_status lh_snapshot_end(lh_ctx *ctx) {
+    LH_ENTER(ctx);
+    if (!ctx->frozen) return fail(ctx, LH_ERR_STATE, "no snapshot in progress");
+    const int f = ctx->active ^ 1;
+    LH_CUDA(ctx, cudaMemsetAsync(ctx->buf[f].d_buckets, 0, (size_t)ctx->H * 65536u * 8u, ctx->snap_stream));
+    LH_CUDA(ctx, cudaMemsetAsync(ctx->buf[f].d_counters, 0, (size_t)ctx->C * 8u, ctx->snap_stream));
+    LH_CUDA(ctx, cudaEventRecord(ctx->buf[f].cleared, ctx->snap_stream));
+    ctx->frozen = false;
+    return LH_OK;
+}
+
+// =========================================================== probes
+extern "C" lh_status lh_compress_f64(lh_ctx *ctx, const double *d_values, size_t n, int16_t *d_out, int mode, void *stream) {
+    LH_ENTER(ctx);
+    if (n && (!d_values || !d_out)) return fail(ctx, LH_ERR_INVALID, "NULL input");
+    if (!n) return LH_OK;
+    cudaStream_t s = pick_stream(ctx, stream);
+    k_compress_probe<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_values, n, d_out, mode);
+    LH_CUDA(ctx, cudaGetLastError());
+    return LH_OK;
+}
+
+extern "C" lh_status lh_decompress_table(lh_ctx *ctx, double *h_out) {
+    LH_ENTER(ctx);
+    if (!h_out) return fail(ctx, LH_ERR_INVALID, "h_out is NULL");
+    LH_CUDA(ctx, cudaMemcpy(h_out, ctx->d_decomp, 65536 * sizeof(double), cudaMemcpyDeviceToHost));
+    return LH_OK;
+}
+
+extern "C" lh_status lh_fastpath_margin(lh_ctx *ctx, const double *d_values, size_t n, double *h_max_err, uint64_t *h_n_slow, void *stream) {
+    LH_ENTER(ctx);
+    if (n && !d_values) return fail(ctx, LH_ERR_INVALID, "NULL input");
+    cudaStream_t s = pick_stream(ctx, stream);
+    unsigned long long *d = nullptr;
+    LH_CUDA(ctx, cudaMalloc(&d, 16));
+    LH_CUDA(ctx, cudaMemsetAsync(d, 0, 16, s));
+    if (n) k_fastpath_margin<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_values, n, d, d + 1);
+    unsigned long long h[2];
+    cudaError_t e = cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, LH_ERR_CUDA, "lh_fastpath_margin", e);
+    if (h_max_err) memcpy(h_max_err, &h[0], 8);
+    if (h_n_slow) *h_n_slow = h[1];
+    return LH_OK;
+}
+
+// =========================================================== streams
+extern "C" lh_status lh_gen_stream_f64(lh_ctx *ctx, int kind, uint64_t seed, uint64_t start, size_t n, double *d_out, void *stream) {
+    LH_ENTER(ctx);
+    if (n && !d_out) return fail(ctx, LH_ERR_INVALID, "d_out is NULL");
+    if (!n) return LH_OK;
+    k_gen_stream<<<ctx->sm_count * 8, 256, 0, pick_stream(ctx, stream)>>>(kind, seed, start, n, d_out);
+    LH_CUDA(ctx, cudaGetLastError());
+    return LH_OK;
+}
+extern "C" lh_status lh_gen_ids_u16(lh_ctx *ctx, int kind, uint64_t seed, uint64_t start, size_t n, uint32_t n_ids, uint16_t *d_out, void *stream) {
+    LH_ENTER(ctx);
+    if (n && !d_out) return fail(ctx, LH_ERR_INVALID, "d_out is NULL");
+    if (n_ids == 0 || n_ids > 65536) return fail(ctx, LH_ERR_RANGE, "n_ids must be in 1..65536");
+    if (!n) return LH_OK;
+    k_gen_ids_u16<<<ctx->sm_count * 8, 256, 0, pick_stream(ctx, stream)>>>(kind, seed, start, n, n_ids, d_out);
+    LH_CUDA(ctx, cudaGetLastError());
+    return LH_OK;
+}
+
+// =========================================================== misc
+extern "C" lh_status lh_get_stats(lh_ctx *ctx, lh_stats *out) {
+    LH_ENTER(ctx);
+    if (!out) return fail(ctx, LH_ERR_INVALID, "out is NULL");
+    unsigned long long dropped = 0;
+    LH_CUDA(ctx, cudaMemcpy(&dropped, ctx->d_dropped, 8, cudaMemcpyDeviceToHost));
+    ctx->stats.dropped = dropped;
+    *out = ctx->stats;
+    return LH_OK;
+}
+extern "C" lh_status lh_sync(lh_ctx *ctx) {
+    LH_ENTER(ctx);
+    LH_CUDA(ctx, cudaDeviceSynchronize());
+    for (auto &sl : ctx->slots) if (sl.state == SLOT_INFLIGHT) sl.state = SLOT_FREE;
+    return LH_OK;
+}
+extern "C" void *lh_ingest_stream(lh_ctx *ctx) { return ctx ? (void *)ctx->ingest_stream : nullptr; }
+
+extern "C" lh_status lh_device_alloc(lh_ctx *ctx, size_t bytes, void **d_out) {
+    LH_ENTER(ctx);
+    if (!d_out) return fail(ctx, LH_ERR_INVALID, "d_out is NULL");
+    cudaError_t e = cudaMalloc(d_out, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(ctx, e == cudaErrorMemoryAllocation ? LH_ERR_NOMEM : LH_ERR_CUDA, "cudaMalloc", e);
+    return LH_OK;
+}
+extern "C" lh_status lh_device_free(lh_ctx *ctx, void *d_ptr) {
+    LH_ENTER(ctx);
+    LH_CUDA(ctx, cudaFree(d_ptr));
+    return LH_OK;
+}
+extern "C" lh_status lh_host_alloc_pinned(lh_ctx *ctx, size_t bytes, void **h_out) {
+    LH_ENTER(ctx);
+    if (!h_out) return fail(ctx, LH_ERR_INVALID, "h_out is NULL");
+    cudaError_t e = cudaMallocHost(h_out, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(ctx, e == cudaErrorMemoryAllocation ? LH_ERR_NOMEM : LH_ERR_CUDA, "cudaMallocHost", e);
+    return LH_OK;
+}
+extern "C" lh_status lh_host_free_pinned(lh_ctx *ctx, void *h_ptr) {
+    LH_ENTER(ctx);
+    LH_CUDA(ctx, cudaFreeHost(h_ptr));
+    return LH_OK;
+}
+extern "C" lh_status lh_memcpy_h2d(lh_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
+    LH_ENTER(ctx);
+    LH_CUDA(ctx, cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice));
+    return LH_OK;
+}
+extern "C" lh_status lh_memcpy_d2h(lh_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
+    LH_ENTER(ctx);
+    LH_CUDA(ctx, cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return LH_OK;
+}
+
+extern "C" lh_status lh_tune(lh_ctx *ctx, const char *key, int64_t value) {
+    LH_ENTER(ctx);
+    if (!key) return fail(ctx, LH_ERR_INVALID, "key is NULL");
+    if (!strcmp(key, "k1")) {
+        if (value < 0 || value >= kNumK1Variants) return fail(ctx, LH_ERR_RANGE, "unknown k1 variant");
+        ctx->k1_variant = (int)value;
+        return LH_OK;
+    }
+    if (!strcmp(key, "k1_grid_mult")) {
+        if (value < 1 || value > 64) return fail(ctx, LH_ERR_RANGE, "k1_grid_mult out of range");
+        ctx->k1_grid_mult = (int)value;
+        return LH_OK;
+    }
+    if (!strcmp(key, "keyed_blocks_per_sm")) {
+        if (value < 1 || value > 32) return fail(ctx, LH_ERR_RANGE, "keyed_blocks_per_sm out of range");
+        ctx->keyed_blocks_per_sm = (int)value;
+        return LH_OK;
+    }
+    return fail(ctx, LH_ERR_INVALID, "unknown tuning key");
+}
+
+extern "C" int32_t lh_k1_variant_count(void) { return kNumK1Variants; }
+extern "C" const char *lh_k1_variant_name(lh_ctx *ctx, int32_t i) {
+    if (!ctx || i < 0 || i >= kNumK1Variants) return "";
+    return ctx->k1[i].name;
+}
+
+extern "C" lh_status lh_last_kernel_ms(lh_ctx *ctx, float *ms) {
+    LH_ENTER(ctx);
+    if (!ms) return fail(ctx, LH_ERR_INVALID, "ms is NULL");
+    if (!ctx->timing_valid) return fail(ctx, LH_ERR_STATE, "no ingest kernel has been launched");
+    LH_CUDA(ctx, cudaEventSynchronize(ctx->ev_t1));
+    LH_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev_t0, ctx->ev_t1));
+    return LH_OK;
+}

@@ -1,0 +1,535 @@
+// lh_kernels.cuh -- sm_100a kernels of the loghisto hot path.
+//
+//   K1   ingest_single_*   one histogram, float64 stream -> bucket counts
+//                          (compress + Histogram increment, metrics.go:273-295, 316-322)
+//          _ldg   : vectorised ld.global.nc.v2.f64, software-pipelined registers
+//          _bulk  : cp.async.bulk (TMA 1-D, UBLKCP) into a shared-memory ring
+//                   guarded by mbarriers, one producer warp + N consumer warps
+//        both privatise the histogram in shared memory (uint32 sub-histograms,
+//        shared atomics) and flush once per CTA with one global 64-bit atomic
+//        per non-empty bucket.
+//   K1k  ingest_keyed      (id,value) pairs -> buckets[id][key]   (name dispatch path)
+//   K2   counter_add       (id,amount) pairs -> counters[id]      (metrics.go:251-269)
+//   K3   reduce            per histogram: count, sum, avg, percentiles
+//                          (processHistograms + percentile, metrics.go:336-418)
+//   K4   export            sparse (key,count) lists               (RawMetricSet.Histograms)
+#pragma once
+#include "lh_device.cuh"
+
+namespace lh {
+
+// ---------------------------------------------------------------- helpers
+// Streaming loads: read-once data, keep it out of L1 and first in line for L2 eviction.
+// sm_100 has 256-bit global loads (ld.global.v4.b64 -> LDG.E.256); the L2
+// eviction-priority qualifier is only accepted on those.
+struct f64x4 { double a, b, c, d; };
+__device__ __forceinline__ f64x4 ldg_stream_f64x4(const void *p) {
+    unsigned long long a, b, c, d;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
+                 : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    f64x4 r;
+    r.a = __longlong_as_double((long long)a); r.b = __longlong_as_double((long long)b);
+    r.c = __longlong_as_double((long long)c); r.d = __longlong_as_double((long long)d);
+    return r;
+}
+__device__ __forceinline__ f64x4 ldg_stream_f64x2x2(const void *p) {   // two 128-bit loads (comparison variant)
+    f64x4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.a), "=d"(r.b) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.c), "=d"(r.d) : "l"((const char *)p + 16));
+    return r;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "LH_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra LH_DONE_%=;\n\t"
+        "bra LH_WAIT_%=;\n\t"
+        "LH_DONE_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar,
+                                         uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+// One sample -> shared sub-histogram slot.  Samples outside the window are
+// counted straight into the global array and redirected to a trash slot so
+// the shared atomic below stays unconditional.
+constexpr uint32_t LH_TRASH = LH_SUBHIST;          // slot never flushed
+constexpr uint32_t LH_SUBHIST_ALLOC = LH_SUBHIST + 8;
+
+template <int NS>
+__device__ __forceinline__ void bucket_samples(const double (&v)[NS], uint32_t *hist,
+                                               unsigned long long *__restrict__ counts) {
+    uint32_t idx[NS];
+    bool slow[NS];
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < NS; i++) { fast_candidate(v[i], idx[i], slow[i]); any |= slow[i]; }
+    if (__any_sync(0xFFFFFFFFu, any)) {
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            if (slow[i]) {
+                uint32_t key = exact_key16(v[i]);
+                uint32_t slot = key16_to_slot(key);
+                if (slot == 0xFFFFFFFFu) { atomicAdd(&counts[key], 1ull); slot = LH_TRASH; }
+                idx[i] = slot;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NS; i++) atomicAdd(&hist[idx[i]], 1u);
+}
+
+__device__ __forceinline__ void flush_subhist(const uint32_t *hist, int copies, int tid, int nthreads,
+                                              unsigned long long *__restrict__ counts) {
+    for (int slot = tid; slot < LH_SUBHIST; slot += nthreads) {
+        uint32_t c = 0;
+        for (int k = 0; k < copies; k++) c += hist[k * LH_SUBHIST_ALLOC + slot];
+        if (c) atomicAdd(&counts[slot_to_key16((uint32_t)slot)], (unsigned long long)c);
+    }
+}
+
+// ------------------------------------------------------------------- K1/ldg
+// vals32: 32-byte aligned, nvec 32-byte vectors (4 samples each).  Up to three
+// scalar stragglers on either side (misaligned head, ragged tail) come separately.
+__device__ __forceinline__ void bucket_stragglers(const double *p, int n, unsigned long long *__restrict__ counts) {
+    for (int i = 0; i < n; i++) atomicAdd(&counts[key16_of(p[i])], 1ull);
+}
+
+template <int THREADS, int UNROLL, int COPIES, int MINB, bool WIDE>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_ingest_single_ldg(const double *__restrict__ vals32, size_t nvec, const double *head, int nhead,
+                    const double *tail, int ntail, unsigned long long *__restrict__ counts) {
+    extern __shared__ __align__(16) uint32_t s_hist[];
+    for (int i = threadIdx.x; i < COPIES * (int)LH_SUBHIST_ALLOC; i += THREADS) s_hist[i] = 0;
+    __syncthreads();
+    uint32_t *my = s_hist + ((threadIdx.x >> 5) % COPIES) * LH_SUBHIST_ALLOC;
+    const char *base = reinterpret_cast<const char *>(vals32);
+
+    constexpr size_t TILE = (size_t)THREADS * UNROLL;   // 32-byte vectors per tile
+    const size_t ntiles = nvec / TILE;
+    f64x4 cur[UNROLL], nxt[UNROLL];
+    size_t tile = blockIdx.x;
+    if (tile < ntiles) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const char *p = base + (tile * TILE + (size_t)u * THREADS + threadIdx.x) * 32;
+            cur[u] = WIDE ? ldg_stream_f64x4(p) : ldg_stream_f64x2x2(p);
+        }
+    }
+    while (tile < ntiles) {
+        size_t nt = tile + gridDim.x;
+        if (nt < ntiles) {
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const char *p = base + (nt * TILE + (size_t)u * THREADS + threadIdx.x) * 32;
+                nxt[u] = WIDE ? ldg_stream_f64x4(p) : ldg_stream_f64x2x2(p);
+            }
+        }
+        double v[4 * UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) { v[4 * u] = cur[u].a; v[4 * u + 1] = cur[u].b; v[4 * u + 2] = cur[u].c; v[4 * u + 3] = cur[u].d; }
+        bucket_samples<4 * UNROLL>(v, my, counts);
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) cur[u] = nxt[u];
+        tile = nt;
+    }
+    // partial last tile + stragglers: one CTA, bounds-checked (rare, < TILE vectors)
+    if (blockIdx.x == ntiles % gridDim.x) {
+        for (size_t j = ntiles * TILE * 4 + threadIdx.x; j < nvec * 4; j += THREADS) {
+            uint32_t k0 = key16_of(vals32[j]);
+            uint32_t s0 = key16_to_slot(k0);
+            if (s0 == 0xFFFFFFFFu) atomicAdd(&counts[k0], 1ull); else atomicAdd(&my[s0], 1u);
+        }
+        if (threadIdx.x == 0) { bucket_stragglers(head, nhead, counts); bucket_stragglers(tail, ntail, counts); }
+    }
+    __syncthreads();
+    flush_subhist(s_hist, COPIES, threadIdx.x, THREADS, counts);
+}
+
+// ------------------------------------------------------------------ K1/bulk
+// Producer warp streams STAGE_BYTES tiles into a STAGES-deep shared ring with
+// cp.async.bulk; CW consumer warps bucket them.  Tiles are dealt round-robin.
+template <int CW, int STAGES, int STAGE_BYTES, int COPIES, int MINB>
+__global__ void __launch_bounds__((CW + 1) * 32, MINB)
+k_ingest_single_bulk(const double *__restrict__ vals32, size_t nvec32, const double *head, int nhead,
+                     const double *tail, int ntail, unsigned long long *__restrict__ counts) {
+    const double2 *vals16 = reinterpret_cast<const double2 *>(vals32);
+    const size_t nvec = nvec32 * 2;   // 16-byte vectors
+    constexpr int CT = CW * 32;                       // consumer threads
+    constexpr int STAGE_VEC = STAGE_BYTES / 16;
+    constexpr int PER_THREAD = STAGE_VEC / CT;        // double2 per consumer thread per stage
+    static_assert(STAGE_VEC % CT == 0, "stage must divide evenly over consumer threads");
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    double2 *s_data = reinterpret_cast<double2 *>(s_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_raw + (size_t)STAGES * STAGE_BYTES);
+    uint64_t *empty = full + STAGES;
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(empty + STAGES);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    for (int i = tid; i < COPIES * (int)LH_SUBHIST_ALLOC; i += (CW + 1) * 32) s_hist[i] = 0;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const size_t ntiles = (nvec + STAGE_VEC - 1) / STAGE_VEC;
+    if (warp == CW) {
+        // ===== producer =====
+        if ((tid & 31) == 0) {
+            const uint64_t pol = policy_evict_first();
+            uint32_t it = 0;
+            for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+                const int s = it % STAGES;
+                mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                size_t first = tile * (size_t)STAGE_VEC;
+                size_t rem = nvec - first;
+                uint32_t bytes = (uint32_t)((rem < (size_t)STAGE_VEC ? rem : (size_t)STAGE_VEC) * 16);
+                mbar_expect_tx(&full[s], bytes);
+                bulk_g2s(s_data + (size_t)s * STAGE_VEC, vals16 + first, bytes, &full[s], pol);
+            }
+        }
+    } else {
+        // ===== consumers =====
+        uint32_t *my = s_hist + (warp % COPIES) * LH_SUBHIST_ALLOC;
+        uint32_t it = 0;
+        for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+            const int s = it % STAGES;
+            mbar_wait(&full[s], (it / STAGES) & 1);
+            const double2 *st = s_data + (size_t)s * STAGE_VEC;
+            size_t first = tile * (size_t)STAGE_VEC;
+            size_t rem = nvec - first;
+            if (rem >= (size_t)STAGE_VEC) {
+                double v[2 * PER_THREAD];
+#pragma unroll
+                for (int u = 0; u < PER_THREAD; u++) {
+                    double2 d = st[u * CT + tid];
+                    v[2 * u] = d.x; v[2 * u + 1] = d.y;
+                }
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&empty[s]);   // registers hold the data: release early
+                bucket_samples<2 * PER_THREAD>(v, my, counts);
+            } else {
+                for (int j = tid; j < (int)rem; j += CT) {
+                    double2 d = st[j];
+                    uint32_t k0 = key16_of(d.x), k1 = key16_of(d.y);
+                    uint32_t s0 = key16_to_slot(k0), s1 = key16_to_slot(k1);
+                    if (s0 == 0xFFFFFFFFu) atomicAdd(&counts[k0], 1ull); else atomicAdd(&my[s0], 1u);
+                    if (s1 == 0xFFFFFFFFu) atomicAdd(&counts[k1], 1ull); else atomicAdd(&my[s1], 1u);
+                }
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+            }
+        }
+        if (blockIdx.x == 0 && tid == 0) { bucket_stragglers(head, nhead, counts); bucket_stragglers(tail, ntail, counts); }
+    }
+    __syncthreads();
+    flush_subhist(s_hist, COPIES, tid, (CW + 1) * 32, counts);
+}
+
+// --------------------------------------------------------------------- K1k
+template <typename T> __device__ __forceinline__ double sample_to_f64(T v);
+template <> __device__ __forceinline__ double sample_to_f64<double>(double v) { return v; }
+// float64(duration.Nanoseconds()): CVTSQ2SD, round-to-nearest-even
+template <> __device__ __forceinline__ double sample_to_f64<long long>(long long v) { return __ll2double_rn(v); }
+
+template <typename IdT, typename ValT, int THREADS, int UNROLL>
+__global__ void __launch_bounds__(THREADS)
+k_ingest_keyed(const IdT *__restrict__ ids, const ValT *__restrict__ vals, size_t n,
+               unsigned long long *__restrict__ buckets, uint32_t H,
+               unsigned long long *__restrict__ dropped) {
+    const size_t stride = (size_t)gridDim.x * THREADS * UNROLL;
+    for (size_t base = (size_t)blockIdx.x * THREADS * UNROLL; base < n; base += stride) {
+        double v[UNROLL];
+        uint32_t id[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            size_t i = base + (size_t)u * THREADS + threadIdx.x;
+            bool ok = i < n;
+            v[u] = ok ? sample_to_f64<ValT>(vals[i]) : 0.0;
+            id[u] = ok ? (uint32_t)ids[i] : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            size_t i = base + (size_t)u * THREADS + threadIdx.x;
+            if (i < n) {
+                uint32_t key = key16_of(v[u]);
+                if (id[u] < H) atomicAdd(&buckets[(size_t)id[u] * 65536u + key], 1ull);
+                else atomicAdd(dropped, 1ull);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------- K2
+template <typename IdT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_counter_add(const IdT *__restrict__ ids, const unsigned long long *__restrict__ amounts, size_t n,
+              unsigned long long *__restrict__ counters, uint32_t C,
+              unsigned long long *__restrict__ dropped) {
+    const size_t stride = (size_t)gridDim.x * THREADS;
+    for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += stride) {
+        uint32_t id = (uint32_t)ids[i];
+        if (id < C) atomicAdd(&counters[id], amounts[i]);
+        else atomicAdd(dropped, 1ull);
+    }
+}
+
+// ---------------------------------------------------------------------- K3
+// One CTA per histogram.  Thread t owns the 64 consecutive keys
+// [-32768 + 64 t, -32768 + 64 t + 63] (ascending key == ascending value, the
+// order percentile() sorts into, metrics.go:409).
+constexpr int K3_THREADS = 1024;
+constexpr int K3_PER = 65536 / K3_THREADS;
+
+__global__ void __launch_bounds__(K3_THREADS)
+k_reduce(const unsigned long long *__restrict__ buckets, const double *__restrict__ decomp,
+         const double *__restrict__ ps, int np, unsigned long long *__restrict__ out_count,
+         double *__restrict__ out_sum, double *__restrict__ out_avg, int *__restrict__ out_pkeys,
+         double *__restrict__ out_pvals, uint32_t *__restrict__ out_nnz) {
+    __shared__ unsigned long long s_warp_cnt[32];
+    __shared__ double s_warp_sum[32];
+    __shared__ unsigned int s_warp_nnz[32];
+    __shared__ int s_owner[LH_MAX_PCT];
+    __shared__ unsigned long long s_total;
+    const int h = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const unsigned long long *hb = buckets + (size_t)h * 65536u;
+
+    unsigned long long c[K3_PER];
+    unsigned long long mine = 0;
+    double msum = 0.0;
+    unsigned int nnz = 0;
+#pragma unroll 8
+    for (int j = 0; j < K3_PER; j++) {
+        int key = -32768 + t * K3_PER + j;
+        unsigned int slot = (unsigned int)key & 0xFFFFu;
+        c[j] = hb[slot];
+        if (c[j]) { mine += c[j]; msum += decomp[slot] * (double)c[j]; nnz++; }
+    }
+    // block-wide inclusive scan of `mine` (warp shuffle + per-warp totals)
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    double wsum = msum;
+    unsigned int wnnz = nnz;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        wsum += __shfl_xor_sync(0xFFFFFFFFu, wsum, o);
+        wnnz += __shfl_xor_sync(0xFFFFFFFFu, wnnz, o);
+    }
+    if (lane == 31) s_warp_cnt[warp] = incl;
+    if (lane == 0) { s_warp_sum[warp] = wsum; s_warp_nnz[warp] = wnnz; }
+    if (t < LH_MAX_PCT) s_owner[t] = 0x7FFFFFFF;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = s_warp_cnt[lane];
+        unsigned long long wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+            if (lane >= o) wi += y;
+        }
+        s_warp_cnt[lane] = wi - w;   // exclusive prefix of warp totals
+        if (lane == 31) s_total = wi;
+        double ts = s_warp_sum[lane];
+        unsigned int tn = s_warp_nnz[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ts += __shfl_xor_sync(0xFFFFFFFFu, ts, o);
+            tn += __shfl_xor_sync(0xFFFFFFFFu, tn, o);
+        }
+        if (lane == 0) { s_warp_sum[0] = ts; s_warp_nnz[0] = tn; }
+    }
+    __syncthreads();
+    const unsigned long long total = s_total;
+    const unsigned long long end_incl = s_warp_cnt[warp] + incl;   // counts up to and including my keys
+    const double ftotal = (double)total;
+    // which thread owns each percentile: the first non-empty one whose inclusive prefix satisfies the rule
+    if (mine) {
+        for (int j = 0; j < np; j++)
+            if (__ddiv_rn((double)end_incl, ftotal) >= ps[j]) atomicMin(&s_owner[j], t);
+    }
+    __syncthreads();
+    for (int j = 0; j < np; j++) {
+        if (s_owner[j] == t) {
+            unsigned long long sofar = end_incl - mine;
+            const double p = ps[j];
+#pragma unroll 8
+            for (int q = 0; q < K3_PER; q++) {
+                if (!c[q]) continue;
+                sofar += c[q];
+                if (__ddiv_rn((double)sofar, ftotal) >= p) {   // metrics.go:413
+                    int key = -32768 + t * K3_PER + q;
+                    out_pkeys[(size_t)h * np + j] = key;
+                    out_pvals[(size_t)h * np + j] = decomp[(unsigned int)key & 0xFFFFu];
+                    break;
+                }
+            }
+        }
+        if (t == 0 && s_owner[j] == 0x7FFFFFFF) {   // percentile() error: key omitted by the caller
+            out_pkeys[(size_t)h * np + j] = (int)0x80000000;
+            out_pvals[(size_t)h * np + j] = __longlong_as_double(0x7FF8000000000000ll);
+        }
+    }
+    if (t == 0) {
+        out_count[h] = total;
+        out_sum[h] = s_warp_sum[0];
+        out_avg[h] = __ddiv_rn(s_warp_sum[0], ftotal);    // metrics.go:356 (NaN when empty)
+        out_nnz[h] = s_warp_nnz[0];
+    }
+}
+
+// ---------------------------------------------------------------------- K4
+// offsets[h] = exclusive prefix of nnz (computed by k_scan_nnz); entries are
+// written in ascending key order.
+__global__ void k_scan_nnz(const uint32_t *__restrict__ nnz, uint32_t H, uint32_t *__restrict__ offsets) {
+    // single CTA, H is small (<= a few thousand): serial per-chunk scan is fine
+    __shared__ uint32_t s_part[1024];
+    const int t = threadIdx.x;
+    const uint32_t per = (H + 1023u) / 1024u;
+    uint32_t a = 0;
+    for (uint32_t i = 0; i < per; i++) { uint32_t idx = t * per + i; if (idx < H) a += nnz[idx]; }
+    s_part[t] = a;
+    __syncthreads();
+    if (t == 0) { uint32_t run = 0; for (int i = 0; i < 1024; i++) { uint32_t x = s_part[i]; s_part[i] = run; run += x; } offsets[H] = run; }
+    __syncthreads();
+    uint32_t run = s_part[t];
+    for (uint32_t i = 0; i < per; i++) { uint32_t idx = t * per + i; if (idx < H) { offsets[idx] = run; run += nnz[idx]; } }
+}
+
+__global__ void __launch_bounds__(K3_THREADS)
+k_export(const unsigned long long *__restrict__ buckets, const uint32_t *__restrict__ offsets,
+         short *__restrict__ out_keys, unsigned long long *__restrict__ out_counts) {
+    __shared__ unsigned int s_warp[32];
+    const int h = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const unsigned long long *hb = buckets + (size_t)h * 65536u;
+    unsigned long long c[K3_PER];
+    unsigned int nnz = 0;
+#pragma unroll 8
+    for (int j = 0; j < K3_PER; j++) {
+        int key = -32768 + t * K3_PER + j;
+        c[j] = hb[(unsigned int)key & 0xFFFFu];
+        nnz += c[j] != 0;
+    }
+    unsigned int incl = nnz;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned int y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned int w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned int y = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= o) wi += y; }
+        s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    unsigned int pos = offsets[h] + s_warp[warp] + incl - nnz;
+#pragma unroll 8
+    for (int j = 0; j < K3_PER; j++) {
+        if (c[j]) { out_keys[pos] = (short)(-32768 + t * K3_PER + j); out_counts[pos] = c[j]; pos++; }
+    }
+}
+
+// ----------------------------------------------------------- probes / tables
+__global__ void k_fill_decompress(double *__restrict__ table) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 65536) table[i] = go_decompress((int)(short)i);
+}
+
+__global__ void k_compress_probe(const double *__restrict__ v, size_t n, short *__restrict__ out, int mode) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (short)(mode == 1 ? exact_key16(v[i]) : key16_of(v[i]));
+}
+
+// max | (69 e + w) - 100 ln(x) | over samples inside the fast window, plus the slow-flag tally
+__global__ void k_fastpath_margin(const double *__restrict__ v, size_t n, unsigned long long *__restrict__ max_err_bits,
+                                  unsigned long long *__restrict__ n_slow) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x = __dadd_rn(1.0, fabs(v[i]));
+    uint32_t hi = (uint32_t)__double2hiint(x), lo = (uint32_t)__double2loint(x);
+    uint32_t idx; bool slow;
+    fast_candidate(v[i], idx, slow);
+    if (slow) atomicAdd(n_slow, 1ull);
+    if (hi >= 0x43E00000u) return;
+    uint32_t t = __funnelshift_l(lo, hi, 3);
+    float m = __uint_as_float((t & 0x007FFFFFu) | 0x3F800000u);
+    float lg;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(m));
+    uint32_t eb = hi >> 20;
+    float ef = __fadd_rn(__uint_as_float(0x4B000000u | eb), -(8388608.0f + 1023.0f));
+    float w = __fmaf_rn(lg, 69.31471805599453f, __fmul_rn(ef, 0.31471805599453f));
+    double est = (double)(int)(eb - 1023u) * 69.0 + (double)w;
+    double err = fabs(est - 100.0 * log(x));
+    atomicMax(max_err_bits, (unsigned long long)__double_as_longlong(err));
+}
+
+// ---------------------------------------------------------- synthetic streams
+__device__ __constant__ unsigned char c_streamL_exp[16] = {17, 18, 18, 19, 19, 19, 20, 20, 20, 20, 21, 21, 21, 22, 22, 23};
+
+__device__ __forceinline__ uint64_t stream_bits(int kind, uint64_t seed, uint64_t i) {
+    uint64_t u = splitmix64(seed + i);
+    uint64_t mant = u & 0x000FFFFFFFFFFFFFull;
+    switch (kind) {
+    case 0: return ((uint64_t)(1023 + (u >> 52) % 63) << 52) | mant;
+    case 1: return ((uint64_t)(1023 + c_streamL_exp[(u >> 52) & 15]) << 52) | mant;
+    case 2: {
+        uint32_t sel = (uint32_t)(u >> 52) & 0xFFFu;
+        if (sel < 41) return 0x8000000000000000ull | ((uint64_t)(1023 + (u >> 40) % 63) << 52) | mant;
+        if (sel < 60) return splitmix64(u);
+        if (sel < 80) return ((u >> 11) & 0x8000000000000000ull) | ((uint64_t)(1023 - 10 + (u >> 40) % 12) << 52) | mant;
+        if (sel < 90) return ((u >> 13) & 0x8000000000000000ull) | ((uint64_t)(1023 + 63 + (u >> 40) % 961) << 52) | mant;
+        return ((uint64_t)(1023 + (u >> 40) % 63) << 52) | mant;
+    }
+    case 3: return 0x40F86A0000000000ull;
+    case 4:
+        if (u >> 63) return 0x40F86A0000000000ull;
+        return ((uint64_t)(1023 + c_streamL_exp[(u >> 52) & 15]) << 52) | mant;
+    default: return u;
+    }
+}
+
+__global__ void k_gen_stream(int kind, uint64_t seed, uint64_t start, size_t n, double *__restrict__ out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = u64_as_f64(stream_bits(kind, seed, start + i));
+}
+
+__global__ void k_gen_ids_u16(int kind, uint64_t seed, uint64_t start, size_t n, uint32_t H,
+                              unsigned short *__restrict__ out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t u = splitmix64((seed ^ 0xA5A5A5A5DEADBEEFull) + start + i);
+        uint32_t a = (uint32_t)((u & 0xFFFFFFFFu) % H), b = (uint32_t)((u >> 32) % H);
+        out[i] = (unsigned short)(kind == 0 ? a : (a < b ? a : b));
+    }
+}
+
+}  // namespace lh

@@ -1,0 +1,75 @@
+"""CPU-side checks of the drop-in boundary: the library builds, loads, exports every symbol the header
+declares, and refuses to run without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "loghisto_b200.h")).read()
+    return sorted(set(re.findall(r"^LH_API [^;(]*?\b(lh_[a-z0-9_]+)\(", src, flags=re.M)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from loghisto_b200 import _lib, build
+    build.build()
+    lib = ctypes.CDLL(build.LIB)
+    syms = header_symbols()
+    assert len(syms) >= 40
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/loghisto_b200.h but not exported"
+    # the ctypes binding covers exactly the declared surface
+    assert sorted(_lib.SIGNATURES) == syms
+
+
+def test_abi_version_and_strerror():
+    from loghisto_b200 import _lib
+    lib = _lib.load()
+    assert lib.lh_abi_version() == 1
+    assert lib.lh_strerror(0) == b"ok"
+    assert b"no CPU fallback" in lib.lh_strerror(_lib.LH_ERR_NO_DEVICE)
+    assert lib.lh_k1_variant_count() >= 4
+
+
+def test_struct_layouts_match_header():
+    from loghisto_b200 import _lib
+    assert ctypes.sizeof(_lib.lh_config) == 32
+    assert ctypes.sizeof(_lib.lh_staging) == 24
+    assert ctypes.sizeof(_lib.lh_device_view) == 40
+    assert ctypes.sizeof(_lib.lh_sparse) == 40
+    assert ctypes.sizeof(_lib.lh_stats) == 56
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import loghisto_b200 as lh
+    with pytest.raises(lh.LhError) as e:
+        lh.Engine()
+    assert e.value.status == -4
+
+
+def test_create_rejects_bad_config():
+    from loghisto_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    cfg = _lib.lh_config(ctypes.sizeof(_lib.lh_config), 0, 0, 1, 0, 0, 0)
+    assert lib.lh_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.LH_ERR_INVALID
+    cfg = _lib.lh_config(8, 0, 1, 1, 0, 0, 0)
+    assert lib.lh_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.LH_ERR_INVALID
+    assert lib.lh_destroy(None) == 0
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "loghisto_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"liblh_oracle|from oracle|import oracle|oracle[./]", text), \
+                    f"{f} reaches into oracle/"
