@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- loghisto hot path on B200: samples/s, HBM roofline fraction, CPU baseline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--impl b200|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic float64
+samples: ingest (bucket index + increment) of the whole batch, then the
+snapshot (double-buffer swap, bucket-array all-reduce when N > 1) and the
+bucket->percentile reduction, result read back to the host.
+
+  value      whole-job samples/s with the batch already resident in HBM
+  e2e        same steps fed from pinned HOST memory through lh_ingest_f64_host
+             (H2D copies inside the timed region)
+  roofline   the dominant kernel (K1 ingest) alone: 8 B/sample (10 B for c3)
+             over its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the CPU oracle port of metrics.go:273-295 timed on this box's
+             host cores over a bounded sample (N=1, rank 0 only)
+
+--impl reference times that CPU port alone (the Go reference cannot be built
+here: no Go toolchain in the image).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 0x10C415C0
+PERCENTILES = [0.0, 0.5, 0.75, 0.9, 0.95, 0.99, 0.999, 0.9999, 1.0]   # metrics.go:145-155
+PUBLISHED_SAMPLES_PER_S = 2.0171025e7   # readme.md:34, the reference's only published ingest rate
+FALLBACK_HBM_GBS = 6650.0               # /opt/skills/guides/B200_PROFILING.md
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
+    ap.add_argument("--stream", default="U", choices=["U", "L", "S", "C", "Z"])
+    ap.add_argument("--n", type=int, default=0, help="samples per GPU per step (default: BASELINE config)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps for the host-fed leg (default min(steps, 5))")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = []
+        for line in open(self.f.name):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 7:
+                try:
+                    rows.append((float(parts[0]), float(parts[1]), float(parts[2]), parts[3:7]))
+                except ValueError:
+                    pass
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        # "under load" = the busier half by power draw
+        rows.sort(key=lambda r: r[2])
+        load = rows[len(rows) // 2:]
+        sm = sorted(r[0] for r in load)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in rows for i in range(4) if r[3][i].lower().startswith("active")})
+        out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(r[1] for r in rows), reasons=reasons,
+                   samples=len(rows), power_w_max=max(r[2] for r in rows))
+        return out
+
+
+# ----------------------------------------------------------------- CPU arm
+def _thread_ladder():
+    ncpu = os.cpu_count() or 1
+    return sorted({1, min(2, ncpu), min(4, ncpu), min(16, ncpu), ncpu})
+
+
+def _calibrate_cpu_port(o, kind, n_hist, names):
+    """The port's shared reader count and bucket cells ping-pong between cores (as the reference's RWMutex and
+    atomics do), so more threads is not always faster: probe a ladder of thread counts and keep the best."""
+    # long enough (>= 0.25 s) that the scheduler has spread the threads over distinct cores
+    probe = 8_000_000
+    vals = o.gen_stream(kind, probe, SEED)
+    ids = o.gen_ids(0, probe, n_hist, SEED) if n_hist > 1 else None
+    best = (0.0, 1)
+    ladder = {}
+    for t in _thread_ladder():
+        ms = o.OracleMetricSystem()
+        ms.bench_ingest(vals[:100_000], ids[:100_000] if ids is not None else None, names, t)   # create the cells
+        dt = ms.bench_ingest(vals, ids, names, t)
+        ms.close()
+        ladder[t] = probe / dt
+        if probe / dt > best[0]:
+            best = (probe / dt, t)
+    return best[0], best[1], ladder
+
+
+def cpu_port_rate(n_hist, stream_kind, seconds):
+    """Times the oracle's structure-faithful port of MetricSystem.Histogram (metrics.go:273-295: Go-style
+    RWMutex + name->map[int16] lookups + atomic add, Go-exact compress) on a bounded sample of the same
+    synthetic stream, at the thread count that runs fastest on this host.
+    Returns (samples_per_s, threads, n_sample, dense_rate, ladder)."""
+    from oracle import oracle as o
+    o.build()
+    names = ["histogram%d" % i for i in range(n_hist)]
+    rate, threads, ladder = _calibrate_cpu_port(o, stream_kind, n_hist, names)
+    n = int(min(max(rate * seconds, 1_000_000), 400_000_000))
+    vals = o.gen_stream(stream_kind, n, SEED)
+    ids = o.gen_ids(0, n, n_hist, SEED) if n_hist > 1 else None
+    ms = o.OracleMetricSystem()
+    dt = ms.bench_ingest(vals, ids, names, threads)
+    ms.close()
+    # "best-case CPU" (dense private arrays, no locks/maps, every core) for context
+    m = min(n, 50_000_000)
+    t0 = time.perf_counter()
+    o.ingest(vals[:m], threads=os.cpu_count() or 1)
+    dense = m / (time.perf_counter() - t0)
+    return n / dt, threads, n, dense, ladder
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU implementation of the path on the host cores, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as o
+    o.build()
+    n_hist = 1024 if a.workload == "c3" else 1
+    kind = {"U": 0, "L": 1, "S": 2, "C": 3, "Z": 4}[a.stream]
+    names = ["histogram%d" % i for i in range(n_hist)]
+    rate, threads, ladder = _calibrate_cpu_port(o, kind, n_hist, names)
+    n = int(min(max(rate * 1.0, 1_000_000), 200_000_000))     # about 1 s of CPU work per step
+    vals = o.gen_stream(kind, n, SEED)
+    ids = o.gen_ids(0, n, n_hist, SEED) if n_hist > 1 else None
+    ms = o.OracleMetricSystem()
+    for _ in range(a.warmup):
+        ms.bench_ingest(vals, ids, names, threads)
+        ms.collect_and_process()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        ms.bench_ingest(vals, ids, names, threads)
+        ms.collect_and_process()          # snapshot + percentile reduction, like one b200 step
+    dt = time.perf_counter() - t0
+    ms.close()
+    value = n * a.steps / dt
+    unit = "samples/s"
+    print(json.dumps({
+        "impl": "reference", "metric": "histogram ingest throughput (samples/s)", "value": value, "unit": unit,
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": value / PUBLISHED_SAMPLES_PER_S,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(a, n, a.gpus, sample_of="bounded sample of %d samples per step" % n),
+        "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port",
+                         "host_cpus": os.cpu_count(), "thread_ladder_samples_per_s": ladder,
+                         "sample": "%d samples/step x %d steps, stream %s, %d name(s); C port of "
+                                   "metrics.go:273-295 incl. Go's RWMutex algorithm (Go toolchain absent), run at "
+                                   "the fastest thread count of the ladder" % (n, a.steps, a.stream, n_hist)},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(a, n_per_gpu, n_gpus, sample_of=None):
+    if a.workload == "c2":
+        name = ("BASELINE configs[1]: 1 GPU, 1 histogram, 1e9-sample synthetic float64 stream" if n_gpus == 1 else
+                "BASELINE configs[3] slice: %d GPU(s), 1 histogram, %d samples per GPU, bucket-array all-reduce "
+                "before percentiles" % (n_gpus, n_per_gpu))
+    else:
+        name = "BASELINE configs[2]: 1024 keyed histograms, (uint16 id, float64 value) pairs"
+    cfg = {"workload": name, "stream": a.stream, "samples_per_gpu_per_step": n_per_gpu,
+           "histograms": 1024 if a.workload == "c3" else 1, "percentiles": len(PERCENTILES),
+           "l2": "inputs (%.1f GB per GPU) are larger than the 126 MB L2; no flush needed" % (n_per_gpu * 8 / 1e9),
+           "published_ref": "readme.md:34 (2014, unnamed CPU, Timer path incl. two time.Now() per sample)"}
+    if sample_of:
+        cfg["sample"] = sample_of
+        cfg["l2"] = "n/a (CPU arm)"
+    return cfg
+
+
+# ----------------------------------------------------------------- GPU arm
+def run_b200(a):
+    import numpy as np
+    import torch
+    import loghisto_b200 as lh
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("bench.py --gpus %d must be launched with torch.distributed.run (one rank per GPU)" % a.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    keyed = a.workload == "c3"
+    n = a.n or (1_000_000_000 if (world == 1 or keyed) else 1_250_000_000)
+    H = 1024 if keyed else 1
+    kind = {"U": 0, "L": 1, "S": 2, "C": 3, "Z": 4}[a.stream]
+    bytes_per_sample = 10 if keyed else 8
+
+    eng = lh.Engine(device=local, max_histograms=H, max_counters=1)
+    stream = torch.cuda.current_stream()
+    d_vals = eng.gen_stream(kind, n, SEED, start=rank * n, stream=stream)
+    d_ids = eng.gen_ids_u16(0, n, H, SEED, start=rank * n, stream=stream) if keyed else None
+    torch.cuda.synchronize()
+
+    class _View:   # zero-copy torch view of the frozen bucket array for the all-reduce
+        def __init__(self, ptr, words):
+            self.__cuda_array_interface__ = {"shape": (words,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+    kernel_ms = []
+    allreduce_ms = []
+
+    def step(host_src=None):
+        if host_src is None:
+            if keyed:
+                eng.ingest_keyed_f64_u16(d_ids, d_vals, n, stream=stream)
+            else:
+                eng.ingest_f64(0, d_vals, n, stream=stream)
+            kernel_ms.append(None)    # filled after the step (events), see below
+        else:
+            if keyed:
+                eng.ingest_keyed_f64_u16_host(host_src[1], host_src[0], n)
+            else:
+                eng.ingest_f64_host(0, host_src, n)
+        eng.snapshot_begin()
+        if world > 1:
+            v = eng.snapshot_device()
+            ext = torch.cuda.ExternalStream(v.stream, device=local)
+            with torch.cuda.stream(ext):
+                t = torch.as_tensor(_View(v.d_buckets, int(v.n_bucket_words)), device="cuda:%d" % local)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(ext)
+                dist.all_reduce(t)     # uint64 sum == int64 sum bit-for-bit (two's complement)
+                e1.record(ext)
+            allreduce_ms.append((e0, e1))
+        red = eng.snapshot_reduce(PERCENTILES)     # host-synchronous: D2H of count/sum/avg/percentiles
+        eng.snapshot_end()
+        if host_src is None:
+            kernel_ms[-1] = eng.last_kernel_ms()
+        return red
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg
+    for _ in range(max(a.warmup, 3)):
+        red = step()
+    del kernel_ms[:]
+    del allreduce_ms[:]
+    launches0 = eng.stats()["kernel_launches"]
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record(stream)
+    t_wall = time.perf_counter()
+    for _ in range(a.steps):
+        red = step()
+    e_stop.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    dev_ms = max(e_start.elapsed_time(e_stop), 0.0)
+    # the snapshot leg runs on the context's own stream and ends host-synchronously, so the step loop's
+    # wall time bounds it; report the larger of the two clocks (they agree within launch latency)
+    total_ms = max(dev_ms, wall_ms)
+    clk = clocks.stop() if clocks else None
+    launches = eng.stats()["kernel_launches"] - launches0
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    kms = sum(kernel_ms) / len(kernel_ms)
+    ar_ms = (sum(e0.elapsed_time(e1) for e0, e1 in allreduce_ms) / len(allreduce_ms)) if allreduce_ms else 0.0
+    count_ok = int(red.counts.sum()) == n * world
+
+    # ---- host-fed leg (e2e)
+    e2e = None
+    if not a.no_e2e:
+        ksteps = a.e2e_steps or min(a.steps, 5)
+        hv = eng.pinned(n, np.float64)
+        eng._check(eng.lib.lh_memcpy_d2h(eng.h, hv.ptr, d_vals.ptr, n * 8))
+        hsrc = hv.array
+        hi = None
+        if keyed:
+            hi = eng.pinned(n, np.uint16)
+            eng._check(eng.lib.lh_memcpy_d2h(eng.h, hi.ptr, d_ids.ptr, n * 2))
+            hsrc = (hv.array, hi.array)
+        step(hsrc)
+        step(hsrc)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            red_h = step(hsrc)
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        d2h = H * 8 * 3 + H * len(PERCENTILES) * 12
+        e2e = {"value": n * world * ksteps / (e2e_ms / 1e3), "unit": "samples/s",
+               "h2d_bytes_per_step": n * bytes_per_sample, "d2h_bytes_per_step": d2h, "steps": ksteps,
+               "ms_per_step": e2e_ms / ksteps, "api": "lh_ingest_f64_host + lh_snapshot_* (pinned host buffers)",
+               "count_ok": int(red_h.counts.sum()) == n * world}
+        hv.free()
+        if hi is not None:
+            hi.free()
+
+    if rank == 0:
+        peak, peak_src = peak_hbm()
+        achieved = n * bytes_per_sample / (kms / 1e3) / 1e9
+        value = n * world * a.steps / (total_ms / 1e3)
+        line = {
+            "metric": "histogram ingest throughput (samples/s)", "value": value, "unit": "samples/s",
+            "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": total_ms / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": value / PUBLISHED_SAMPLES_PER_S,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_config(a, n, world),
+            "gpu_launches": launches, "count_ok": count_ok, "clocks": clk,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": "k_ingest_keyed" if keyed else "k_ingest_single_ldg (%s)" % eng.k1_variants()[0],
+                         "kernel_ms": kms, "bytes_per_sample": bytes_per_sample},
+            "allreduce_ms": ar_ms,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not a.no_cpu_baseline:
+            rate, threads, ns, dense, ladder = cpu_port_rate(H, kind, a.cpu_seconds)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
+                "sample": "%d samples of the same stream; C port of metrics.go:273-295 (RWMutex + maps + atomic add, "
+                          "Go-exact compress), all host threads; Go toolchain absent so the reference itself cannot run"
+                          % ns,
+                "host_cpus": os.cpu_count(), "thread_ladder_samples_per_s": ladder,
+                "dense_private_arrays_all_cores_value": dense}
+        print(json.dumps(line))
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

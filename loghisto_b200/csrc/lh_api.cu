@@ -23,6 +23,8 @@ struct WriterEvent { cudaStream_t stream; cudaEvent_t ev; };
 struct Buffer {
     unsigned long long *d_buckets = nullptr;   // [H][65536]
     unsigned long long *d_counters = nullptr;  // [C]
+    unsigned int *d_hot = nullptr;             // [H][LH_SUBHIST] uint32 window of the keyed path
+    unsigned long long hot_pending = 0;        // samples added to d_hot since it was last drained
     cudaEvent_t cleared = nullptr;             // zeroing finished
     std::vector<WriterEvent> writers;          // last ingest per stream
 };
@@ -204,18 +206,59 @@ lh_status launch_single(lh_ctx *ctx, uint32_t hid, const double *d_values, size_
     return after_write(ctx, b, s);
 }
 
+lh_status fold_hot(lh_ctx *ctx, int b, cudaStream_t s) {
+    const size_t cells = (size_t)ctx->H * LH_SUBHIST;
+    int grid = (int)std::min<size_t>((cells + 255) / 256, (size_t)ctx->sm_count * 16);
+    k_fold_hot<<<grid, 256, 0, s>>>(ctx->buf[b].d_hot, ctx->buf[b].d_buckets, cells);
+    LH_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    ctx->buf[b].hot_pending = 0;
+    return LH_OK;
+}
+
 template <typename IdT, typename ValT>
 lh_status launch_keyed(lh_ctx *ctx, const IdT *d_ids, const ValT *d_vals, size_t n, cudaStream_t s) {
+    if (((uintptr_t)d_vals & 7u) || ((uintptr_t)d_ids & (sizeof(IdT) - 1)))
+        return fail(ctx, LH_ERR_INVALID, "ids / values are not naturally aligned");
     const int b = ctx->active;
     lh_status st = before_write(ctx, b, s);
     if (st != LH_OK) return st;
+    constexpr int T = 256;
     LH_CUDA(ctx, cudaEventRecord(ctx->ev_t0, s));
-    if (n) {
-        constexpr int T = 256, U = 4;
-        int grid = grid_1d(ctx, n, T, U, ctx->keyed_blocks_per_sm);
-        k_ingest_keyed<IdT, ValT, T, U><<<grid, T, 0, s>>>(d_ids, d_vals, n, ctx->buf[b].d_buckets, ctx->H, ctx->d_dropped);
+    size_t done = 0;
+    while (done < n) {
+        // no uint32 cell of the hot window may wrap: drain it before 2^32 samples have gone in
+        const unsigned long long kCap = 0xFFFFFFFFull;
+        if (ctx->buf[b].hot_pending >= kCap) { st = fold_hot(ctx, b, s); if (st != LH_OK) return st; }
+        size_t m = (size_t)std::min<unsigned long long>(n - done, kCap - ctx->buf[b].hot_pending);
+        const IdT *ids = d_ids + done;
+        const ValT *vals = d_vals + done;
+        // scalar head until the values are 32-byte aligned; the vector body also needs ids aligned to 4 ids
+        size_t head = std::min<size_t>(m, ((32u - ((uintptr_t)vals & 31u)) & 31u) / 8u);
+        bool vec_ok = (((uintptr_t)(ids + head)) & (4 * sizeof(IdT) - 1)) == 0;
+        size_t n4 = vec_ok ? (m - head) / 4 : 0;
+        size_t tail_off = head + n4 * 4;
+        if (!vec_ok) { head = 0; tail_off = 0; }
+        if (head) {
+            k_ingest_keyed<IdT, ValT, T><<<1, T, 0, s>>>(ids, vals, head, ctx->H, ctx->buf[b].d_hot, ctx->buf[b].d_buckets, ctx->d_dropped);
+            ctx->stats.kernel_launches++;
+        }
+        if (n4) {
+            int grid = grid_1d(ctx, n4, T, 1, ctx->keyed_blocks_per_sm);
+            k_ingest_keyed_vec<IdT, ValT, T><<<grid, T, 0, s>>>(ids + head, vals + head, n4, ctx->H, ctx->buf[b].d_hot,
+                                                                ctx->buf[b].d_buckets, ctx->d_dropped);
+            ctx->stats.kernel_launches++;
+        }
+        if (tail_off < m) {
+            size_t r = m - tail_off;
+            int grid = grid_1d(ctx, r, T, 1, ctx->keyed_blocks_per_sm);
+            k_ingest_keyed<IdT, ValT, T><<<grid, T, 0, s>>>(ids + tail_off, vals + tail_off, r, ctx->H, ctx->buf[b].d_hot,
+                                                            ctx->buf[b].d_buckets, ctx->d_dropped);
+            ctx->stats.kernel_launches++;
+        }
         LH_CUDA(ctx, cudaGetLastError());
-        ctx->stats.kernel_launches++;
+        ctx->buf[b].hot_pending += m;
+        done += m;
     }
     LH_CUDA(ctx, cudaEventRecord(ctx->ev_t1, s));
     ctx->timing_valid = true;
@@ -230,10 +273,16 @@ lh_status launch_counter(lh_ctx *ctx, const IdT *d_ids, const uint64_t *d_amount
     if (st != LH_OK) return st;
     LH_CUDA(ctx, cudaEventRecord(ctx->ev_t0, s));
     if (n) {
-        constexpr int T = 256;
-        int grid = grid_1d(ctx, n, T, 4, 8);
-        k_counter_add<IdT, T><<<grid, T, 0, s>>>(d_ids, reinterpret_cast<const unsigned long long *>(d_amounts), n,
-                                                 ctx->buf[b].d_counters, ctx->C, ctx->d_dropped);
+        constexpr int T = 512;
+        const unsigned long long *amts = reinterpret_cast<const unsigned long long *>(d_amounts);
+        if (ctx->C <= (uint32_t)K2_SMEM_COUNTERS) {
+            // privatised per CTA; one CTA per SM keeps the flush (C global atomics per CTA) small
+            int grid = grid_1d(ctx, n, T, 8, 2);
+            k_counter_add_smem<IdT, T><<<grid, T, (size_t)ctx->C * 8, s>>>(d_ids, amts, n, ctx->buf[b].d_counters, ctx->C, ctx->d_dropped);
+        } else {
+            int grid = grid_1d(ctx, n, T, 4, 4);
+            k_counter_add<IdT, T><<<grid, T, 0, s>>>(d_ids, amts, n, ctx->buf[b].d_counters, ctx->C, ctx->d_dropped);
+        }
         LH_CUDA(ctx, cudaGetLastError());
         ctx->stats.kernel_launches++;
     }
@@ -340,6 +389,8 @@ extern "C" lh_status lh_create(const lh_config *cfg, lh_ctx **out) {
         LH_CREATE_CUDA(cudaMalloc(&ctx->buf[b].d_counters, counter_bytes));
         LH_CREATE_CUDA(cudaMemsetAsync(ctx->buf[b].d_buckets, 0, bucket_bytes, ctx->snap_stream));
         LH_CREATE_CUDA(cudaMemsetAsync(ctx->buf[b].d_counters, 0, counter_bytes, ctx->snap_stream));
+        LH_CREATE_CUDA(cudaMalloc(&ctx->buf[b].d_hot, (size_t)ctx->H * LH_SUBHIST * 4u));
+        LH_CREATE_CUDA(cudaMemsetAsync(ctx->buf[b].d_hot, 0, (size_t)ctx->H * LH_SUBHIST * 4u, ctx->snap_stream));
         LH_CREATE_CUDA(cudaEventCreateWithFlags(&ctx->buf[b].cleared, cudaEventDisableTiming));
         LH_CREATE_CUDA(cudaEventRecord(ctx->buf[b].cleared, ctx->snap_stream));
     }
@@ -366,6 +417,8 @@ extern "C" lh_status lh_create(const lh_config *cfg, lh_ctx **out) {
         LH_CREATE_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
     }
 
+    LH_CREATE_CUDA(cudaFuncSetAttribute((const void *)k_counter_add_smem<unsigned short, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_COUNTERS * 8));
+    LH_CREATE_CUDA(cudaFuncSetAttribute((const void *)k_counter_add_smem<unsigned int, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_COUNTERS * 8));
     for (int i = 0; i < kNumK1Variants; i++) {
         ctx->k1[i] = g_k1_variants[i];
         LH_CREATE_CUDA(cudaFuncSetAttribute(ctx->k1[i].func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->k1[i].smem));
@@ -384,7 +437,7 @@ extern "C" lh_status lh_destroy(lh_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (int b = 0; b < 2; b++) {
-        cudaFree(ctx->buf[b].d_buckets); cudaFree(ctx->buf[b].d_counters);
+        cudaFree(ctx->buf[b].d_buckets); cudaFree(ctx->buf[b].d_counters); cudaFree(ctx->buf[b].d_hot);
         if (ctx->buf[b].cleared) cudaEventDestroy(ctx->buf[b].cleared);
         for (auto &w : ctx->buf[b].writers) cudaEventDestroy(w.ev);
     }
@@ -595,6 +648,10 @@ extern "C" lh_status lh_snapshot_begin(lh_ctx *ctx) {
     const int f = ctx->active;
     // order the snapshot stream after every ingest launch that wrote the buffer being frozen
     for (auto &w : ctx->buf[f].writers) LH_CUDA(ctx, cudaStreamWaitEvent(ctx->snap_stream, w.ev, 0));
+    if (ctx->buf[f].hot_pending) {   // drain the keyed path's uint32 window into the uint64 buckets
+        lh_status st = fold_hot(ctx, f, ctx->snap_stream);
+        if (st != LH_OK) return st;
+    }
     ctx->active ^= 1;
     ctx->frozen = true;
     ctx->nnz_valid = false;

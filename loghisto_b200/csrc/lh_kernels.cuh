@@ -252,40 +252,136 @@ k_ingest_single_bulk(const double *__restrict__ vals32, size_t nvec32, const dou
 }
 
 // --------------------------------------------------------------------- K1k
+// (id,value) pairs.  1024 histograms x ~4.4K live buckets cannot be privatised
+// in shared memory, so the cells live in L2: a compact uint32 "hot window"
+// [H][LH_SUBHIST] (36 MB at H = 1024, vs 512 MB for the dense uint64 arrays)
+// updated with no-return atomics that carry an L2 evict_last policy, while the
+// sample stream is read once with 256-bit evict_first loads so it does not push
+// the cells out of the 126 MB L2.  Keys outside the window go straight to the
+// uint64 array.  k_fold_hot drains the window into the uint64 buckets at every
+// snapshot (and before any cell could reach 2^32).
 template <typename T> __device__ __forceinline__ double sample_to_f64(T v);
 template <> __device__ __forceinline__ double sample_to_f64<double>(double v) { return v; }
 // float64(duration.Nanoseconds()): CVTSQ2SD, round-to-nearest-even
 template <> __device__ __forceinline__ double sample_to_f64<long long>(long long v) { return __ll2double_rn(v); }
 
-template <typename IdT, typename ValT, int THREADS, int UNROLL>
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void red_add_u32_keep(unsigned int *addr, unsigned int v, uint64_t policy) {
+    asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(addr), "r"(v), "l"(policy) : "memory");
+}
+
+template <typename ValT>
+__device__ __forceinline__ void keyed_one(uint32_t id, ValT raw, uint32_t H, unsigned int *__restrict__ hot,
+                                          unsigned long long *__restrict__ buckets,
+                                          unsigned long long *__restrict__ dropped, uint64_t pol) {
+    if (id >= H) { atomicAdd(dropped, 1ull); return; }
+    double v = sample_to_f64<ValT>(raw);
+    uint32_t idx; bool slow;
+    fast_candidate(v, idx, slow);
+    if (slow) {
+        uint32_t key = exact_key16(v);
+        idx = key16_to_slot(key);
+        if (idx == 0xFFFFFFFFu) { atomicAdd(&buckets[(size_t)id * 65536u + key], 1ull); return; }
+    }
+    red_add_u32_keep(&hot[(size_t)id * LH_SUBHIST + idx], 1u, pol);
+}
+
+// Vector body: every thread takes 4 consecutive pairs (one 256-bit value load, one 64/128-bit id load).
+// vals must be 32-byte aligned and ids 4*sizeof(IdT)-aligned; n4 = number of 4-sample groups.
+template <typename IdT, typename ValT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-k_ingest_keyed(const IdT *__restrict__ ids, const ValT *__restrict__ vals, size_t n,
-               unsigned long long *__restrict__ buckets, uint32_t H,
-               unsigned long long *__restrict__ dropped) {
-    const size_t stride = (size_t)gridDim.x * THREADS * UNROLL;
-    for (size_t base = (size_t)blockIdx.x * THREADS * UNROLL; base < n; base += stride) {
-        double v[UNROLL];
-        uint32_t id[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            size_t i = base + (size_t)u * THREADS + threadIdx.x;
-            bool ok = i < n;
-            v[u] = ok ? sample_to_f64<ValT>(vals[i]) : 0.0;
-            id[u] = ok ? (uint32_t)ids[i] : 0xFFFFFFFFu;
+k_ingest_keyed_vec(const IdT *__restrict__ ids, const ValT *__restrict__ vals, size_t n4, uint32_t H,
+                   unsigned int *__restrict__ hot, unsigned long long *__restrict__ buckets,
+                   unsigned long long *__restrict__ dropped) {
+    const uint64_t pol = policy_evict_last();
+    const size_t stride = (size_t)gridDim.x * THREADS;
+    for (size_t g = (size_t)blockIdx.x * THREADS + threadIdx.x; g < n4; g += stride) {
+        unsigned long long a, b, c, d;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
+                     : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(reinterpret_cast<const char *>(vals) + g * 32));
+        uint32_t i0, i1, i2, i3;
+        if (sizeof(IdT) == 2) {
+            unsigned int lo, hi;
+            asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi)
+                         : "l"(reinterpret_cast<const char *>(ids) + g * 8));
+            i0 = lo & 0xFFFFu; i1 = lo >> 16; i2 = hi & 0xFFFFu; i3 = hi >> 16;
+        } else {
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(i0), "=r"(i1), "=r"(i2), "=r"(i3)
+                         : "l"(reinterpret_cast<const char *>(ids) + g * 16));
         }
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            size_t i = base + (size_t)u * THREADS + threadIdx.x;
-            if (i < n) {
-                uint32_t key = key16_of(v[u]);
-                if (id[u] < H) atomicAdd(&buckets[(size_t)id[u] * 65536u + key], 1ull);
-                else atomicAdd(dropped, 1ull);
-            }
+        ValT r0, r1, r2, r3;
+        memcpy(&r0, &a, 8); memcpy(&r1, &b, 8); memcpy(&r2, &c, 8); memcpy(&r3, &d, 8);
+        keyed_one<ValT>(i0, r0, H, hot, buckets, dropped, pol);
+        keyed_one<ValT>(i1, r1, H, hot, buckets, dropped, pol);
+        keyed_one<ValT>(i2, r2, H, hot, buckets, dropped, pol);
+        keyed_one<ValT>(i3, r3, H, hot, buckets, dropped, pol);
+    }
+}
+
+// Scalar version for ragged heads/tails and misaligned inputs.
+template <typename IdT, typename ValT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_ingest_keyed(const IdT *__restrict__ ids, const ValT *__restrict__ vals, size_t n, uint32_t H,
+               unsigned int *__restrict__ hot, unsigned long long *__restrict__ buckets,
+               unsigned long long *__restrict__ dropped) {
+    const uint64_t pol = policy_evict_last();
+    const size_t stride = (size_t)gridDim.x * THREADS;
+    for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += stride)
+        keyed_one<ValT>((uint32_t)ids[i], vals[i], H, hot, buckets, dropped, pol);
+}
+
+// Drain the hot window into the uint64 buckets.  atomicExch/atomicAdd so that ingest on other
+// streams may keep running against the same buffer.
+__global__ void k_fold_hot(unsigned int *__restrict__ hot, unsigned long long *__restrict__ buckets, size_t cells) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += stride) {
+        unsigned int v = hot[i];
+        if (v) {
+            v = atomicExch(&hot[i], 0u);
+            size_t h = i / LH_SUBHIST;
+            uint32_t slot = (uint32_t)(i - h * LH_SUBHIST);
+            if (v) atomicAdd(&buckets[h * 65536u + slot_to_key16(slot)], (unsigned long long)v);
         }
     }
 }
 
 // ---------------------------------------------------------------------- K2
+// Counter(name, amount): counters[id] += amount (wrapping uint64).  Up to
+// K2_SMEM_COUNTERS ids are privatised per CTA as lo/hi uint32 halves in shared
+// memory: one returning shared atomic on the low half, a second one on the
+// high half only when the amount has high bits or the low half carried.
+constexpr int K2_SMEM_COUNTERS = 8192;
+
+template <typename IdT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_counter_add_smem(const IdT *__restrict__ ids, const unsigned long long *__restrict__ amounts, size_t n,
+                   unsigned long long *__restrict__ counters, uint32_t C,
+                   unsigned long long *__restrict__ dropped) {
+    extern __shared__ unsigned int s_cnt[];          // [C] low halves, [C] high halves
+    unsigned int *lo = s_cnt, *hi = s_cnt + C;
+    for (uint32_t i = threadIdx.x; i < 2 * C; i += THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * THREADS;
+    for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += stride) {
+        uint32_t id = (uint32_t)ids[i];
+        unsigned long long amt = amounts[i];
+        if (id >= C) { atomicAdd(dropped, 1ull); continue; }
+        unsigned int a_lo = (unsigned int)amt, a_hi = (unsigned int)(amt >> 32);
+        unsigned int old = atomicAdd(&lo[id], a_lo);
+        a_hi += (old + a_lo < old) ? 1u : 0u;        // carry out of the low half
+        if (a_hi) atomicAdd(&hi[id], a_hi);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < C; i += THREADS) {
+        unsigned long long v = ((unsigned long long)hi[i] << 32) | lo[i];
+        if (v) atomicAdd(&counters[i], v);
+    }
+}
+
 template <typename IdT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_counter_add(const IdT *__restrict__ ids, const unsigned long long *__restrict__ amounts, size_t n,

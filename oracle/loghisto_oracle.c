@@ -42,6 +42,7 @@
 #define _GNU_SOURCE
 #include <math.h>
 #include <pthread.h>
+#include <semaphore.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -447,8 +448,46 @@ typedef struct {
     histo_entry *e; uint32_t cap, len;
 } histo_map; /* map[string]map[int16]*uint64 */
 
+/* sync.RWMutex restated (src/sync/rwmutex.go): the reader fast path is one
+ * atomic add on readerCount for RLock and one for RUnlock -- the "2 atomic
+ * RMWs on one shared cache line" that metrics.go:275/:279 pay per sample.
+ * pthread_rwlock_t is NOT a fair stand-in (it collapses into futex sleeps
+ * under reader contention), so the port carries Go's algorithm itself. */
+#define GO_RWMUTEX_MAX_READERS (1 << 30)
+typedef struct {
+    pthread_mutex_t w;          /* held if there are pending writers */
+    sem_t writer_sem, reader_sem;
+    int32_t reader_count;       /* number of pending readers */
+    int32_t reader_wait;        /* number of departing readers */
+} go_rwmutex;
+static void go_rw_init(go_rwmutex *rw) {
+    pthread_mutex_init(&rw->w, NULL);
+    sem_init(&rw->writer_sem, 0, 0); sem_init(&rw->reader_sem, 0, 0);
+    rw->reader_count = 0; rw->reader_wait = 0;
+}
+static inline void go_rw_rlock(go_rwmutex *rw) {
+    if (__atomic_add_fetch(&rw->reader_count, 1, __ATOMIC_SEQ_CST) < 0)
+        while (sem_wait(&rw->reader_sem) != 0) {}          /* a writer is pending */
+}
+static inline void go_rw_runlock(go_rwmutex *rw) {
+    if (__atomic_add_fetch(&rw->reader_count, -1, __ATOMIC_SEQ_CST) < 0)
+        if (__atomic_add_fetch(&rw->reader_wait, -1, __ATOMIC_SEQ_CST) == 0)
+            sem_post(&rw->writer_sem);                     /* last departing reader wakes the writer */
+}
+static void go_rw_lock(go_rwmutex *rw) {
+    pthread_mutex_lock(&rw->w);
+    int32_t r = __atomic_add_fetch(&rw->reader_count, -GO_RWMUTEX_MAX_READERS, __ATOMIC_SEQ_CST) + GO_RWMUTEX_MAX_READERS;
+    if (r != 0 && __atomic_add_fetch(&rw->reader_wait, r, __ATOMIC_SEQ_CST) != 0)
+        while (sem_wait(&rw->writer_sem) != 0) {}
+}
+static void go_rw_unlock(go_rwmutex *rw) {
+    int32_t r = __atomic_add_fetch(&rw->reader_count, GO_RWMUTEX_MAX_READERS, __ATOMIC_SEQ_CST);
+    for (int32_t i = 0; i < r; i++) sem_post(&rw->reader_sem);
+    pthread_mutex_unlock(&rw->w);
+}
+
 typedef struct lho_ms {
-    pthread_rwlock_t histogram_mu, counter_mu, counter_store_mu, histogram_count_mu;
+    go_rwmutex histogram_mu, counter_mu, counter_store_mu, histogram_count_mu;
     histo_map histogram_cache;
     counter_map counter_cache, counter_store, histogram_count_store;
     double percentiles[32]; char plabels[32][24]; int np;
@@ -568,10 +607,10 @@ static void counter_map_free(counter_map *m) {
 /* NewMetricSystem, metrics.go:143-195 (default percentile labels :145-155). */
 LHO_EXPORT lho_ms *lho_ms_new(void) {
     lho_ms *ms = (lho_ms *)calloc(1, sizeof(lho_ms));
-    pthread_rwlock_init(&ms->histogram_mu, NULL);
-    pthread_rwlock_init(&ms->counter_mu, NULL);
-    pthread_rwlock_init(&ms->counter_store_mu, NULL);
-    pthread_rwlock_init(&ms->histogram_count_mu, NULL);
+    go_rw_init(&ms->histogram_mu);
+    go_rw_init(&ms->counter_mu);
+    go_rw_init(&ms->counter_store_mu);
+    go_rw_init(&ms->histogram_count_mu);
     static const char *labels[9] = {"%s_min", "%s_50", "%s_75", "%s_90", "%s_95", "%s_99", "%s_99.9", "%s_99.99", "%s_max"};
     static const double ps[9] = {0, .5, .75, .9, .95, .99, .999, .9999, 1};
     ms->np = 9;
@@ -597,36 +636,36 @@ LHO_EXPORT void lho_ms_specify_percentiles(lho_ms *ms, int np, const char *const
 /* Histogram, metrics.go:273-295. */
 LHO_EXPORT void lho_ms_histogram(lho_ms *ms, const char *name, double value) {
     int16_t c = lho_compress(value);
-    pthread_rwlock_rdlock(&ms->histogram_mu);
+    go_rw_rlock(&ms->histogram_mu);
     histo_entry *h = histo_map_find(&ms->histogram_cache, name);
     uint64_t *cell = h ? bucket_map_find(&h->buckets, c) : NULL;
     if (cell) {
         __atomic_fetch_add(cell, 1, __ATOMIC_SEQ_CST);
-        pthread_rwlock_unlock(&ms->histogram_mu);
+        go_rw_runlock(&ms->histogram_mu);
         return;
     }
-    pthread_rwlock_unlock(&ms->histogram_mu);
-    pthread_rwlock_wrlock(&ms->histogram_mu);
+    go_rw_runlock(&ms->histogram_mu);
+    go_rw_lock(&ms->histogram_mu);
     h = histo_map_insert(&ms->histogram_cache, name);
     cell = bucket_map_insert(&h->buckets, c);
     __atomic_fetch_add(cell, 1, __ATOMIC_SEQ_CST);
-    pthread_rwlock_unlock(&ms->histogram_mu);
+    go_rw_unlock(&ms->histogram_mu);
 }
 
 /* Counter, metrics.go:251-269. */
 LHO_EXPORT void lho_ms_counter(lho_ms *ms, const char *name, uint64_t amount) {
-    pthread_rwlock_rdlock(&ms->counter_mu);
+    go_rw_rlock(&ms->counter_mu);
     counter_entry *e = counter_map_find(&ms->counter_cache, name);
     if (e) {
         __atomic_fetch_add(&e->val, amount, __ATOMIC_SEQ_CST);
-        pthread_rwlock_unlock(&ms->counter_mu);
+        go_rw_runlock(&ms->counter_mu);
         return;
     }
-    pthread_rwlock_unlock(&ms->counter_mu);
-    pthread_rwlock_wrlock(&ms->counter_mu);
+    go_rw_runlock(&ms->counter_mu);
+    go_rw_lock(&ms->counter_mu);
     e = counter_map_insert(&ms->counter_cache, name);
     __atomic_fetch_add(&e->val, amount, __ATOMIC_SEQ_CST);
-    pthread_rwlock_unlock(&ms->counter_mu);
+    go_rw_unlock(&ms->counter_mu);
 }
 
 /*
@@ -656,12 +695,12 @@ static void fmt_label(char *dst, size_t cap, const char *label, const char *name
 LHO_EXPORT void lho_ms_collect_and_process(lho_ms *ms, lho_emit_fn emit, void *ctx) {
     char buf[512], nm[512];
     /* swap counter cache, metrics.go:425-428 */
-    pthread_rwlock_wrlock(&ms->counter_mu);
+    go_rw_lock(&ms->counter_mu);
     counter_map fresh = ms->counter_cache;
     memset(&ms->counter_cache, 0, sizeof(counter_map));
-    pthread_rwlock_unlock(&ms->counter_mu);
+    go_rw_unlock(&ms->counter_mu);
     /* rates :430-433; fold into store :435-453 */
-    pthread_rwlock_wrlock(&ms->counter_store_mu);
+    go_rw_lock(&ms->counter_store_mu);
     for (uint32_t i = 0; i < fresh.cap; i++) {
         if (!fresh.e[i].name) continue;
         emit(ctx, 1, fresh.e[i].name, 0, fresh.e[i].val, 0);
@@ -675,14 +714,14 @@ LHO_EXPORT void lho_ms_collect_and_process(lho_ms *ms, lho_emit_fn emit, void *c
         emit(ctx, 0, ms->counter_store.e[i].name, 0, ms->counter_store.e[i].val, 0);
         emit(ctx, 3, ms->counter_store.e[i].name, 0, 0, (double)ms->counter_store.e[i].val);
     }
-    pthread_rwlock_unlock(&ms->counter_store_mu);
+    go_rw_unlock(&ms->counter_store_mu);
     counter_map_free(&fresh);
 
     /* swap histogram cache :460-463 */
-    pthread_rwlock_wrlock(&ms->histogram_mu);
+    go_rw_lock(&ms->histogram_mu);
     histo_map histos = ms->histogram_cache;
     memset(&ms->histogram_cache, 0, sizeof(histo_map));
-    pthread_rwlock_unlock(&ms->histogram_mu);
+    go_rw_unlock(&ms->histogram_mu);
 
     uint64_t *dense = (uint64_t *)malloc(65536 * 8);
     for (uint32_t hi = 0; hi < histos.cap; hi++) {
@@ -706,7 +745,7 @@ LHO_EXPORT void lho_ms_collect_and_process(lho_ms *ms, lho_emit_fn emit, void *c
             emit(ctx, 3, nm, 0, 0, pv[j]);
         }
         /* aggregate store :359-376 and reaper :590-608 */
-        pthread_rwlock_wrlock(&ms->histogram_count_mu);
+        go_rw_lock(&ms->histogram_count_mu);
         snprintf(buf, sizeof buf, "%s_sum", h->name);
         counter_entry *as = counter_map_insert(&ms->histogram_count_store, buf);
         as->val += lho_go_f64_to_u64(stats[1]);
@@ -715,7 +754,7 @@ LHO_EXPORT void lho_ms_collect_and_process(lho_ms *ms, lho_emit_fn emit, void *c
         counter_entry *ac = counter_map_insert(&ms->histogram_count_store, buf);
         ac->val += total;
         uint64_t agg_count = ac->val;
-        pthread_rwlock_unlock(&ms->histogram_count_mu);
+        go_rw_unlock(&ms->histogram_count_mu);
         if (agg_count > 0) {
             snprintf(buf, sizeof buf, "%s_agg_avg", h->name);   emit(ctx, 3, buf, 0, 0, (double)(agg_sum / agg_count));
             snprintf(buf, sizeof buf, "%s_agg_count", h->name); emit(ctx, 3, buf, 0, 0, (double)agg_count);
@@ -762,10 +801,10 @@ LHO_EXPORT double lho_ms_bench_ingest(lho_ms *ms, const double *v, const uint32_
 
 /* Fetch one raw bucket count from the live cache (test helper). */
 LHO_EXPORT uint64_t lho_ms_peek_bucket(lho_ms *ms, const char *name, int16_t key) {
-    pthread_rwlock_rdlock(&ms->histogram_mu);
+    go_rw_rlock(&ms->histogram_mu);
     histo_entry *h = histo_map_find(&ms->histogram_cache, name);
     uint64_t *c = h ? bucket_map_find(&h->buckets, key) : NULL;
     uint64_t r = c ? *c : 0;
-    pthread_rwlock_unlock(&ms->histogram_mu);
+    go_rw_runlock(&ms->histogram_mu);
     return r;
 }

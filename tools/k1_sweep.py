@@ -81,6 +81,27 @@ def main():
                 print(json.dumps(rec), flush=True)
                 out.write(json.dumps(rec) + "\n")
             ids.free()
+    # counters: C = 1024 ids, random and single-id (worst-case contention)
+    nc = min(a.n, 400_000_000)
+    amounts = eng.alloc(nc, np.uint64)
+    # amounts: reuse raw splitmix bits (kind 5 = raw u64)
+    eng._check(eng.lib.lh_gen_stream_f64(eng.h, 5, lh.DEFAULT_SEED, 0, nc, amounts.ptr, 0))
+    for idkind, nid in ((0, 1024), (0, 1)):
+        ids = eng.gen_ids_u16(idkind, nc, nid, lh.DEFAULT_SEED)
+        times = []
+        for it in range(a.iters + 2):
+            eng.counter_add_u16(ids, amounts, nc)
+            ms = eng.last_kernel_ms()
+            if it >= 2:
+                times.append(ms)
+        _, sp = eng.snapshot([0.5])
+        med = sorted(times)[len(times) // 2]
+        rec = {"kernel": "counter_add_u16", "n_ids": nid, "n": nc, "ms_median": med, "gops_s": nc / med / 1e6,
+               "gb_s": nc * 10 / med / 1e6}
+        print(json.dumps(rec), flush=True)
+        out.write(json.dumps(rec) + "\n")
+        ids.free()
+    amounts.free()
     d.free()
     eng.close()
 
