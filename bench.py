@@ -22,9 +22,7 @@ here: no Go toolchain in the image).
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -63,49 +61,66 @@ def peak_hbm():
 
 # ----------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons through NVML every ~2 ms while the timed region runs
+    (nvidia-smi -lms cannot resolve a region this short)."""
 
     def __init__(self, device_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        import threading
+        self.rows = []
+        self.stop_flag = False
+        self.ok = False
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            idx = device_index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[device_index])
+                except Exception:
+                    idx = device_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
         except Exception:
-            self.p = None
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.rows.append((sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
+        if not self.ok:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = []
-        for line in open(self.f.name):
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) >= 7:
-                try:
-                    rows.append((float(parts[0]), float(parts[1]), float(parts[2]), parts[3:7]))
-                except ValueError:
-                    pass
-        os.unlink(self.f.name)
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        nv = self.nv
+        rows = self.rows
         if not rows:
+            out["sm_max_mhz"] = self.max_sm
             return out
-        # "under load" = the busier half by power draw
-        rows.sort(key=lambda r: r[2])
-        load = rows[len(rows) // 2:]
-        sm = sorted(r[0] for r in load)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in rows for i in range(4) if r[3][i].lower().startswith("active")})
-        out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(r[1] for r in rows), reasons=reasons,
-                   samples=len(rows), power_w_max=max(r[2] for r in rows))
+        sm = sorted(r[0] for r in rows)
+        flags = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        reasons = sorted(k for k, bit in flags.items() if any(r[2] & bit for r in rows))
+        out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=self.max_sm, reasons=reasons, samples=len(rows),
+                   power_w_max=max(r[1] for r in rows), sm_mhz_min=sm[0])
         return out
 
 
@@ -248,10 +263,8 @@ def run_b200(a):
     d_ids = eng.gen_ids_u16(0, n, H, SEED, start=rank * n, stream=stream) if keyed else None
     torch.cuda.synchronize()
 
-    class _View:   # zero-copy torch view of the frozen bucket array for the all-reduce
-        def __init__(self, ptr, words):
-            self.__cuda_array_interface__ = {"shape": (words,), "typestr": "<i8", "data": (ptr, False), "version": 3}
-
+    from loghisto_b200.distributed import ShardedEngine
+    sharded = ShardedEngine(eng, local)
     kernel_ms = []
     allreduce_ms = []
 
@@ -261,27 +274,17 @@ def run_b200(a):
                 eng.ingest_keyed_f64_u16(d_ids, d_vals, n, stream=stream)
             else:
                 eng.ingest_f64(0, d_vals, n, stream=stream)
-            kernel_ms.append(None)    # filled after the step (events), see below
         else:
             if keyed:
                 eng.ingest_keyed_f64_u16_host(host_src[1], host_src[0], n)
             else:
                 eng.ingest_f64_host(0, host_src, n)
-        eng.snapshot_begin()
-        if world > 1:
-            v = eng.snapshot_device()
-            ext = torch.cuda.ExternalStream(v.stream, device=local)
-            with torch.cuda.stream(ext):
-                t = torch.as_tensor(_View(v.d_buckets, int(v.n_bucket_words)), device="cuda:%d" % local)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(ext)
-                dist.all_reduce(t)     # uint64 sum == int64 sum bit-for-bit (two's complement)
-                e1.record(ext)
-            allreduce_ms.append((e0, e1))
-        red = eng.snapshot_reduce(PERCENTILES)     # host-synchronous: D2H of count/sum/avg/percentiles
-        eng.snapshot_end()
+        # snapshot: swap, (all-reduce,) percentile reduction, host-synchronous D2H of the results
+        red, _ = sharded.snapshot(PERCENTILES)
         if host_src is None:
-            kernel_ms[-1] = eng.last_kernel_ms()
+            kernel_ms.append(eng.last_kernel_ms())
+            if world > 1:
+                allreduce_ms.append(sharded.last_allreduce_ms())
         return red
 
     def barrier():
@@ -316,7 +319,7 @@ def run_b200(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     kms = sum(kernel_ms) / len(kernel_ms)
-    ar_ms = (sum(e0.elapsed_time(e1) for e0, e1 in allreduce_ms) / len(allreduce_ms)) if allreduce_ms else 0.0
+    ar_ms = (sum(allreduce_ms) / len(allreduce_ms)) if allreduce_ms else 0.0
     count_ok = int(red.counts.sum()) == n * world
 
     # ---- host-fed leg (e2e)

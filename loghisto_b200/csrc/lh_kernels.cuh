@@ -396,109 +396,116 @@ k_counter_add(const IdT *__restrict__ ids, const unsigned long long *__restrict_
 }
 
 // ---------------------------------------------------------------------- K3
-// One CTA per histogram.  Thread t owns the 64 consecutive keys
-// [-32768 + 64 t, -32768 + 64 t + 63] (ascending key == ascending value, the
-// order percentile() sorts into, metrics.go:409).
+// One CTA per histogram, 32 warps.  Warp w owns the 2048 consecutive keys
+// [-32768 + 2048 w, +2047] (ascending key == ascending value, the order
+// percentile() sorts into, metrics.go:409) and reads them as 64 coalesced
+// 256-byte rows.  Pass 1: per-warp count / sum / non-empty totals, then a scan
+// over the 32 warp totals.  Pass 2: the warp whose range contains a
+// percentile's crossing walks its rows again (L2 hits) with a warp prefix sum
+// and applies the reference's rule float64(sofar)/float64(total) >= p
+// (metrics.go:413) to non-empty buckets only.
 constexpr int K3_THREADS = 1024;
-constexpr int K3_PER = 65536 / K3_THREADS;
+constexpr int K3_WARP_KEYS = 2048;
 
 __global__ void __launch_bounds__(K3_THREADS)
 k_reduce(const unsigned long long *__restrict__ buckets, const double *__restrict__ decomp,
          const double *__restrict__ ps, int np, unsigned long long *__restrict__ out_count,
          double *__restrict__ out_sum, double *__restrict__ out_avg, int *__restrict__ out_pkeys,
          double *__restrict__ out_pvals, uint32_t *__restrict__ out_nnz) {
-    __shared__ unsigned long long s_warp_cnt[32];
-    __shared__ double s_warp_sum[32];
-    __shared__ unsigned int s_warp_nnz[32];
+    __shared__ unsigned long long s_cnt[32];    // per-warp totals, then exclusive prefix
+    __shared__ unsigned long long s_tot[32];    // per-warp totals (kept)
+    __shared__ double s_sum[32];
+    __shared__ unsigned int s_nnz[32];
     __shared__ int s_owner[LH_MAX_PCT];
     __shared__ unsigned long long s_total;
     const int h = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const unsigned long long *hb = buckets + (size_t)h * 65536u;
+    const int key0 = -32768 + warp * K3_WARP_KEYS;
 
-    unsigned long long c[K3_PER];
     unsigned long long mine = 0;
     double msum = 0.0;
     unsigned int nnz = 0;
-#pragma unroll 8
-    for (int j = 0; j < K3_PER; j++) {
-        int key = -32768 + t * K3_PER + j;
-        unsigned int slot = (unsigned int)key & 0xFFFFu;
-        c[j] = hb[slot];
-        if (c[j]) { mine += c[j]; msum += decomp[slot] * (double)c[j]; nnz++; }
+#pragma unroll 4
+    for (int r = 0; r < K3_WARP_KEYS / 32; r++) {
+        unsigned int slot = (unsigned int)(key0 + r * 32 + lane) & 0xFFFFu;
+        unsigned long long c = hb[slot];
+        if (c) { mine += c; msum += decomp[slot] * (double)c; nnz++; }
     }
-    // block-wide inclusive scan of `mine` (warp shuffle + per-warp totals)
-    unsigned long long incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= o) incl += y;
-    }
-    double wsum = msum;
-    unsigned int wnnz = nnz;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        wsum += __shfl_xor_sync(0xFFFFFFFFu, wsum, o);
-        wnnz += __shfl_xor_sync(0xFFFFFFFFu, wnnz, o);
+        mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
+        msum += __shfl_xor_sync(0xFFFFFFFFu, msum, o);
+        nnz += __shfl_xor_sync(0xFFFFFFFFu, nnz, o);
     }
-    if (lane == 31) s_warp_cnt[warp] = incl;
-    if (lane == 0) { s_warp_sum[warp] = wsum; s_warp_nnz[warp] = wnnz; }
+    if (lane == 0) { s_cnt[warp] = mine; s_tot[warp] = mine; s_sum[warp] = msum; s_nnz[warp] = nnz; }
     if (t < LH_MAX_PCT) s_owner[t] = 0x7FFFFFFF;
     __syncthreads();
     if (warp == 0) {
-        unsigned long long w = s_warp_cnt[lane];
-        unsigned long long wi = w;
+        unsigned long long w = s_cnt[lane], wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, wi, o);
             if (lane >= o) wi += y;
         }
-        s_warp_cnt[lane] = wi - w;   // exclusive prefix of warp totals
+        s_cnt[lane] = wi - w;
         if (lane == 31) s_total = wi;
-        double ts = s_warp_sum[lane];
-        unsigned int tn = s_warp_nnz[lane];
+        double ts = s_sum[lane];
+        unsigned int tn = s_nnz[lane];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             ts += __shfl_xor_sync(0xFFFFFFFFu, ts, o);
             tn += __shfl_xor_sync(0xFFFFFFFFu, tn, o);
         }
-        if (lane == 0) { s_warp_sum[0] = ts; s_warp_nnz[0] = tn; }
+        if (lane == 0) { s_sum[0] = ts; s_nnz[0] = tn; }
     }
     __syncthreads();
     const unsigned long long total = s_total;
-    const unsigned long long end_incl = s_warp_cnt[warp] + incl;   // counts up to and including my keys
     const double ftotal = (double)total;
-    // which thread owns each percentile: the first non-empty one whose inclusive prefix satisfies the rule
-    if (mine) {
+    // owner of percentile j = first non-empty warp whose inclusive prefix satisfies the rule
+    if (lane == 0 && s_tot[warp]) {
+        const unsigned long long end_incl = s_cnt[warp] + s_tot[warp];
         for (int j = 0; j < np; j++)
-            if (__ddiv_rn((double)end_incl, ftotal) >= ps[j]) atomicMin(&s_owner[j], t);
+            if (__ddiv_rn((double)end_incl, ftotal) >= ps[j]) atomicMin(&s_owner[j], warp);
     }
     __syncthreads();
-    for (int j = 0; j < np; j++) {
-        if (s_owner[j] == t) {
-            unsigned long long sofar = end_incl - mine;
-            const double p = ps[j];
-#pragma unroll 8
-            for (int q = 0; q < K3_PER; q++) {
-                if (!c[q]) continue;
-                sofar += c[q];
-                if (__ddiv_rn((double)sofar, ftotal) >= p) {   // metrics.go:413
-                    int key = -32768 + t * K3_PER + q;
-                    out_pkeys[(size_t)h * np + j] = key;
-                    out_pvals[(size_t)h * np + j] = decomp[(unsigned int)key & 0xFFFFu];
-                    break;
+    unsigned int pending = 0;
+    for (int j = 0; j < np; j++) if (s_owner[j] == warp) pending |= 1u << j;
+    if (pending) {
+        unsigned long long sofar = s_cnt[warp];
+        for (int r = 0; r < K3_WARP_KEYS / 32 && pending; r++) {
+            int key = key0 + r * 32 + lane;
+            unsigned long long c = hb[(unsigned int)key & 0xFFFFu];
+            unsigned long long incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            const double frac = __ddiv_rn((double)(sofar + incl), ftotal);
+            for (int j = 0; j < np; j++) {
+                if (!(pending >> j & 1u)) continue;
+                unsigned int hit = __ballot_sync(0xFFFFFFFFu, c != 0 && frac >= ps[j]);
+                if (hit) {
+                    if (lane == __ffs(hit) - 1) {
+                        out_pkeys[(size_t)h * np + j] = key;
+                        out_pvals[(size_t)h * np + j] = decomp[(unsigned int)key & 0xFFFFu];
+                    }
+                    pending &= ~(1u << j);
                 }
             }
-        }
-        if (t == 0 && s_owner[j] == 0x7FFFFFFF) {   // percentile() error: key omitted by the caller
-            out_pkeys[(size_t)h * np + j] = (int)0x80000000;
-            out_pvals[(size_t)h * np + j] = __longlong_as_double(0x7FF8000000000000ll);
+            sofar += __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
     }
     if (t == 0) {
+        for (int j = 0; j < np; j++)
+            if (s_owner[j] == 0x7FFFFFFF) {   // percentile() error (p > 1, NaN, empty): key omitted by the caller
+                out_pkeys[(size_t)h * np + j] = (int)0x80000000;
+                out_pvals[(size_t)h * np + j] = __longlong_as_double(0x7FF8000000000000ll);
+            }
         out_count[h] = total;
-        out_sum[h] = s_warp_sum[0];
-        out_avg[h] = __ddiv_rn(s_warp_sum[0], ftotal);    // metrics.go:356 (NaN when empty)
-        out_nnz[h] = s_warp_nnz[0];
+        out_sum[h] = s_sum[0];
+        out_avg[h] = __ddiv_rn(s_sum[0], ftotal);    // metrics.go:356 (NaN when empty)
+        out_nnz[h] = s_nnz[0];
     }
 }
 
@@ -526,18 +533,12 @@ k_export(const unsigned long long *__restrict__ buckets, const uint32_t *__restr
     __shared__ unsigned int s_warp[32];
     const int h = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const unsigned long long *hb = buckets + (size_t)h * 65536u;
-    unsigned long long c[K3_PER];
+    const int key0 = -32768 + warp * K3_WARP_KEYS;
     unsigned int nnz = 0;
-#pragma unroll 8
-    for (int j = 0; j < K3_PER; j++) {
-        int key = -32768 + t * K3_PER + j;
-        c[j] = hb[(unsigned int)key & 0xFFFFu];
-        nnz += c[j] != 0;
-    }
-    unsigned int incl = nnz;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { unsigned int y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
-    if (lane == 31) s_warp[warp] = incl;
+#pragma unroll 4
+    for (int r = 0; r < K3_WARP_KEYS / 32; r++)
+        nnz += __popc(__ballot_sync(0xFFFFFFFFu, hb[(unsigned int)(key0 + r * 32 + lane) & 0xFFFFu] != 0));
+    if (lane == 0) s_warp[warp] = nnz;     // every lane holds the warp total
     __syncthreads();
     if (warp == 0) {
         unsigned int w = s_warp[lane], wi = w;
@@ -546,10 +547,18 @@ k_export(const unsigned long long *__restrict__ buckets, const uint32_t *__restr
         s_warp[lane] = wi - w;
     }
     __syncthreads();
-    unsigned int pos = offsets[h] + s_warp[warp] + incl - nnz;
-#pragma unroll 8
-    for (int j = 0; j < K3_PER; j++) {
-        if (c[j]) { out_keys[pos] = (short)(-32768 + t * K3_PER + j); out_counts[pos] = c[j]; pos++; }
+    if (!nnz) return;
+    unsigned int pos = offsets[h] + s_warp[warp];
+    for (int r = 0; r < K3_WARP_KEYS / 32; r++) {
+        int key = key0 + r * 32 + lane;
+        unsigned long long c = hb[(unsigned int)key & 0xFFFFu];
+        unsigned int m = __ballot_sync(0xFFFFFFFFu, c != 0);
+        if (c) {
+            unsigned int p = pos + __popc(m & ((1u << lane) - 1u));
+            out_keys[p] = (short)key;
+            out_counts[p] = c;
+        }
+        pos += __popc(m);
     }
 }
 

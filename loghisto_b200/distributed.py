@@ -1,0 +1,87 @@
+"""Multi-GPU plumbing for the sharded sample stream.
+
+The stream shards with no data-path exchange: rank r ingests the contiguous
+index range shard_range(r, world, n_total) into its own bucket arrays.  The
+only collective is one sum all-reduce of the frozen uint64 bucket (and counter)
+arrays per snapshot, issued through torch.distributed (NCCL over NVLink on
+GPUs, gloo in the CPU tests).  Integer sums are associative, so the reduced
+counts are bit-identical to a single-GPU run over the whole stream; uint64
+addition and int64 addition produce the same bits, which is why an int64 view
+is what gets reduced.
+"""
+from __future__ import annotations
+
+
+def shard_range(rank: int, world: int, n_total: int) -> tuple[int, int]:
+    """[start, stop) of rank's contiguous slice; the first n_total % world ranks take one extra sample."""
+    base, extra = divmod(n_total, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def allreduce_sum_u64(t, group=None):
+    """In-place sum all-reduce of a tensor holding uint64 bit patterns (dtype int64 or uint64 view)."""
+    import torch
+    import torch.distributed as dist
+    if t.dtype == torch.uint64:
+        t = t.view(torch.int64)
+    assert t.dtype == torch.int64
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+class _CudaView:
+    """Zero-copy __cuda_array_interface__ wrapper over a raw device pointer."""
+
+    def __init__(self, ptr: int, words: int):
+        self.__cuda_array_interface__ = {"shape": (words,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+
+class ShardedEngine:
+    """An Engine per rank plus the snapshot-time all-reduce.
+
+    snapshot() = lh_snapshot_begin -> all-reduce of the frozen device arrays on the snapshot stream ->
+    lh_snapshot_reduce (+ export) -> lh_snapshot_end, so every rank ends with the global percentiles.
+    """
+
+    def __init__(self, engine, device_index: int, group=None):
+        import torch.distributed as dist
+        self.engine = engine
+        self.device_index = device_index
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.last_allreduce_events = None
+
+    def snapshot(self, percentiles, export: bool = False, counters: bool = False):
+        import torch
+        eng = self.engine
+        eng.snapshot_begin()
+        try:
+            if self.world > 1:
+                v = eng.snapshot_device()
+                ext = torch.cuda.ExternalStream(int(v.stream), device=self.device_index)
+                with torch.cuda.stream(ext):
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    t = torch.as_tensor(_CudaView(int(v.d_buckets), int(v.n_bucket_words)),
+                                        device="cuda:%d" % self.device_index)
+                    e0.record(ext)
+                    allreduce_sum_u64(t, self.group)
+                    if counters:
+                        c = torch.as_tensor(_CudaView(int(v.d_counters), int(v.n_counter_words)),
+                                            device="cuda:%d" % self.device_index)
+                        allreduce_sum_u64(c, self.group)
+                    e1.record(ext)
+                self.last_allreduce_events = (e0, e1)
+            red = eng.snapshot_reduce(percentiles)
+            sp = eng.snapshot_export() if export else None
+        finally:
+            eng.snapshot_end()
+        return red, sp
+
+    def last_allreduce_ms(self) -> float:
+        if not self.last_allreduce_events:
+            return 0.0
+        e0, e1 = self.last_allreduce_events
+        e1.synchronize()
+        return float(e0.elapsed_time(e1))
