@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--k1-grid-mult", type=int, default=0, help="override the K1 waves-per-launch tuning")
+    ap.add_argument("--k1-variant", type=int, default=-1)
     return ap.parse_args()
 
 
@@ -248,6 +250,7 @@ def run_b200(a):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")   # the bucket all-reduce outranks the ingest kernel
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -258,6 +261,10 @@ def run_b200(a):
     bytes_per_sample = 10 if keyed else 8
 
     eng = lh.Engine(device=local, max_histograms=H, max_counters=1)
+    if a.k1_grid_mult:
+        eng.tune("k1_grid_mult", a.k1_grid_mult)
+    if a.k1_variant >= 0:
+        eng.tune("k1", a.k1_variant)
     stream = torch.cuda.current_stream()
     d_vals = eng.gen_stream(kind, n, SEED, start=rank * n, stream=stream)
     d_ids = eng.gen_ids_u16(0, n, H, SEED, start=rank * n, stream=stream) if keyed else None
@@ -268,7 +275,7 @@ def run_b200(a):
     kernel_ms = []
     allreduce_ms = []
 
-    def step(host_src=None):
+    def ingest(host_src=None):
         if host_src is None:
             if keyed:
                 eng.ingest_keyed_f64_u16(d_ids, d_vals, n, stream=stream)
@@ -279,12 +286,25 @@ def run_b200(a):
                 eng.ingest_keyed_f64_u16_host(host_src[1], host_src[0], n)
             else:
                 eng.ingest_f64_host(0, host_src, n)
-        # snapshot: swap, (all-reduce,) percentile reduction, host-synchronous D2H of the results
-        red, _ = sharded.snapshot(PERCENTILES)
-        if host_src is None:
-            kernel_ms.append(eng.last_kernel_ms())
-            if world > 1:
-                allreduce_ms.append(sharded.last_allreduce_ms())
+
+    def run_steps(k, host_src=None, record=False):
+        """k steps.  Step i = ingest of batch i, then its snapshot (buffer swap, all-reduce, percentile
+        reduction, D2H of the results).  The snapshot of step i is only enqueued (high-priority stream, spare
+        buffer) before batch i+1 is launched, as loghisto's reaper overlaps processing with the next interval
+        (metrics.go:583-587); its results are collected on the host before step i+1's snapshot begins.  All k
+        ingests and all k snapshots complete inside the call."""
+        red = None
+        ingest(host_src)
+        for i in range(k):
+            seq = eng.ingest_seq()
+            h = sharded.snapshot_async(PERCENTILES)
+            if i + 1 < k:
+                ingest(host_src)
+            red = sharded.result(h)
+            if record and host_src is None:
+                kernel_ms.append(eng.kernel_ms(seq))      # CUDA events around batch i's ingest kernel
+                if world > 1:
+                    allreduce_ms.append(sharded.last_allreduce_ms())
         return red
 
     def barrier():
@@ -293,18 +313,16 @@ def run_b200(a):
         torch.cuda.synchronize()
 
     # ---- device-resident leg
-    for _ in range(max(a.warmup, 3)):
-        red = step()
-    del kernel_ms[:]
+    run_steps(max(a.warmup, 3))
     del allreduce_ms[:]
+    del kernel_ms[:]
     launches0 = eng.stats()["kernel_launches"]
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record(stream)
     t_wall = time.perf_counter()
-    for _ in range(a.steps):
-        red = step()
+    red = run_steps(a.steps, record=True)
     e_stop.record(stream)
     barrier()
     wall_ms = (time.perf_counter() - t_wall) * 1e3
@@ -334,12 +352,10 @@ def run_b200(a):
             hi = eng.pinned(n, np.uint16)
             eng._check(eng.lib.lh_memcpy_d2h(eng.h, hi.ptr, d_ids.ptr, n * 2))
             hsrc = (hv.array, hi.array)
-        step(hsrc)
-        step(hsrc)
+        run_steps(2, hsrc)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(ksteps):
-            red_h = step(hsrc)
+        red_h = run_steps(ksteps, hsrc)
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
         t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")

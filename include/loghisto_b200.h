@@ -169,6 +169,14 @@ LH_API lh_status lh_snapshot_reduce(lh_ctx *ctx, const double *percentiles, uint
                              uint64_t *counts, double *sums, double *avgs, int32_t *pkeys,
                              double *pvals);
 
+/* Asynchronous form for pipelined callers (the reaper overlaps the next interval's ingest with this
+ * interval's reduction): enqueue the reduction of the open snapshot and get a ticket.  The frozen
+ * arrays may be released with lh_snapshot_end right away; lh_snapshot_result waits for the ticket and
+ * copies its results out.  Two tickets may be in flight; a ticket expires when the second-next is issued. */
+LH_API lh_status lh_snapshot_reduce_async(lh_ctx *ctx, const double *percentiles, uint32_t np, uint64_t *ticket);
+LH_API lh_status lh_snapshot_result(lh_ctx *ctx, uint64_t ticket, uint64_t *counts, double *sums, double *avgs,
+                                    int32_t *pkeys, double *pvals);
+
 typedef struct lh_sparse {
     const uint32_t *offsets;   /* [H+1] prefix offsets into keys/counts */
     const int16_t *keys;       /* ascending per histogram */
@@ -231,6 +239,10 @@ LH_API const char *lh_k1_variant_name(lh_ctx *ctx, int32_t i);
 /* time the last `lh_ingest_*` launch range on its stream: CUDA events bracket
  * every ingest kernel; returns the device time of the most recent one in ms */
 LH_API lh_status lh_last_kernel_ms(lh_ctx *ctx, float *ms);
+/* lh_ingest_seq = number of ingest calls issued so far (1-based sequence number of the latest);
+ * lh_kernel_ms = device time of ingest call `seq` (its events stay available for the next 15 calls) */
+LH_API uint64_t lh_ingest_seq(lh_ctx *ctx);
+LH_API lh_status lh_kernel_ms(lh_ctx *ctx, uint64_t seq, float *ms);
 
 #ifdef __cplusplus
 }

@@ -84,6 +84,8 @@ SIGNATURES = {
     "lh_snapshot_begin": (_i32, [_vp]),
     "lh_snapshot_device": (_i32, [_vp, C.POINTER(lh_device_view)]),
     "lh_snapshot_reduce": (_i32, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "lh_snapshot_reduce_async": (_i32, [_vp, _vp, _u32, C.POINTER(_u64)]),
+    "lh_snapshot_result": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _vp]),
     "lh_snapshot_export": (_i32, [_vp, C.POINTER(lh_sparse)]),
     "lh_snapshot_copy_histogram": (_i32, [_vp, _u32, _vp]),
     "lh_snapshot_end": (_i32, [_vp]),
@@ -105,6 +107,8 @@ SIGNATURES = {
     "lh_k1_variant_count": (_i32, []),
     "lh_k1_variant_name": (C.c_char_p, [_vp, _i32]),
     "lh_last_kernel_ms": (_i32, [_vp, C.POINTER(C.c_float)]),
+    "lh_ingest_seq": (_u64, [_vp]),
+    "lh_kernel_ms": (_i32, [_vp, _u64, C.POINTER(C.c_float)]),
 }
 
 _lib = None

@@ -99,14 +99,17 @@ struct lh_ctx {
     double *d_decomp = nullptr;
     unsigned long long *d_dropped = nullptr;
     // reduce / export scratch
-    double *d_ps = nullptr;
-    unsigned long long *d_r_count = nullptr;
-    double *d_r_sum = nullptr, *d_r_avg = nullptr, *d_r_pvals = nullptr;
-    int *d_r_pkeys = nullptr;
+    // two result slots (ticket & 1): packed [count H][sum H][avg H][pvals H*np][pkeys H*np]
+    double *d_ps[2] = {nullptr, nullptr};
+    char *d_res[2] = {nullptr, nullptr};
+    char *h_res[2] = {nullptr, nullptr};
+    cudaEvent_t res_done[2] = {nullptr, nullptr};
+    uint32_t res_np[2] = {0, 0};
+    uint64_t res_ticket[2] = {0, 0};
+    uint64_t next_ticket = 1;
     uint32_t *d_nnz = nullptr, *d_offsets = nullptr;
     short *d_x_keys = nullptr; unsigned long long *d_x_counts = nullptr; size_t x_cap = 0;
     // pinned host mirrors
-    void *h_scratch = nullptr; size_t h_scratch_bytes = 0;
     uint32_t *h_offsets = nullptr;
     short *h_x_keys = nullptr; unsigned long long *h_x_counts = nullptr; size_t hx_cap = 0;
     unsigned long long *h_counter_deltas = nullptr;
@@ -120,7 +123,11 @@ struct lh_ctx {
     int keyed_blocks_per_sm = 8;
     K1Variant k1[kNumK1Variants];
     // timing of the most recent ingest kernel
-    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    // CUDA events bracket every ingest launch; a ring keeps the last kTimingRing of them
+    static constexpr int kTimingRing = 16;
+    cudaEvent_t ev_t0s[kTimingRing] = {}, ev_t1s[kTimingRing] = {};
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // the pair of the launch being issued
+    uint64_t ingest_seq = 0;                         // launches issued so far
     bool timing_valid = false;
     // stats
     lh_stats stats{};
@@ -161,6 +168,13 @@ lh_status after_write(lh_ctx *ctx, int b, cudaStream_t s) {
     return LH_OK;
 }
 
+void next_timing_slot(lh_ctx *ctx) {
+    const int i = (int)(ctx->ingest_seq % lh_ctx::kTimingRing);
+    ctx->ev_t0 = ctx->ev_t0s[i];
+    ctx->ev_t1 = ctx->ev_t1s[i];
+    ctx->ingest_seq++;
+}
+
 cudaStream_t pick_stream(lh_ctx *ctx, void *stream) { return stream ? (cudaStream_t)stream : ctx->ingest_stream; }
 
 int grid_1d(lh_ctx *ctx, size_t n, int threads, int per_thread, int blocks_per_sm) {
@@ -181,6 +195,7 @@ lh_status launch_single(lh_ctx *ctx, uint32_t hid, const double *d_values, size_
     // a CTA's uint32 sub-histogram must not overflow: bound samples per launch
     const size_t kMaxPerLaunch = (size_t)1 << 36;
     size_t done = 0;
+    next_timing_slot(ctx);
     LH_CUDA(ctx, cudaEventRecord(ctx->ev_t0, s));
     while (done < n) {
         size_t m = std::min(n - done, kMaxPerLaunch);
@@ -224,6 +239,7 @@ lh_status launch_keyed(lh_ctx *ctx, const IdT *d_ids, const ValT *d_vals, size_t
     lh_status st = before_write(ctx, b, s);
     if (st != LH_OK) return st;
     constexpr int T = 256;
+    next_timing_slot(ctx);
     LH_CUDA(ctx, cudaEventRecord(ctx->ev_t0, s));
     size_t done = 0;
     while (done < n) {
@@ -271,6 +287,7 @@ lh_status launch_counter(lh_ctx *ctx, const IdT *d_ids, const uint64_t *d_amount
     const int b = ctx->active;
     lh_status st = before_write(ctx, b, s);
     if (st != LH_OK) return st;
+    next_timing_slot(ctx);
     LH_CUDA(ctx, cudaEventRecord(ctx->ev_t0, s));
     if (n) {
         constexpr int T = 512;
@@ -304,15 +321,6 @@ lh_status slot_wait_free(lh_ctx *ctx, int *out) {
     LH_CUDA(ctx, cudaEventSynchronize(ctx->slots[best].done));
     ctx->slots[best].state = SLOT_FREE;
     *out = best;
-    return LH_OK;
-}
-
-lh_status ensure_host_scratch(lh_ctx *ctx, size_t bytes) {
-    if (ctx->h_scratch_bytes >= bytes) return LH_OK;
-    if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
-    ctx->h_scratch = nullptr; ctx->h_scratch_bytes = 0;
-    LH_CUDA(ctx, cudaMallocHost(&ctx->h_scratch, bytes));
-    ctx->h_scratch_bytes = bytes;
     return LH_OK;
 }
 
@@ -379,9 +387,15 @@ extern "C" lh_status lh_create(const lh_config *cfg, lh_ctx **out) {
     }
     ctx->sm_count = prop.multiProcessorCount;
     LH_CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->ingest_stream, cudaStreamNonBlocking));
-    LH_CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->snap_stream, cudaStreamNonBlocking));
-    LH_CREATE_CUDA(cudaEventCreate(&ctx->ev_t0));
-    LH_CREATE_CUDA(cudaEventCreate(&ctx->ev_t1));
+    {   // the snapshot stream outranks ingest: its small kernels slot in as soon as any ingest CTA retires
+        int least = 0, greatest = 0;
+        LH_CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        LH_CREATE_CUDA(cudaStreamCreateWithPriority(&ctx->snap_stream, cudaStreamNonBlocking, greatest));
+    }
+    for (int i = 0; i < lh_ctx::kTimingRing; i++) {
+        LH_CREATE_CUDA(cudaEventCreate(&ctx->ev_t0s[i]));
+        LH_CREATE_CUDA(cudaEventCreate(&ctx->ev_t1s[i]));
+    }
 
     const size_t bucket_bytes = (size_t)ctx->H * 65536u * 8u, counter_bytes = (size_t)ctx->C * 8u;
     for (int b = 0; b < 2; b++) {
@@ -399,12 +413,13 @@ extern "C" lh_status lh_create(const lh_config *cfg, lh_ctx **out) {
     LH_CREATE_CUDA(cudaGetLastError());
     LH_CREATE_CUDA(cudaMalloc(&ctx->d_dropped, 8));
     LH_CREATE_CUDA(cudaMemsetAsync(ctx->d_dropped, 0, 8, ctx->snap_stream));
-    LH_CREATE_CUDA(cudaMalloc(&ctx->d_ps, LH_MAX_PERCENTILES * sizeof(double)));
-    LH_CREATE_CUDA(cudaMalloc(&ctx->d_r_count, (size_t)ctx->H * 8));
-    LH_CREATE_CUDA(cudaMalloc(&ctx->d_r_sum, (size_t)ctx->H * 8));
-    LH_CREATE_CUDA(cudaMalloc(&ctx->d_r_avg, (size_t)ctx->H * 8));
-    LH_CREATE_CUDA(cudaMalloc(&ctx->d_r_pkeys, (size_t)ctx->H * LH_MAX_PERCENTILES * 4));
-    LH_CREATE_CUDA(cudaMalloc(&ctx->d_r_pvals, (size_t)ctx->H * LH_MAX_PERCENTILES * 8));
+    for (int i = 0; i < 2; i++) {
+        const size_t res_bytes = (size_t)ctx->H * (24 + LH_MAX_PERCENTILES * 12);
+        LH_CREATE_CUDA(cudaMalloc(&ctx->d_ps[i], LH_MAX_PERCENTILES * sizeof(double)));
+        LH_CREATE_CUDA(cudaMalloc(&ctx->d_res[i], res_bytes));
+        LH_CREATE_CUDA(cudaMallocHost(&ctx->h_res[i], res_bytes));
+        LH_CREATE_CUDA(cudaEventCreateWithFlags(&ctx->res_done[i], cudaEventDisableTiming));
+    }
     LH_CREATE_CUDA(cudaMalloc(&ctx->d_nnz, (size_t)ctx->H * 4));
     LH_CREATE_CUDA(cudaMalloc(&ctx->d_offsets, ((size_t)ctx->H + 1) * 4));
     LH_CREATE_CUDA(cudaMallocHost(&ctx->h_offsets, ((size_t)ctx->H + 1) * 4));
@@ -441,11 +456,14 @@ extern "C" lh_status lh_destroy(lh_ctx *ctx) {
         if (ctx->buf[b].cleared) cudaEventDestroy(ctx->buf[b].cleared);
         for (auto &w : ctx->buf[b].writers) cudaEventDestroy(w.ev);
     }
-    cudaFree(ctx->d_decomp); cudaFree(ctx->d_dropped); cudaFree(ctx->d_ps);
-    cudaFree(ctx->d_r_count); cudaFree(ctx->d_r_sum); cudaFree(ctx->d_r_avg);
-    cudaFree(ctx->d_r_pkeys); cudaFree(ctx->d_r_pvals); cudaFree(ctx->d_nnz); cudaFree(ctx->d_offsets);
+    cudaFree(ctx->d_decomp); cudaFree(ctx->d_dropped);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(ctx->d_ps[i]); cudaFree(ctx->d_res[i]);
+        if (ctx->h_res[i]) cudaFreeHost(ctx->h_res[i]);
+        if (ctx->res_done[i]) cudaEventDestroy(ctx->res_done[i]);
+    }
+    cudaFree(ctx->d_nnz); cudaFree(ctx->d_offsets);
     cudaFree(ctx->d_x_keys); cudaFree(ctx->d_x_counts);
-    if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
     if (ctx->h_offsets) cudaFreeHost(ctx->h_offsets);
     if (ctx->h_x_keys) cudaFreeHost(ctx->h_x_keys);
     if (ctx->h_x_counts) cudaFreeHost(ctx->h_x_counts);
@@ -455,8 +473,10 @@ extern "C" lh_status lh_destroy(lh_ctx *ctx) {
         cudaFree(sl.d);
         if (sl.done) cudaEventDestroy(sl.done);
     }
-    if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
-    if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+    for (int i = 0; i < lh_ctx::kTimingRing; i++) {
+        if (ctx->ev_t0s[i]) cudaEventDestroy(ctx->ev_t0s[i]);
+        if (ctx->ev_t1s[i]) cudaEventDestroy(ctx->ev_t1s[i]);
+    }
     if (ctx->ingest_stream) cudaStreamDestroy(ctx->ingest_stream);
     if (ctx->snap_stream) cudaStreamDestroy(ctx->snap_stream);
     cudaGetLastError();
@@ -673,52 +693,86 @@ extern "C" lh_status lh_snapshot_device(lh_ctx *ctx, lh_device_view *out) {
 }
 
 namespace {
-lh_status run_reduce(lh_ctx *ctx, const double *ps, uint32_t np) {
+struct ResLayout { size_t count, sum, avg, pvals, pkeys, total; };
+ResLayout res_layout(size_t H, uint32_t np) {
+    ResLayout l;
+    l.count = 0; l.sum = H * 8; l.avg = H * 16; l.pvals = H * 24; l.pkeys = H * 24 + H * np * 8;
+    l.total = l.pkeys + H * np * 4;
+    return l;
+}
+
+// enqueue K3 + one packed D2H for the open snapshot into result slot `slot`
+lh_status enqueue_reduce(lh_ctx *ctx, const double *ps, uint32_t np, int slot) {
     const int f = ctx->active ^ 1;
-    if (np) LH_CUDA(ctx, cudaMemcpyAsync(ctx->d_ps, ps, np * sizeof(double), cudaMemcpyHostToDevice, ctx->snap_stream));
-    k_reduce<<<ctx->H, K3_THREADS, 0, ctx->snap_stream>>>(ctx->buf[f].d_buckets, ctx->d_decomp, ctx->d_ps, (int)np,
-                                                          ctx->d_r_count, ctx->d_r_sum, ctx->d_r_avg, ctx->d_r_pkeys,
-                                                          ctx->d_r_pvals, ctx->d_nnz);
+    cudaStream_t s = ctx->snap_stream;
+    const ResLayout l = res_layout(ctx->H, np);
+    if (np) {
+        LH_CUDA(ctx, cudaMemcpyAsync(ctx->d_ps[slot], ps, np * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
+    char *d = ctx->d_res[slot];
+    k_reduce<<<ctx->H, K3_THREADS, 0, s>>>(ctx->buf[f].d_buckets, ctx->d_decomp, ctx->d_ps[slot], (int)np,
+                                           (unsigned long long *)(d + l.count), (double *)(d + l.sum), (double *)(d + l.avg),
+                                           (int *)(d + l.pkeys), (double *)(d + l.pvals), ctx->d_nnz);
     LH_CUDA(ctx, cudaGetLastError());
+    LH_CUDA(ctx, cudaMemcpyAsync(ctx->h_res[slot], d, l.total, cudaMemcpyDeviceToHost, s));
+    LH_CUDA(ctx, cudaEventRecord(ctx->res_done[slot], s));
     ctx->stats.kernel_launches++;
+    ctx->stats.d2h_bytes += l.total;
     ctx->nnz_valid = true;
+    ctx->res_np[slot] = np;
     return LH_OK;
 }
 }  // namespace
 
-extern "C" lh_status lh_snapshot_reduce(lh_ctx *ctx, const double *percentiles, uint32_t np, uint64_t *counts,
-                                        double *sums, double *avgs, int32_t *pkeys, double *pvals) {
+extern "C" lh_status lh_snapshot_reduce_async(lh_ctx *ctx, const double *percentiles, uint32_t np, uint64_t *ticket) {
     LH_ENTER(ctx);
+    if (!ticket) return fail(ctx, LH_ERR_INVALID, "ticket is NULL");
     if (!ctx->frozen) return fail(ctx, LH_ERR_STATE, "no snapshot in progress");
     if (np > LH_MAX_PERCENTILES || (np && !percentiles)) return fail(ctx, LH_ERR_INVALID, "bad percentile array");
-    lh_status st = run_reduce(ctx, percentiles, np);
+    const uint64_t t = ctx->next_ticket++;
+    const int slot = (int)(t & 1);
+    // the slot's previous results (ticket t-2) are overwritten: make sure its copy is not still in flight
+    if (ctx->res_ticket[slot]) LH_CUDA(ctx, cudaEventSynchronize(ctx->res_done[slot]));
+    lh_status st = enqueue_reduce(ctx, percentiles, np, slot);
     if (st != LH_OK) return st;
-    const size_t H = ctx->H;
-    const size_t bytes = H * 8 * 3 + H * np * 12;
-    st = ensure_host_scratch(ctx, bytes + 64);
-    if (st != LH_OK) return st;
-    char *p = (char *)ctx->h_scratch;
-    unsigned long long *hc = (unsigned long long *)p; p += H * 8;
-    double *hs = (double *)p; p += H * 8;
-    double *ha = (double *)p; p += H * 8;
-    double *hv = (double *)p; p += H * np * 8;
-    int *hk = (int *)p;
-    cudaStream_t s = ctx->snap_stream;
-    LH_CUDA(ctx, cudaMemcpyAsync(hc, ctx->d_r_count, H * 8, cudaMemcpyDeviceToHost, s));
-    LH_CUDA(ctx, cudaMemcpyAsync(hs, ctx->d_r_sum, H * 8, cudaMemcpyDeviceToHost, s));
-    LH_CUDA(ctx, cudaMemcpyAsync(ha, ctx->d_r_avg, H * 8, cudaMemcpyDeviceToHost, s));
-    if (np) {
-        LH_CUDA(ctx, cudaMemcpyAsync(hv, ctx->d_r_pvals, H * np * 8, cudaMemcpyDeviceToHost, s));
-        LH_CUDA(ctx, cudaMemcpyAsync(hk, ctx->d_r_pkeys, H * np * 4, cudaMemcpyDeviceToHost, s));
-    }
-    LH_CUDA(ctx, cudaStreamSynchronize(s));
-    ctx->stats.d2h_bytes += bytes;
-    if (counts) memcpy(counts, hc, H * 8);
-    if (sums) memcpy(sums, hs, H * 8);
-    if (avgs) memcpy(avgs, ha, H * 8);
-    if (pvals && np) memcpy(pvals, hv, H * np * 8);
-    if (pkeys && np) memcpy(pkeys, hk, H * np * 4);
+    ctx->res_ticket[slot] = t;
+    *ticket = t;
     return LH_OK;
+}
+
+extern "C" lh_status lh_snapshot_result(lh_ctx *ctx, uint64_t ticket, uint64_t *counts, double *sums, double *avgs,
+                                        int32_t *pkeys, double *pvals) {
+    if (!ctx) return LH_ERR_INVALID;
+    const int slot = (int)(ticket & 1);
+    cudaEvent_t ev;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (ticket == 0 || ctx->res_ticket[slot] != ticket) return fail(ctx, LH_ERR_STATE, "ticket expired or unknown");
+        ev = ctx->res_done[slot];
+    }
+    // wait outside the lock so ingest threads are not held up by the reaper
+    cudaError_t e = cudaEventSynchronize(ev);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (e != cudaSuccess) return fail(ctx, LH_ERR_CUDA, "cudaEventSynchronize(result)", e);
+    if (ctx->res_ticket[slot] != ticket) return fail(ctx, LH_ERR_STATE, "ticket expired while waiting");
+    const size_t H = ctx->H;
+    const uint32_t np = ctx->res_np[slot];
+    const ResLayout l = res_layout(H, np);
+    const char *h = ctx->h_res[slot];
+    if (counts) memcpy(counts, h + l.count, H * 8);
+    if (sums) memcpy(sums, h + l.sum, H * 8);
+    if (avgs) memcpy(avgs, h + l.avg, H * 8);
+    if (pvals && np) memcpy(pvals, h + l.pvals, H * np * 8);
+    if (pkeys && np) memcpy(pkeys, h + l.pkeys, H * np * 4);
+    return LH_OK;
+}
+
+extern "C" lh_status lh_snapshot_reduce(lh_ctx *ctx, const double *percentiles, uint32_t np, uint64_t *counts,
+                                        double *sums, double *avgs, int32_t *pkeys, double *pvals) {
+    uint64_t t = 0;
+    lh_status st = lh_snapshot_reduce_async(ctx, percentiles, np, &t);
+    if (st != LH_OK) return st;
+    return lh_snapshot_result(ctx, t, counts, sums, avgs, pkeys, pvals);
 }
 
 extern "C" lh_status lh_snapshot_export(lh_ctx *ctx, lh_sparse *out) {
@@ -727,7 +781,14 @@ extern "C" lh_status lh_snapshot_export(lh_ctx *ctx, lh_sparse *out) {
     if (!ctx->frozen) return fail(ctx, LH_ERR_STATE, "no snapshot in progress");
     const int f = ctx->active ^ 1;
     cudaStream_t s = ctx->snap_stream;
-    if (!ctx->nnz_valid) { lh_status st = run_reduce(ctx, nullptr, 0); if (st != LH_OK) return st; }
+    if (!ctx->nnz_valid) {   // non-empty bucket counts come out of K3; run it with no percentiles if nobody has yet
+        const uint64_t t = ctx->next_ticket++;
+        const int slot = (int)(t & 1);
+        if (ctx->res_ticket[slot]) LH_CUDA(ctx, cudaEventSynchronize(ctx->res_done[slot]));
+        lh_status st = enqueue_reduce(ctx, nullptr, 0, slot);
+        if (st != LH_OK) return st;
+        ctx->res_ticket[slot] = t;
+    }
     k_scan_nnz<<<1, 1024, 0, s>>>(ctx->d_nnz, ctx->H, ctx->d_offsets);
     LH_CUDA(ctx, cudaGetLastError());
     LH_CUDA(ctx, cudaMemcpyAsync(ctx->h_offsets, ctx->d_offsets, ((size_t)ctx->H + 1) * 4, cudaMemcpyDeviceToHost, s));
@@ -919,6 +980,23 @@ extern "C" int32_t lh_k1_variant_count(void) { return kNumK1Variants; }
 extern "C" const char *lh_k1_variant_name(lh_ctx *ctx, int32_t i) {
     if (!ctx || i < 0 || i >= kNumK1Variants) return "";
     return ctx->k1[i].name;
+}
+
+extern "C" uint64_t lh_ingest_seq(lh_ctx *ctx) {
+    if (!ctx) return 0;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return ctx->ingest_seq;
+}
+
+extern "C" lh_status lh_kernel_ms(lh_ctx *ctx, uint64_t seq, float *ms) {
+    LH_ENTER(ctx);
+    if (!ms) return fail(ctx, LH_ERR_INVALID, "ms is NULL");
+    if (seq == 0 || seq > ctx->ingest_seq || ctx->ingest_seq - seq >= (uint64_t)lh_ctx::kTimingRing)
+        return fail(ctx, LH_ERR_STATE, "that ingest launch is unknown or its events were recycled");
+    const int i = (int)((seq - 1) % lh_ctx::kTimingRing);
+    LH_CUDA(ctx, cudaEventSynchronize(ctx->ev_t1s[i]));
+    LH_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev_t0s[i], ctx->ev_t1s[i]));
+    return LH_OK;
 }
 
 extern "C" lh_status lh_last_kernel_ms(lh_ctx *ctx, float *ms) {

@@ -42,6 +42,8 @@ class ShardedEngine:
 
     snapshot() = lh_snapshot_begin -> all-reduce of the frozen device arrays on the snapshot stream ->
     lh_snapshot_reduce (+ export) -> lh_snapshot_end, so every rank ends with the global percentiles.
+    snapshot_async()/result() is the pipelined form: everything is only enqueued (the snapshot stream
+    outranks the ingest stream), the caller launches the next interval's ingest, then collects the result.
     """
 
     def __init__(self, engine, device_index: int, group=None):
@@ -51,33 +53,60 @@ class ShardedEngine:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.last_allreduce_events = None
+        self._views = {}     # device pointer -> cached zero-copy tensor
+        self._ext = None
+
+    def _tensor(self, ptr: int, words: int):
+        import torch
+        t = self._views.get(ptr)
+        if t is None or t.numel() != words:
+            t = torch.as_tensor(_CudaView(ptr, words), device="cuda:%d" % self.device_index)
+            self._views[ptr] = t
+        return t
+
+    def _allreduce_frozen(self, counters: bool):
+        import torch
+        eng = self.engine
+        v = eng.snapshot_device()
+        if self._ext is None or self._ext.cuda_stream != int(v.stream):
+            self._ext = torch.cuda.ExternalStream(int(v.stream), device=self.device_index)
+        ext = self._ext
+        with torch.cuda.stream(ext):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(ext)
+            allreduce_sum_u64(self._tensor(int(v.d_buckets), int(v.n_bucket_words)), self.group)
+            if counters:
+                allreduce_sum_u64(self._tensor(int(v.d_counters), int(v.n_counter_words)), self.group)
+            e1.record(ext)
+        self.last_allreduce_events = (e0, e1)
 
     def snapshot(self, percentiles, export: bool = False, counters: bool = False):
-        import torch
         eng = self.engine
         eng.snapshot_begin()
         try:
             if self.world > 1:
-                v = eng.snapshot_device()
-                ext = torch.cuda.ExternalStream(int(v.stream), device=self.device_index)
-                with torch.cuda.stream(ext):
-                    e0 = torch.cuda.Event(enable_timing=True)
-                    e1 = torch.cuda.Event(enable_timing=True)
-                    t = torch.as_tensor(_CudaView(int(v.d_buckets), int(v.n_bucket_words)),
-                                        device="cuda:%d" % self.device_index)
-                    e0.record(ext)
-                    allreduce_sum_u64(t, self.group)
-                    if counters:
-                        c = torch.as_tensor(_CudaView(int(v.d_counters), int(v.n_counter_words)),
-                                            device="cuda:%d" % self.device_index)
-                        allreduce_sum_u64(c, self.group)
-                    e1.record(ext)
-                self.last_allreduce_events = (e0, e1)
+                self._allreduce_frozen(counters)
             red = eng.snapshot_reduce(percentiles)
             sp = eng.snapshot_export() if export else None
         finally:
             eng.snapshot_end()
         return red, sp
+
+    def snapshot_async(self, percentiles, counters: bool = False):
+        """begin + all-reduce + reduce + end, all enqueued; returns a handle for result()."""
+        eng = self.engine
+        eng.snapshot_begin()
+        try:
+            if self.world > 1:
+                self._allreduce_frozen(counters)
+            h = eng.snapshot_reduce_async(percentiles)
+        finally:
+            eng.snapshot_end()
+        return h
+
+    def result(self, handle):
+        return self.engine.snapshot_result(handle)
 
     def last_allreduce_ms(self) -> float:
         if not self.last_allreduce_events:

@@ -202,6 +202,14 @@ class Engine:
         self._check(self.lib.lh_last_kernel_ms(self.h, C.byref(ms)))
         return float(ms.value)
 
+    def ingest_seq(self) -> int:
+        return int(self.lib.lh_ingest_seq(self.h))
+
+    def kernel_ms(self, seq: int) -> float:
+        ms = C.c_float()
+        self._check(self.lib.lh_kernel_ms(self.h, seq, C.byref(ms)))
+        return float(ms.value)
+
     def stats(self) -> dict:
         s = L.lh_stats()
         self._check(self.lib.lh_get_stats(self.h, C.byref(s)))
@@ -288,6 +296,25 @@ class Engine:
         self._check(self.lib.lh_snapshot_reduce(self.h, ps.ctypes.data if npct else 0, npct, counts.ctypes.data,
                                                 sums.ctypes.data, avgs.ctypes.data, pkeys.ctypes.data,
                                                 pvals.ctypes.data))
+        return Reduced(counts, sums, avgs, pkeys, pvals)
+
+    def snapshot_reduce_async(self, percentiles) -> tuple:
+        """Enqueue the reduction; returns an opaque handle for snapshot_result()."""
+        ps = np.ascontiguousarray(percentiles, dtype=np.float64)
+        t = C.c_uint64()
+        self._check(self.lib.lh_snapshot_reduce_async(self.h, ps.ctypes.data if ps.size else 0, ps.size, C.byref(t)))
+        return (int(t.value), ps.size)
+
+    def snapshot_result(self, handle) -> Reduced:
+        ticket, npct = handle
+        H = self.H
+        counts = np.zeros(H, dtype=np.uint64)
+        sums = np.zeros(H, dtype=np.float64)
+        avgs = np.zeros(H, dtype=np.float64)
+        pkeys = np.zeros((H, npct), dtype=np.int32)
+        pvals = np.zeros((H, npct), dtype=np.float64)
+        self._check(self.lib.lh_snapshot_result(self.h, ticket, counts.ctypes.data, sums.ctypes.data, avgs.ctypes.data,
+                                                pkeys.ctypes.data, pvals.ctypes.data))
         return Reduced(counts, sums, avgs, pkeys, pvals)
 
     def snapshot_export(self) -> Sparse:

@@ -292,6 +292,28 @@ def test_snapshot_interval_semantics(eng, lh, oracle):
     d.free()
 
 
+def test_async_snapshot_pipeline(eng, lh, oracle):
+    """lh_snapshot_reduce_async / lh_snapshot_result: the reduction of interval k is collected after interval
+    k+1's ingest has been launched; two tickets may be in flight, older ones expire."""
+    vals = oracle.gen_stream(lh.STREAM_U, 300_000, SEED ^ 0x21)
+    d = eng.upload(vals)
+    handles = []
+    for i in range(3):
+        eng.ingest_f64(1, d.offset(i * 100_000), 100_000)
+        eng.snapshot_begin()
+        handles.append(eng.snapshot_reduce_async(PS))
+        eng.snapshot_end()
+    for i in (1, 2):
+        red = eng.snapshot_result(handles[i])
+        ref = oracle.process_histogram(oracle.ingest(vals[i * 100_000:(i + 1) * 100_000]), PS)
+        assert int(red.counts[1]) == 100_000 and (red.pkeys[1] == ref["pkeys"]).all()
+        assert (red.pvals[1].view(np.uint64) == ref["pvals"].view(np.uint64)).all()
+    with pytest.raises(lh.LhError):
+        eng.snapshot_result(handles[0])        # its slot was reused by the third ticket
+    assert eng.kernel_ms(eng.ingest_seq()) > 0 and eng.kernel_ms(eng.ingest_seq() - 2) > 0
+    d.free()
+
+
 def test_host_and_staging_paths(lh, oracle):
     n = 3_000_017
     vals = oracle.gen_stream(lh.STREAM_S, n, SEED ^ 9)
