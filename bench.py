@@ -265,7 +265,9 @@ def run_b200(a):
         eng.tune("k1_grid_mult", a.k1_grid_mult)
     if a.k1_variant >= 0:
         eng.tune("k1", a.k1_variant)
-    stream = torch.cuda.current_stream()
+    # launch on the context's own non-blocking ingest stream (torch's legacy default stream serialises against
+    # other streams); torch only wraps it so that torch.cuda.Event can time the region on the launching stream
+    stream = torch.cuda.ExternalStream(eng.ingest_stream, device=local)
     d_vals = eng.gen_stream(kind, n, SEED, start=rank * n, stream=stream)
     d_ids = eng.gen_ids_u16(0, n, H, SEED, start=rank * n, stream=stream) if keyed else None
     torch.cuda.synchronize()
