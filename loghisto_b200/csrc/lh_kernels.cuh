@@ -169,6 +169,29 @@ k_ingest_single_ldg(const double *__restrict__ vals32, size_t nvec, const double
     flush_subhist(s_hist, COPIES, threadIdx.x, THREADS, counts);
 }
 
+// --------------------------------------------------------------- read probe
+// Diagnostic only (lh_tune "k1" = last variant): the same 256-bit streaming loads as K1/ldg with the
+// bucket arithmetic replaced by an XOR fold, to separate memory-side from SM-side limits.  Counts are NOT
+// produced; one word per CTA is written so the loads cannot be elided.
+template <int THREADS, int UNROLL>
+__global__ void __launch_bounds__(THREADS, 2)
+k_stream_probe(const double *__restrict__ vals32, size_t nvec, const double *, int, const double *, int,
+               unsigned long long *__restrict__ counts) {
+    const char *base = reinterpret_cast<const char *>(vals32);
+    constexpr size_t TILE = (size_t)THREADS * UNROLL;
+    const size_t ntiles = nvec / TILE;
+    unsigned long long acc = 0;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        f64x4 v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) v[u] = ldg_stream_f64x4(base + (tile * TILE + (size_t)u * THREADS + threadIdx.x) * 32);
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++)
+            acc ^= f64_as_u64(v[u].a) ^ f64_as_u64(v[u].b) ^ f64_as_u64(v[u].c) ^ f64_as_u64(v[u].d);
+    }
+    if (acc == 0x123456789ABCDEFull) counts[65535] = acc;   // never true in practice; keeps the loads alive
+}
+
 // ------------------------------------------------------------------ K1/bulk
 // Producer warp streams STAGE_BYTES tiles into a STAGES-deep shared ring with
 // cp.async.bulk; CW consumer warps bucket them.  Tiles are dealt round-robin.

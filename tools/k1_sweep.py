@@ -31,7 +31,8 @@ def main():
     H = max(a.keyed, 1)
     eng = lh.Engine(device=0, max_histograms=H, max_counters=1024)
     names = eng.k1_variants()
-    variants = range(len(names)) if a.variants == "all" else [int(x) for x in a.variants.split(",")]
+    variants = ([i for i, nm in enumerate(names) if not nm.startswith("probe")] if a.variants == "all"
+                else [int(x) for x in a.variants.split(",")])
     d = eng.alloc(a.n, np.float64)
     for sname in a.streams.split(","):
         eng.gen_stream(KINDS[sname], a.n, lh.DEFAULT_SEED, out=d)
