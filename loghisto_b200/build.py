@@ -21,6 +21,33 @@ NVCC_FLAGS = [
 ]
 
 
+HOST_LIB = os.path.join(HERE, "libloghisto_host.so")
+HOST_SRC = os.path.join(HERE, "host", "metric_system.cc")
+
+
+def needs_build_host() -> bool:
+    if not os.path.exists(HOST_LIB):
+        return True
+    deps = [HOST_SRC, os.path.join(HERE, "host", "metric_system.h"), os.path.join(ROOT, "include", "loghisto_b200.h"), LIB]
+    return _newest([d for d in deps if os.path.exists(d)]) > os.path.getmtime(HOST_LIB)
+
+
+def build_host(force: bool = False) -> str:
+    """C++ mirror of MetricSystem (host glue above the C ABI); links against libloghisto_b200.so."""
+    build()
+    if not force and not needs_build_host():
+        return HOST_LIB
+    gxx = shutil.which("g++") or "g++"
+    cmd = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-Wextra",
+           "-I", os.path.join(ROOT, "include"), "-o", HOST_LIB, HOST_SRC,
+           "-L", HERE, "-lloghisto_b200", "-Wl,-rpath,$ORIGIN", "-lpthread"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building libloghisto_host.so")
+    return HOST_LIB
+
+
 def sources():
     return [os.path.join(CSRC, "lh_api.cu")]
 
@@ -57,3 +84,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_host(force="--force" in sys.argv))

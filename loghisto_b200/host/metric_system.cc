@@ -1,0 +1,547 @@
+// metric_system.cc -- see metric_system.h.  Host glue only: interning, batching into the pinned staging
+// ring, rebuilding RawMetricSet / ProcessedMetricSet from what the device returns.
+#include "metric_system.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+
+#include "../../include/loghisto_b200.h"
+
+namespace loghisto {
+
+namespace {
+
+std::string format_label(const std::string &label, const std::string &name) {   // fmt.Sprintf(label, name), one %s
+    size_t p = label.find("%s");
+    if (p == std::string::npos) return label;
+    return label.substr(0, p) + name + label.substr(p + 2);
+}
+
+// uint64(float64) as the Go compiler lowers it on amd64 (metrics.go:374): CVTTSD2SQ below 2^63
+// (negative values wrap two's-complement), subtract-2^63 path above.
+uint64_t go_f64_to_u64(double x) {
+    if (x < 9223372036854775808.0) {
+        if (!(x > -9223372036854777856.0)) return 0x8000000000000000ull;
+        return (uint64_t)(int64_t)x;
+    }
+    if (!(x < 18446744073709551616.0)) return 0;
+    return (uint64_t)(int64_t)(x - 9223372036854775808.0) ^ 0x8000000000000000ull;
+}
+
+void check(lh_ctx *ctx, lh_status st, const char *what) {
+    if (st != LH_OK) {
+        std::string msg = std::string(what) + ": " + lh_strerror(st);
+        if (ctx) msg += std::string(" (") + lh_last_error(ctx) + ")";
+        throw std::runtime_error(msg);
+    }
+}
+
+size_t this_thread_slot(size_t n) {
+    static std::atomic<size_t> next{0};
+    thread_local size_t mine = next.fetch_add(1);
+    return mine % n;
+}
+
+}  // namespace
+
+struct MetricSystem::Shard {
+    std::mutex mu;
+    // histogram / timer samples
+    lh_staging hs{};
+    bool h_open = false;
+    size_t h_n = 0, h_cap = 0;
+    double *h_vals = nullptr;
+    uint16_t *h_ids = nullptr;
+    // counter ops
+    lh_staging cs{};
+    bool c_open = false;
+    size_t c_n = 0, c_cap = 0;
+    uint64_t *c_amounts = nullptr;
+    uint16_t *c_ids = nullptr;
+};
+
+std::chrono::nanoseconds TimerToken::Stop() {
+    auto d = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - Start);
+    System->Histogram(Name, (double)d.count());   // float64(duration.Nanoseconds())
+    return d;
+}
+
+MetricSystem::MetricSystem(std::chrono::nanoseconds interval, bool /*sysStats*/, const Options &opt)
+    : interval_(interval.count() > 0 ? interval : std::chrono::nanoseconds(1)), opt_(opt) {
+    percentiles_ = {{"%s_min", 0.0}, {"%s_50", .5}, {"%s_75", .75}, {"%s_90", .9}, {"%s_95", .95},
+                    {"%s_99", .99}, {"%s_99.9", .999}, {"%s_99.99", .9999}, {"%s_max", 1.0}};   // metrics.go:145-155
+    uint32_t nshards = opt.shards ? opt.shards : std::min<uint32_t>(std::max(1u, std::thread::hardware_concurrency()), 8u);
+    lh_config cfg{};
+    cfg.struct_size = sizeof(cfg);
+    cfg.device = opt.device;
+    cfg.max_histograms = opt.max_histograms;
+    cfg.max_counters = opt.max_counters;
+    cfg.staging_bytes = opt.staging_bytes;
+    cfg.staging_slots = 2 * nshards + 2;   // every shard may hold one histogram and one counter slot
+    lh_status st = lh_create(&cfg, &ctx_);
+    if (st != LH_OK) throw std::runtime_error(std::string("lh_create: ") + lh_strerror(st));
+    for (uint32_t i = 0; i < nshards; i++) shards_.emplace_back(new Shard());
+}
+
+MetricSystem::~MetricSystem() {
+    try { Stop(); } catch (...) {}
+    if (reaper_thread_.joinable()) reaper_thread_.join();
+    lh_destroy(ctx_);
+}
+
+void MetricSystem::SpecifyPercentiles(const std::map<std::string, double> &percentiles) {
+    std::lock_guard<std::mutex> lk(percentiles_mu_);
+    percentiles_.assign(percentiles.begin(), percentiles.end());
+    if (percentiles_.size() > LH_MAX_PERCENTILES) percentiles_.resize(LH_MAX_PERCENTILES);
+}
+
+uint16_t MetricSystem::intern(std::shared_mutex &mu, std::unordered_map<std::string, uint32_t> &ids,
+                              std::vector<std::string> &names, const std::string &name, uint32_t limit, bool *ok) {
+    {   // read-lock fast path, then write-lock and re-check: the idiom of metrics.go:275-294
+        std::shared_lock<std::shared_mutex> rl(mu);
+        auto it = ids.find(name);
+        if (it != ids.end()) { *ok = true; return (uint16_t)it->second; }
+    }
+    std::unique_lock<std::shared_mutex> wl(mu);
+    auto it = ids.find(name);
+    if (it != ids.end()) { *ok = true; return (uint16_t)it->second; }
+    if (names.size() >= limit || names.size() >= 65536) { *ok = false; return 0; }
+    uint32_t id = (uint32_t)names.size();
+    ids.emplace(name, id);
+    names.push_back(name);
+    *ok = true;
+    return (uint16_t)id;
+}
+
+void MetricSystem::Histogram(const std::string &name, double value) {
+    bool ok;
+    uint16_t id = intern(histo_mu_, histo_ids_, histo_names_, name, opt_.max_histograms, &ok);
+    if (!ok) {   // never fail the caller: drop and count (metrics.go's "drop and log" philosophy)
+        std::lock_guard<std::mutex> lk(counter_store_mu_);
+        dropped_over_limit_++;
+        return;
+    }
+    Shard &s = *shards_[this_thread_slot(shards_.size())];
+    std::lock_guard<std::mutex> lk(s.mu);
+    if (!s.h_open) {
+        check(ctx_, lh_staging_acquire(ctx_, &s.hs), "lh_staging_acquire");
+        s.h_cap = ((size_t)s.hs.bytes / 10) & ~(size_t)15;
+        s.h_vals = reinterpret_cast<double *>(s.hs.host);
+        s.h_ids = reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(s.hs.host) + s.h_cap * 8);
+        s.h_n = 0;
+        s.h_open = true;
+    }
+    s.h_vals[s.h_n] = value;
+    s.h_ids[s.h_n] = id;
+    if (++s.h_n == s.h_cap) {
+        check(ctx_, lh_staging_commit_keyed_f64_u16(ctx_, &s.hs, s.h_n, s.h_cap * 8), "lh_staging_commit_keyed_f64_u16");
+        s.h_open = false;
+    }
+}
+
+void MetricSystem::Counter(const std::string &name, uint64_t amount) {
+    bool ok;
+    uint16_t id = intern(counter_mu_, counter_ids_, counter_names_, name, opt_.max_counters, &ok);
+    if (!ok) {
+        std::lock_guard<std::mutex> lk(counter_store_mu_);
+        dropped_over_limit_++;
+        return;
+    }
+    Shard &s = *shards_[this_thread_slot(shards_.size())];
+    std::lock_guard<std::mutex> lk(s.mu);
+    if (!s.c_open) {
+        check(ctx_, lh_staging_acquire(ctx_, &s.cs), "lh_staging_acquire");
+        s.c_cap = ((size_t)s.cs.bytes / 10) & ~(size_t)15;
+        s.c_amounts = reinterpret_cast<uint64_t *>(s.cs.host);
+        s.c_ids = reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(s.cs.host) + s.c_cap * 8);
+        s.c_n = 0;
+        s.c_open = true;
+    }
+    s.c_amounts[s.c_n] = amount;
+    s.c_ids[s.c_n] = id;
+    if (++s.c_n == s.c_cap) {
+        check(ctx_, lh_staging_commit_counter_u16(ctx_, &s.cs, s.c_n, s.c_cap * 8), "lh_staging_commit_counter_u16");
+        s.c_open = false;
+    }
+}
+
+TimerToken MetricSystem::StartTimer(const std::string &name) {
+    return TimerToken{name, std::chrono::steady_clock::now(), this};
+}
+
+void MetricSystem::RegisterGaugeFunc(const std::string &name, std::function<double()> f) {
+    std::lock_guard<std::mutex> lk(gauge_mu_);
+    gauge_funcs_[name] = std::move(f);
+}
+void MetricSystem::DeregisterGaugeFunc(const std::string &name) {
+    std::lock_guard<std::mutex> lk(gauge_mu_);
+    gauge_funcs_.erase(name);
+}
+
+void MetricSystem::flush_shard(Shard &s) {
+    std::lock_guard<std::mutex> lk(s.mu);
+    if (s.h_open) {
+        check(ctx_, lh_staging_commit_keyed_f64_u16(ctx_, &s.hs, s.h_n, s.h_cap * 8), "lh_staging_commit_keyed_f64_u16");
+        s.h_open = false;
+    }
+    if (s.c_open) {
+        check(ctx_, lh_staging_commit_counter_u16(ctx_, &s.cs, s.c_n, s.c_cap * 8), "lh_staging_commit_counter_u16");
+        s.c_open = false;
+    }
+}
+
+uint64_t MetricSystem::dropped_samples() {
+    lh_stats st{};
+    lh_get_stats(ctx_, &st);
+    std::lock_guard<std::mutex> lk(counter_store_mu_);
+    return st.dropped + dropped_over_limit_;
+}
+
+// collectRawMetrics, metrics.go:420-479.
+std::shared_ptr<RawMetricSet> MetricSystem::collectRawMetrics() {
+    std::lock_guard<std::mutex> snap(snapshot_mu_);
+    auto raw = std::make_shared<RawMetricSet>();
+    const int64_t now = std::chrono::duration_cast<std::chrono::nanoseconds>(
+                            std::chrono::system_clock::now().time_since_epoch()).count();
+    const int64_t iv = interval_.count();
+    raw->Time = TimePoint(std::chrono::duration_cast<TimePoint::duration>(std::chrono::nanoseconds(now / iv * iv)));   // :421-423
+    raw->origin = this;
+    {
+        std::lock_guard<std::mutex> lk(percentiles_mu_);
+        raw->percentile_labels = percentiles_;
+    }
+
+    for (auto &s : shards_) flush_shard(*s);
+    check(ctx_, lh_snapshot_begin(ctx_), "lh_snapshot_begin");   // the cache swaps of :425-428 and :460-463
+
+    std::vector<std::string> hnames, cnames;
+    {
+        std::shared_lock<std::shared_mutex> rl(histo_mu_);
+        hnames = histo_names_;
+    }
+    {
+        std::shared_lock<std::shared_mutex> rl(counter_mu_);
+        cnames = counter_names_;
+    }
+    const uint32_t H = opt_.max_histograms, np = (uint32_t)raw->percentile_labels.size();
+    std::vector<double> ps(np);
+    for (uint32_t j = 0; j < np; j++) ps[j] = raw->percentile_labels[j].second;
+    std::vector<uint64_t> counts(H);
+    std::vector<double> sums(H), avgs(H), pvals((size_t)H * np);
+    std::vector<int32_t> pkeys((size_t)H * np);
+    lh_sparse sp{};
+    try {
+        check(ctx_, lh_snapshot_reduce(ctx_, ps.data(), np, counts.data(), sums.data(), avgs.data(), pkeys.data(), pvals.data()),
+              "lh_snapshot_reduce");
+        check(ctx_, lh_snapshot_export(ctx_, &sp), "lh_snapshot_export");
+    } catch (...) {
+        lh_snapshot_end(ctx_);
+        throw;
+    }
+    // histograms: present only when touched this interval (the swapped-out cache only holds touched names)
+    for (size_t h = 0; h < hnames.size(); h++) {
+        if (sp.offsets[h] == sp.offsets[h + 1]) continue;
+        auto &m = raw->Histograms[hnames[h]];
+        for (uint32_t i = sp.offsets[h]; i < sp.offsets[h + 1]; i++) m[sp.keys[i]] = sp.counts[i];
+        ReducedHistogram r;
+        r.count = counts[h]; r.sum = sums[h]; r.avg = avgs[h];
+        r.pkeys.assign(pkeys.begin() + h * np, pkeys.begin() + (h + 1) * np);
+        r.pvals.assign(pvals.begin() + h * np, pvals.begin() + (h + 1) * np);
+        raw->reduced[hnames[h]] = std::move(r);
+    }
+    // counters: Rates = interval deltas of the names touched (:430-433); Counters = cumulative store (:435-458).
+    // A counter whose delta is zero because only Counter(name, 0) was called still counts as touched in Go;
+    // the device cannot tell that apart from "untouched", so a zero delta is reported as untouched.
+    {
+        std::lock_guard<std::mutex> lk(counter_store_mu_);
+        for (size_t c = 0; c < cnames.size(); c++) {
+            uint64_t d = sp.counter_deltas[c];
+            if (d) {
+                raw->Rates[cnames[c]] = d;
+                counter_store_[cnames[c]] += d;
+            }
+        }
+        raw->Counters = counter_store_;
+    }
+    check(ctx_, lh_snapshot_end(ctx_), "lh_snapshot_end");
+    {
+        std::lock_guard<std::mutex> lk(gauge_mu_);
+        for (auto &g : gauge_funcs_) raw->Gauges[g.first] = g.second();   // :465-470
+    }
+    return raw;
+}
+
+// processMetrics + processHistograms, metrics.go:483-506 and :336-387.
+std::shared_ptr<ProcessedMetricSet> MetricSystem::processMetrics(const RawMetricSet &raw) {
+    if (raw.origin != this)
+        throw std::invalid_argument("processMetrics: RawMetricSet was not produced by this MetricSystem's collectRawMetrics");
+    auto out = std::make_shared<ProcessedMetricSet>();
+    out->Time = raw.Time;
+    auto &m = out->Metrics;
+    for (auto &c : raw.Counters) m[c.first] = (double)c.second;
+    for (auto &r : raw.Rates) m[r.first + "_rate"] = (double)r.second;
+    for (auto &h : raw.Histograms) {
+        const std::string &name = h.first;
+        auto it = raw.reduced.find(name);
+        if (it == raw.reduced.end()) continue;
+        const ReducedHistogram &r = it->second;
+        const std::string sumName = name + "_sum", countName = name + "_count", avgName = name + "_avg";
+        m[countName] = (double)r.count;
+        m[sumName] = r.sum;
+        m[avgName] = r.avg;
+        {   // aggregate store, :359-376
+            std::lock_guard<std::mutex> lk(histogram_count_mu_);
+            histogram_count_store_[sumName] += go_f64_to_u64(r.sum);
+            histogram_count_store_[countName] += r.count;
+        }
+        for (size_t j = 0; j < raw.percentile_labels.size(); j++) {
+            if (r.pkeys[j] == std::numeric_limits<int32_t>::min()) {   // percentile() error: logged, key omitted (:380-382)
+                fprintf(stderr, "loghisto: unable to calculate percentile: Invalid percentile.  Should be between 0 and 1.\n");
+                continue;
+            }
+            m[format_label(raw.percentile_labels[j].first, name)] = r.pvals[j];
+        }
+    }
+    for (auto &g : raw.Gauges) m[g.first] = g.second;
+    return out;
+}
+
+// the reaper's "add aggregate mean" step, metrics.go:590-608 (integer division)
+void MetricSystem::add_aggregates(const RawMetricSet &raw, ProcessedMetricSet &out) {
+    for (auto &h : raw.Histograms) {
+        uint64_t aggCount = 0, aggSum = 0;
+        bool countPresent, sumPresent;
+        {
+            std::lock_guard<std::mutex> lk(histogram_count_mu_);
+            auto c = histogram_count_store_.find(h.first + "_count");
+            auto s = histogram_count_store_.find(h.first + "_sum");
+            countPresent = c != histogram_count_store_.end();
+            sumPresent = s != histogram_count_store_.end();
+            if (countPresent) aggCount = c->second;
+            if (sumPresent) aggSum = s->second;
+        }
+        if (countPresent && sumPresent && aggCount > 0) {
+            out.Metrics[h.first + "_agg_avg"] = (double)(aggSum / aggCount);
+            out.Metrics[h.first + "_agg_count"] = (double)aggCount;
+            out.Metrics[h.first + "_agg_sum"] = (double)aggSum;
+        }
+    }
+}
+
+void MetricSystem::SubscribeToRawMetrics(std::shared_ptr<Channel<std::shared_ptr<RawMetricSet>>> ch) {
+    std::lock_guard<std::mutex> lk(subscribers_mu_);
+    raw_subscribers_.push_back(std::move(ch));
+}
+void MetricSystem::UnsubscribeFromRawMetrics(std::shared_ptr<Channel<std::shared_ptr<RawMetricSet>>> ch) {
+    std::lock_guard<std::mutex> lk(subscribers_mu_);
+    raw_subscribers_.erase(std::remove(raw_subscribers_.begin(), raw_subscribers_.end(), ch), raw_subscribers_.end());
+    raw_bad_.erase(ch.get());
+}
+void MetricSystem::SubscribeToProcessedMetrics(std::shared_ptr<Channel<std::shared_ptr<ProcessedMetricSet>>> ch) {
+    std::lock_guard<std::mutex> lk(subscribers_mu_);
+    processed_subscribers_.push_back(std::move(ch));
+}
+void MetricSystem::UnsubscribeFromProcessedMetrics(std::shared_ptr<Channel<std::shared_ptr<ProcessedMetricSet>>> ch) {
+    std::lock_guard<std::mutex> lk(subscribers_mu_);
+    processed_subscribers_.erase(std::remove(processed_subscribers_.begin(), processed_subscribers_.end(), ch),
+                                 processed_subscribers_.end());
+    processed_bad_.erase(ch.get());
+}
+
+// reaper, metrics.go:530-639: wake at wall-clock multiples of the interval, collect, broadcast raw,
+// process, add aggregates, broadcast processed; never block on a subscriber, close one that misses twice.
+void MetricSystem::reaper() {
+    for (;;) {
+        const int64_t iv = interval_.count();
+        const int64_t now = std::chrono::duration_cast<std::chrono::nanoseconds>(
+                                std::chrono::system_clock::now().time_since_epoch()).count();
+        const int64_t tts = iv - (now % iv);
+        {
+            std::unique_lock<std::mutex> lk(run_mu_);
+            if (run_cv_.wait_for(lk, std::chrono::nanoseconds(tts), [&] { return shutdown_; })) {
+                reaping_ = false;
+                return;
+            }
+        }
+        std::shared_ptr<RawMetricSet> raw;
+        try {
+            raw = collectRawMetrics();
+        } catch (const std::exception &e) {
+            fprintf(stderr, "loghisto: collectRawMetrics failed: %s\n", e.what());
+            continue;
+        }
+        {
+            std::lock_guard<std::mutex> lk(subscribers_mu_);
+            for (size_t i = 0; i < raw_subscribers_.size();) {
+                auto &ch = raw_subscribers_[i];
+                if (ch->TrySend(raw)) { raw_bad_.erase(ch.get()); i++; continue; }
+                fprintf(stderr, "loghisto: a raw subscriber has allowed their channel to fill up. dropping their metrics on the floor rather than blocking.\n");
+                if (++raw_bad_[ch.get()] >= 2) {
+                    ch->Close();
+                    raw_bad_.erase(ch.get());
+                    raw_subscribers_.erase(raw_subscribers_.begin() + i);
+                } else {
+                    i++;
+                }
+            }
+        }
+        std::shared_ptr<ProcessedMetricSet> processed;
+        try {
+            processed = processMetrics(*raw);
+        } catch (const std::exception &e) {
+            fprintf(stderr, "loghisto: processMetrics failed: %s\n", e.what());
+            continue;
+        }
+        add_aggregates(*raw, *processed);
+        {
+            std::lock_guard<std::mutex> lk(subscribers_mu_);
+            for (size_t i = 0; i < processed_subscribers_.size();) {
+                auto &ch = processed_subscribers_[i];
+                if (ch->TrySend(processed)) { processed_bad_.erase(ch.get()); i++; continue; }
+                fprintf(stderr, "loghisto: a subscriber has allowed their channel to fill up. dropping their metrics on the floor rather than blocking.\n");
+                if (++processed_bad_[ch.get()] >= 2) {
+                    ch->Close();
+                    processed_bad_.erase(ch.get());
+                    processed_subscribers_.erase(processed_subscribers_.begin() + i);
+                } else {
+                    i++;
+                }
+            }
+        }
+    }
+}
+
+void MetricSystem::Start() {
+    std::lock_guard<std::mutex> lk(run_mu_);
+    if (reaping_ || shutdown_) return;
+    reaping_ = true;
+    reaper_thread_ = std::thread([this] { reaper(); });
+}
+
+void MetricSystem::Stop() {   // idempotent, unlike the reference's double close (metrics.go:652)
+    {
+        std::lock_guard<std::mutex> lk(run_mu_);
+        shutdown_ = true;
+    }
+    run_cv_.notify_all();
+    if (reaper_thread_.joinable() && std::this_thread::get_id() != reaper_thread_.get_id()) reaper_thread_.join();
+}
+
+}  // namespace loghisto
+
+// ---------------------------------------------------------------------------------------------
+// C shim so that ctypes tests can replay the reference's metrics_test.go against the C++ mirror.
+using namespace loghisto;
+
+extern "C" {
+#define LHMS_API __attribute__((visibility("default")))
+typedef void (*lhms_emit_fn)(void *ctx, int kind, const char *name, int key, uint64_t u, double f);
+
+LHMS_API void *lhms_new(int64_t interval_ns, int device, uint32_t max_histograms, uint32_t max_counters, char *err, int errlen) {
+    try {
+        Options o;
+        o.device = device;
+        o.max_histograms = max_histograms;
+        o.max_counters = max_counters;
+        return new MetricSystem(std::chrono::nanoseconds(interval_ns), false, o);
+    } catch (const std::exception &e) {
+        if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s", e.what());
+        return nullptr;
+    }
+}
+LHMS_API void lhms_free(void *ms) { delete static_cast<MetricSystem *>(ms); }
+LHMS_API void lhms_histogram(void *ms, const char *name, double v) { static_cast<MetricSystem *>(ms)->Histogram(name, v); }
+LHMS_API void lhms_counter(void *ms, const char *name, uint64_t a) { static_cast<MetricSystem *>(ms)->Counter(name, a); }
+LHMS_API void lhms_histogram_many(void *ms, const char *name, const double *v, size_t n) {
+    std::string nm(name);
+    auto *m = static_cast<MetricSystem *>(ms);
+    for (size_t i = 0; i < n; i++) m->Histogram(nm, v[i]);
+}
+LHMS_API void *lhms_start_timer(void *ms, const char *name) {
+    return new TimerToken(static_cast<MetricSystem *>(ms)->StartTimer(name));
+}
+LHMS_API int64_t lhms_timer_stop(void *token) {
+    auto *t = static_cast<TimerToken *>(token);
+    int64_t ns = t->Stop().count();
+    delete t;
+    return ns;
+}
+LHMS_API void lhms_specify_percentiles(void *ms, int n, const char *const *labels, const double *ps) {
+    std::map<std::string, double> m;
+    for (int i = 0; i < n; i++) m[labels[i]] = ps[i];
+    static_cast<MetricSystem *>(ms)->SpecifyPercentiles(m);
+}
+LHMS_API void lhms_register_constant_gauge(void *ms, const char *name, double v) {
+    static_cast<MetricSystem *>(ms)->RegisterGaugeFunc(name, [v] { return v; });
+}
+
+static void emit_raw(const RawMetricSet &raw, lhms_emit_fn emit, void *ctx) {
+    for (auto &c : raw.Counters) emit(ctx, 0, c.first.c_str(), 0, c.second, 0);
+    for (auto &r : raw.Rates) emit(ctx, 1, r.first.c_str(), 0, r.second, 0);
+    for (auto &h : raw.Histograms)
+        for (auto &b : h.second) emit(ctx, 2, h.first.c_str(), b.first, b.second, 0);
+    for (auto &g : raw.Gauges) emit(ctx, 4, g.first.c_str(), 0, 0, g.second);
+}
+static void emit_processed(const ProcessedMetricSet &p, lhms_emit_fn emit, void *ctx) {
+    for (auto &m : p.Metrics) emit(ctx, 3, m.first.c_str(), 0, 0, m.second);
+}
+
+// processMetrics(collectRawMetrics()), as metrics_test.go:195 does.  Returns 0, or -1 with err filled.
+LHMS_API int lhms_collect_and_process(void *ms, lhms_emit_fn emit, void *ctx, char *err, int errlen) {
+    try {
+        auto *m = static_cast<MetricSystem *>(ms);
+        auto raw = m->collectRawMetrics();
+        auto p = m->processMetrics(*raw);
+        emit_raw(*raw, emit, ctx);
+        emit_processed(*p, emit, ctx);
+        return 0;
+    } catch (const std::exception &e) {
+        if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s", e.what());
+        return -1;
+    }
+}
+LHMS_API void lhms_start(void *ms) { static_cast<MetricSystem *>(ms)->Start(); }
+LHMS_API void lhms_stop(void *ms) { static_cast<MetricSystem *>(ms)->Stop(); }
+LHMS_API uint64_t lhms_dropped(void *ms) { return static_cast<MetricSystem *>(ms)->dropped_samples(); }
+
+using RawCh = std::shared_ptr<Channel<std::shared_ptr<RawMetricSet>>>;
+using ProcCh = std::shared_ptr<Channel<std::shared_ptr<ProcessedMetricSet>>>;
+
+LHMS_API void *lhms_subscribe_processed(void *ms, int capacity) {
+    auto *ch = new ProcCh(std::make_shared<Channel<std::shared_ptr<ProcessedMetricSet>>>((size_t)capacity));
+    static_cast<MetricSystem *>(ms)->SubscribeToProcessedMetrics(*ch);
+    return ch;
+}
+LHMS_API void lhms_unsubscribe_processed(void *ms, void *ch) {
+    static_cast<MetricSystem *>(ms)->UnsubscribeFromProcessedMetrics(*static_cast<ProcCh *>(ch));
+}
+// 1 = received, 0 = timeout, -1 = channel closed by the reaper
+LHMS_API int lhms_recv_processed(void *ch, int64_t timeout_ns, lhms_emit_fn emit, void *ctx) {
+    auto &c = *static_cast<ProcCh *>(ch);
+    std::shared_ptr<ProcessedMetricSet> p;
+    if (c->Receive(&p, std::chrono::nanoseconds(timeout_ns))) { emit_processed(*p, emit, ctx); return 1; }
+    return c->Closed() ? -1 : 0;
+}
+LHMS_API void lhms_free_processed_channel(void *ch) { delete static_cast<ProcCh *>(ch); }
+
+LHMS_API void *lhms_subscribe_raw(void *ms, int capacity) {
+    auto *ch = new RawCh(std::make_shared<Channel<std::shared_ptr<RawMetricSet>>>((size_t)capacity));
+    static_cast<MetricSystem *>(ms)->SubscribeToRawMetrics(*ch);
+    return ch;
+}
+LHMS_API void lhms_unsubscribe_raw(void *ms, void *ch) {
+    static_cast<MetricSystem *>(ms)->UnsubscribeFromRawMetrics(*static_cast<RawCh *>(ch));
+}
+LHMS_API int lhms_recv_raw(void *ch, int64_t timeout_ns, lhms_emit_fn emit, void *ctx) {
+    auto &c = *static_cast<RawCh *>(ch);
+    std::shared_ptr<RawMetricSet> r;
+    if (c->Receive(&r, std::chrono::nanoseconds(timeout_ns))) { emit_raw(*r, emit, ctx); return 1; }
+    return c->Closed() ? -1 : 0;
+}
+LHMS_API void lhms_free_raw_channel(void *ch) { delete static_cast<RawCh *>(ch); }
+}  // extern "C"
