@@ -80,10 +80,19 @@ K1Variant g_k1_variants[] = {
     BULK_VARIANT(8, 3, 32768, 1, 2),    // 8
     BULK_VARIANT(16, 3, 65536, 1, 1),   // 9
     BULK_VARIANT(4, 4, 8192, 1, 4),     // 10
+#define V2_VARIANT(T, U, M) \
+    { "v2_t" #T "_u" #U "_b" #M, [](int grid, size_t smem, cudaStream_t s, const double *v32, size_t nvec, const double *h, int nh, \
+                                     const double *t, int nt, unsigned long long *c) { k_ingest_single_v2<T, U, M><<<grid, T, smem, s>>>(v32, nvec, h, nh, t, nt, c); }, \
+      (const void *)k_ingest_single_v2<T, U, M>, T, hist_bytes(1), 0 }
     // 11: read-only diagnostic, produces no counts (never selected by default)
     { "probe_read_only_t512_u4", [](int grid, size_t, cudaStream_t s, const double *v32, size_t nvec, const double *h, int nh,
                                     const double *t, int nt, unsigned long long *c) { k_stream_probe<512, 4><<<grid, 512, 0, s>>>(v32, nvec, h, nh, t, nt, c); },
       (const void *)k_stream_probe<512, 4>, 512, 0, 0 },
+    V2_VARIANT(512, 2, 2),    // 12
+    V2_VARIANT(512, 1, 2),    // 13
+    V2_VARIANT(256, 2, 4),    // 14
+    V2_VARIANT(1024, 1, 1),   // 15
+    V2_VARIANT(512, 2, 1),    // 16
 };
 constexpr int kNumK1Variants = (int)(sizeof(g_k1_variants) / sizeof(g_k1_variants[0]));
 constexpr int kDefaultK1Variant = 0;

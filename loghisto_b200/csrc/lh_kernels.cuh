@@ -169,6 +169,119 @@ k_ingest_single_ldg(const double *__restrict__ vals32, size_t nvec, const double
     flush_subhist(s_hist, COPIES, threadIdx.x, THREADS, counts);
 }
 
+// ---------------------------------------------------------------- K1/ldg v2
+// Same algorithm as k_ingest_single_ldg with the per-sample instruction count cut from ~30 to ~20 so that the
+// kernel stays HBM-bound under sustained load (profiles/r01/sustained_probe.txt):
+//   * samples are processed in pairs with Blackwell's packed FP32 ops (fma.rn.f32x2 / add.f32x2);
+//   * (float)e comes from one I2FP and the -1023 bias rides in the FMA addend;
+//   * ONE flag per sample -- estimate too close to a bucket boundary, OR v's high word >= 0x43E00000 unsigned
+//     (|v| >= 2^63, Inf, NaN, and every negative value) -- sends it to a fix-up that re-derives the slot
+//     (negative values cost a second fast evaluation there, not the FP64 path);
+//   * the shared-memory byte offset is built as e*276 + (rounded bits << 2) + const: one IMAD and one LEA;
+//   * two register buffers alternate, so no copies.
+// Extra estimate error vs fast_candidate(): the float constant -1023*c2 (|err| <= 1.6e-5 bucket units), still
+// well inside LH_FAST_EPS.
+__device__ __forceinline__ uint32_t fixup_slot(double v, unsigned long long *__restrict__ counts) {
+    uint32_t key = key16_of(v);
+    uint32_t slot = key16_to_slot(key);
+    if (slot == 0xFFFFFFFFu) { atomicAdd(&counts[key], 1ull); slot = LH_TRASH; }
+    return slot;
+}
+
+template <int NS>
+__device__ __forceinline__ void bucket_samples_v2(const double (&v)[NS], uint32_t *hist, uint32_t one_bits,
+                                                  unsigned long long *__restrict__ counts) {
+    static_assert(NS % 2 == 0, "pairs");
+    constexpr float C1 = 69.31471805599453f, C2 = 0.31471805599453f;
+    constexpr float KB = (float)(-1023.0 * (double)C2);
+    constexpr float MAGIC = 12582912.0f;
+    // byte offset = 4*(69*(eb-1023) + (bits(r) - 0x4B400000))  (mod 2^32)
+    constexpr uint32_t COFF = 0u - (1023u * 69u * 4u) - (0x4B400000u << 2);
+    uint32_t off[NS];
+    bool flag[NS];
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < NS; i += 2) {
+        const double x0 = __dadd_rn(1.0, fabs(v[i])), x1 = __dadd_rn(1.0, fabs(v[i + 1]));
+        const uint32_t h0 = (uint32_t)__double2hiint(x0), h1 = (uint32_t)__double2hiint(x1);
+        const uint32_t t0 = __funnelshift_l((uint32_t)__double2loint(x0), h0, 3);
+        const uint32_t t1 = __funnelshift_l((uint32_t)__double2loint(x1), h1, 3);
+        uint32_t m0, m1;
+        asm("lop3.b32 %0, %1, 0x007FFFFF, %2, 0xEA;" : "=r"(m0) : "r"(t0), "r"(one_bits));   // (t & mask) | 1.0f
+        asm("lop3.b32 %0, %1, 0x007FFFFF, %2, 0xEA;" : "=r"(m1) : "r"(t1), "r"(one_bits));
+        float2 lg;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg.x) : "f"(__uint_as_float(m0)));
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg.y) : "f"(__uint_as_float(m1)));
+        const uint32_t e0 = h0 >> 20, e1 = h1 >> 20;                    // 1023 + e
+        const float2 ef = make_float2(__uint2float_rn(e0), __uint2float_rn(e1));
+        const float2 a = __ffma2_rn(ef, make_float2(C2, C2), make_float2(KB, KB));
+        const float2 w = __ffma2_rn(lg, make_float2(C1, C1), a);
+        const float2 r = __fadd2_rn(w, make_float2(MAGIC, MAGIC));
+        const float2 s = __fadd2_rn(r, make_float2(-MAGIC, -MAGIC));
+        const float2 d = __ffma2_rn(s, make_float2(-1.0f, -1.0f), w);   // w - s, one rounding
+        flag[i] = (fabsf(d.x) > 0.5f - LH_FAST_EPS) | ((uint32_t)__double2hiint(v[i]) >= 0x43E00000u);
+        flag[i + 1] = (fabsf(d.y) > 0.5f - LH_FAST_EPS) | ((uint32_t)__double2hiint(v[i + 1]) >= 0x43E00000u);
+        off[i] = e0 * 276u + (__float_as_uint(r.x) << 2) + COFF;
+        off[i + 1] = e1 * 276u + (__float_as_uint(r.y) << 2) + COFF;
+        any |= flag[i] | flag[i + 1];
+    }
+    if (__any_sync(0xFFFFFFFFu, any)) {
+#pragma unroll
+        for (int i = 0; i < NS; i++)
+            if (flag[i]) off[i] = fixup_slot(v[i], counts) * 4u;
+    }
+#pragma unroll
+    for (int i = 0; i < NS; i++) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(hist) + off[i]), 1u);
+}
+
+template <int THREADS, int UNROLL, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_ingest_single_v2(const double *__restrict__ vals32, size_t nvec, const double *head, int nhead,
+                   const double *tail, int ntail, unsigned long long *__restrict__ counts) {
+    extern __shared__ __align__(16) uint32_t s_hist[];
+    for (int i = threadIdx.x; i < (int)LH_SUBHIST_ALLOC; i += THREADS) s_hist[i] = 0;
+    __syncthreads();
+    uint32_t one_bits;
+    asm volatile("mov.b32 %0, 0x3F800000;" : "=r"(one_bits));   // opaque to constant folding: keeps LOP3 at one instruction
+    const char *base = reinterpret_cast<const char *>(vals32);
+    constexpr size_t TILE = (size_t)THREADS * UNROLL;           // 32-byte vectors per tile
+    const size_t ntiles = nvec / TILE;
+    const size_t step = gridDim.x;
+
+    f64x4 A[UNROLL], B[UNROLL];
+    auto load = [&](f64x4(&buf)[UNROLL], size_t tile) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) buf[u] = ldg_stream_f64x4(base + (tile * TILE + (size_t)u * THREADS + threadIdx.x) * 32);
+    };
+    auto process = [&](const f64x4(&buf)[UNROLL]) {
+        double v[4 * UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) { v[4 * u] = buf[u].a; v[4 * u + 1] = buf[u].b; v[4 * u + 2] = buf[u].c; v[4 * u + 3] = buf[u].d; }
+        bucket_samples_v2<4 * UNROLL>(v, s_hist, one_bits, counts);
+    };
+    size_t tile = blockIdx.x;
+    if (tile < ntiles) load(A, tile);
+    while (tile < ntiles) {
+        const size_t t1 = tile + step;
+        if (t1 < ntiles) load(B, t1);
+        process(A);
+        if (t1 >= ntiles) break;
+        const size_t t2 = t1 + step;
+        if (t2 < ntiles) load(A, t2);
+        process(B);
+        tile = t2;
+    }
+    if (blockIdx.x == ntiles % gridDim.x) {   // partial last tile + stragglers
+        for (size_t j = ntiles * TILE * 4 + threadIdx.x; j < nvec * 4; j += THREADS) {
+            uint32_t slot = fixup_slot(vals32[j], counts);
+            atomicAdd(&s_hist[slot], 1u);
+        }
+        if (threadIdx.x == 0) { bucket_stragglers(head, nhead, counts); bucket_stragglers(tail, ntail, counts); }
+    }
+    __syncthreads();
+    flush_subhist(s_hist, 1, threadIdx.x, THREADS, counts);
+}
+
 // --------------------------------------------------------------- read probe
 // Diagnostic only (lh_tune "k1" = last variant): the same 256-bit streaming loads as K1/ldg with the
 // bucket arithmetic replaced by an XOR fold, to separate memory-side from SM-side limits.  Counts are NOT

@@ -19,6 +19,7 @@ def run(k, v):
     eng.sync()
     pick = [0, 1, 5, 10, 20, 40, 80, 120, 160, 199, 299]
     print("%-28s mean %.3f :" % (names[v], sum(times) / len(times)), " ".join("%d:%.3f" % (i, times[i]) for i in pick if i < k), flush=True)
-for v in (11, 0, 11, 0):
+vs = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [11, 0, 11, 0]
+for v in vs:
     time.sleep(1.5)
     run(300, v)
