@@ -93,6 +93,16 @@ K1Variant g_k1_variants[] = {
     V2_VARIANT(256, 2, 4),    // 14
     V2_VARIANT(1024, 1, 1),   // 15
     V2_VARIANT(512, 2, 1),    // 16
+#define V3_VARIANT(T, M, D) \
+    { "v3_t" #T "_b" #M "_d" #D, [](int grid, size_t smem, cudaStream_t s, const double *v32, size_t nvec, const double *h, int nh, \
+                                      const double *t, int nt, unsigned long long *c) { k_ingest_single_v3<T, M, D><<<grid, T, smem, s>>>(v32, nvec, h, nh, t, nt, c); }, \
+      (const void *)k_ingest_single_v3<T, M, D>, T, hist_bytes(1), 0 }
+    V3_VARIANT(512, 2, 3),    // 17
+    V3_VARIANT(512, 2, 4),    // 18
+    V3_VARIANT(1024, 1, 3),   // 19
+    V3_VARIANT(256, 4, 3),    // 20
+    V3_VARIANT(384, 2, 4),    // 21
+    V3_VARIANT(512, 2, 2),    // 22
 };
 constexpr int kNumK1Variants = (int)(sizeof(g_k1_variants) / sizeof(g_k1_variants[0]));
 constexpr int kDefaultK1Variant = 0;

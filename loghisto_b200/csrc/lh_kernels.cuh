@@ -282,6 +282,51 @@ k_ingest_single_v2(const double *__restrict__ vals32, size_t nvec, const double 
     flush_subhist(s_hist, 1, threadIdx.x, THREADS, counts);
 }
 
+// ---------------------------------------------------------------- K1/ldg v3
+// v2's arithmetic with a three-deep register rotation: every thread always has DEPTH-1 256-bit loads in flight
+// (64 KB per SM at 1024 threads) while it buckets the 4 samples of the oldest one, inside 64 registers.
+template <int THREADS, int MINB, int DEPTH>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_ingest_single_v3(const double *__restrict__ vals32, size_t nvec, const double *head, int nhead,
+                   const double *tail, int ntail, unsigned long long *__restrict__ counts) {
+    extern __shared__ __align__(16) uint32_t s_hist[];
+    for (int i = threadIdx.x; i < (int)LH_SUBHIST_ALLOC; i += THREADS) s_hist[i] = 0;
+    __syncthreads();
+    uint32_t one_bits;
+    asm volatile("mov.b32 %0, 0x3F800000;" : "=r"(one_bits));
+    const char *base = reinterpret_cast<const char *>(vals32) + (size_t)threadIdx.x * 32;
+    constexpr size_t TILE_BYTES = (size_t)THREADS * 32;
+    const size_t ntiles = nvec / THREADS;
+    const size_t step = gridDim.x;
+
+    f64x4 buf[DEPTH];
+    size_t tile = blockIdx.x;          // tile whose data sits in buf[0]
+#pragma unroll
+    for (int d = 0; d < DEPTH - 1; d++)
+        if (tile + d * step < ntiles) buf[d] = ldg_stream_f64x4(base + (tile + d * step) * TILE_BYTES);
+    while (tile < ntiles) {
+#pragma unroll
+        for (int d = 0; d < DEPTH; d++) {          // rotation unrolled: buffer indices are compile-time
+            const size_t cur = tile + (size_t)d * step;
+            if (cur >= ntiles) break;
+            const size_t pre = cur + (size_t)(DEPTH - 1) * step;
+            if (pre < ntiles) buf[(d + DEPTH - 1) % DEPTH] = ldg_stream_f64x4(base + pre * TILE_BYTES);
+            const double v[4] = {buf[d].a, buf[d].b, buf[d].c, buf[d].d};
+            bucket_samples_v2<4>(v, s_hist, one_bits, counts);
+        }
+        tile += (size_t)DEPTH * step;
+    }
+    if (blockIdx.x == ntiles % gridDim.x) {   // partial last tile + stragglers
+        for (size_t j = ntiles * THREADS * 4 + threadIdx.x; j < nvec * 4; j += THREADS) {
+            uint32_t slot = fixup_slot(vals32[j], counts);
+            atomicAdd(&s_hist[slot], 1u);
+        }
+        if (threadIdx.x == 0) { bucket_stragglers(head, nhead, counts); bucket_stragglers(tail, ntail, counts); }
+    }
+    __syncthreads();
+    flush_subhist(s_hist, 1, threadIdx.x, THREADS, counts);
+}
+
 // --------------------------------------------------------------- read probe
 // Diagnostic only (lh_tune "k1" = last variant): the same 256-bit streaming loads as K1/ldg with the
 // bucket arithmetic replaced by an XOR fold, to separate memory-side from SM-side limits.  Counts are NOT
