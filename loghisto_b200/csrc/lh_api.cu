@@ -103,6 +103,15 @@ K1Variant g_k1_variants[] = {
     V3_VARIANT(256, 4, 3),    // 20
     V3_VARIANT(384, 2, 4),    // 21
     V3_VARIANT(512, 2, 2),    // 22
+#define BULK2_VARIANT(W, S, B, M) \
+    { "bulk2_w" #W "_s" #S "_" #B "_b" #M, [](int grid, size_t smem, cudaStream_t s, const double *v32, size_t nvec, const double *h, int nh, \
+          const double *t, int nt, unsigned long long *c) { k_ingest_single_bulk<W, S, B, 1, M, true><<<grid, (W + 1) * 32, smem, s>>>(v32, nvec, h, nh, t, nt, c); }, \
+      (const void *)k_ingest_single_bulk<W, S, B, 1, M, true>, (W + 1) * 32, bulk_smem(S, B, 1), 0 }
+    BULK2_VARIANT(16, 3, 65536, 1),   // 23
+    BULK2_VARIANT(16, 4, 32768, 1),   // 24
+    BULK2_VARIANT(8, 4, 16384, 2),    // 25
+    BULK2_VARIANT(8, 5, 16384, 2),    // 26
+    BULK2_VARIANT(16, 5, 32768, 1),   // 27
 };
 constexpr int kNumK1Variants = (int)(sizeof(g_k1_variants) / sizeof(g_k1_variants[0]));
 constexpr int kDefaultK1Variant = 0;

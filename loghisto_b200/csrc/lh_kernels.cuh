@@ -353,7 +353,11 @@ k_stream_probe(const double *__restrict__ vals32, size_t nvec, const double *, i
 // ------------------------------------------------------------------ K1/bulk
 // Producer warp streams STAGE_BYTES tiles into a STAGES-deep shared ring with
 // cp.async.bulk; CW consumer warps bucket them.  Tiles are dealt round-robin.
-template <int CW, int STAGES, int STAGE_BYTES, int COPIES, int MINB>
+template <int NS>
+__device__ __forceinline__ void bucket_samples_v2(const double (&v)[NS], uint32_t *hist, uint32_t one_bits,
+                                                  unsigned long long *__restrict__ counts);
+
+template <int CW, int STAGES, int STAGE_BYTES, int COPIES, int MINB, bool V2 = false>
 __global__ void __launch_bounds__((CW + 1) * 32, MINB)
 k_ingest_single_bulk(const double *__restrict__ vals32, size_t nvec32, const double *head, int nhead,
                      const double *tail, int ntail, unsigned long long *__restrict__ counts) {
@@ -413,7 +417,17 @@ k_ingest_single_bulk(const double *__restrict__ vals32, size_t nvec32, const dou
                 }
                 __syncwarp();
                 if ((tid & 31) == 0) mbar_arrive(&empty[s]);   // registers hold the data: release early
-                bucket_samples<2 * PER_THREAD>(v, my, counts);
+                if constexpr (V2) {
+                    uint32_t one_bits;
+                    asm volatile("mov.b32 %0, 0x3F800000;" : "=r"(one_bits));
+#pragma unroll
+                    for (int q = 0; q < 2 * PER_THREAD; q += 4) {
+                        const double v4[4] = {v[q], v[q + 1], v[q + 2], v[q + 3]};
+                        bucket_samples_v2<4>(v4, my, one_bits, counts);
+                    }
+                } else {
+                    bucket_samples<2 * PER_THREAD>(v, my, counts);
+                }
             } else {
                 for (int j = tid; j < (int)rem; j += CT) {
                     double2 d = st[j];
