@@ -386,7 +386,7 @@ def run_b200(a):
             "gpu_launches": launches, "count_ok": count_ok, "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
-                         "kernel": "k_ingest_keyed" if keyed else "k_ingest_single_ldg (%s)" % eng.k1_variants()[0],
+                         "kernel": "k_ingest_keyed" if keyed else "k_ingest_single (%s)" % eng.k1_variant_name(),
                          "kernel_ms": kms, "bytes_per_sample": bytes_per_sample},
             "allreduce_ms": ar_ms,
         }

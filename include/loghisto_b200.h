@@ -235,6 +235,7 @@ LH_API lh_status lh_memcpy_d2h(lh_ctx *ctx, void *h_dst, const void *d_src, size
  * "k1_grid_mult", "keyed_blocks_per_sm" */
 LH_API lh_status lh_tune(lh_ctx *ctx, const char *key, int64_t value);
 LH_API int32_t lh_k1_variant_count(void);
+LH_API int32_t lh_k1_variant_current(lh_ctx *ctx);
 LH_API const char *lh_k1_variant_name(lh_ctx *ctx, int32_t i);
 /* time the last `lh_ingest_*` launch range on its stream: CUDA events bracket
  * every ingest kernel; returns the device time of the most recent one in ms */

@@ -105,6 +105,7 @@ SIGNATURES = {
     "lh_memcpy_d2h": (_i32, [_vp, _vp, _vp, _sz]),
     "lh_tune": (_i32, [_vp, C.c_char_p, C.c_int64]),
     "lh_k1_variant_count": (_i32, []),
+    "lh_k1_variant_current": (_i32, [_vp]),
     "lh_k1_variant_name": (C.c_char_p, [_vp, _i32]),
     "lh_last_kernel_ms": (_i32, [_vp, C.POINTER(C.c_float)]),
     "lh_ingest_seq": (_u64, [_vp]),

@@ -114,7 +114,7 @@ K1Variant g_k1_variants[] = {
     BULK2_VARIANT(16, 5, 32768, 1),   // 27
 };
 constexpr int kNumK1Variants = (int)(sizeof(g_k1_variants) / sizeof(g_k1_variants[0]));
-constexpr int kDefaultK1Variant = 0;
+constexpr int kDefaultK1Variant = 24;   // bulk2_w16_s4_32768_b1: best burst and sustained time (profiles/r01/k1_variants_sustained.txt)
 
 }  // namespace
 
@@ -1009,6 +1009,7 @@ extern "C" lh_status lh_tune(lh_ctx *ctx, const char *key, int64_t value) {
 }
 
 extern "C" int32_t lh_k1_variant_count(void) { return kNumK1Variants; }
+extern "C" int32_t lh_k1_variant_current(lh_ctx *ctx) { return ctx ? ctx->k1_variant : -1; }
 extern "C" const char *lh_k1_variant_name(lh_ctx *ctx, int32_t i) {
     if (!ctx || i < 0 || i >= kNumK1Variants) return "";
     return ctx->k1[i].name;

@@ -197,6 +197,9 @@ class Engine:
     def k1_variants(self) -> list:
         return [self.lib.lh_k1_variant_name(self.h, i).decode() for i in range(self.lib.lh_k1_variant_count())]
 
+    def k1_variant_name(self) -> str:
+        return self.lib.lh_k1_variant_name(self.h, self.lib.lh_k1_variant_current(self.h)).decode()
+
     def last_kernel_ms(self) -> float:
         ms = C.c_float()
         self._check(self.lib.lh_last_kernel_ms(self.h, C.byref(ms)))

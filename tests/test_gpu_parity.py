@@ -134,6 +134,7 @@ def test_ingest_single_every_variant(eng, lh, oracle, offset):
     vals = oracle.gen_stream(lh.STREAM_S, n + 8, SEED ^ offset)
     want = oracle.ingest(vals[offset:offset + n])
     d = eng.upload(vals)
+    default = eng.lib.lh_k1_variant_current(eng.h)
     for vi, name in enumerate(eng.k1_variants()):
         if name.startswith("probe"):
             continue
@@ -143,7 +144,7 @@ def test_ingest_single_every_variant(eng, lh, oracle, offset):
         got = dense_from_sparse(sp, 2)
         assert (got == want).all(), (name, offset, np.nonzero(got != want)[0][:10])
         assert int(red.counts[2]) == n and int(red.counts[0]) == 0
-    eng.tune("k1", 0)
+    eng.tune("k1", default)
     d.free()
 
 
@@ -151,13 +152,14 @@ def test_ingest_single_every_variant(eng, lh, oracle, offset):
 def test_ingest_single_ragged_sizes(eng, lh, oracle, n):
     vals = oracle.gen_stream(lh.STREAM_S, n + 4, SEED + n)
     d = eng.upload(vals)
-    for vi in (0, 5):
+    default = eng.lib.lh_k1_variant_current(eng.h)
+    for vi in (0, 5, 13, 17, 24):
         eng.tune("k1", vi)
         eng.ingest_f64(0, d.offset(1), n)
         red, sp = eng.snapshot(PS)
         assert (dense_from_sparse(sp, 0) == oracle.ingest(vals[1:1 + n])).all(), (n, vi)
         assert int(red.counts[0]) == n
-    eng.tune("k1", 0)
+    eng.tune("k1", default)
     d.free()
 
 
@@ -363,10 +365,11 @@ def test_full_size_properties(lh, oracle):
         d = e.gen_stream(lh.STREAM_U, n, SEED)
         e.ingest_f64(0, d, n)                                   # one call
         cuts = [0, 1, 333_333_335, 900_000_002, n]
-        for vi, (a, b) in zip((0, 5, 7, 2), zip(cuts[:-1], cuts[1:])):   # ragged pieces, different kernels
+        default = e.lib.lh_k1_variant_current(e.h)
+        for vi, (a, b) in zip((0, 5, 21, 13), zip(cuts[:-1], cuts[1:])):   # ragged pieces, different kernels
             e.tune("k1", vi)
             e.ingest_f64(1, d.offset(a), b - a)
-        e.tune("k1", 0)
+        e.tune("k1", default)
         # the first 2e6 samples again, checked against the oracle
         e.ingest_f64(2, d, 2_000_000)
         red, sp = e.snapshot(PS)
