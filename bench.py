@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"])
     ap.add_argument("--stream", default="U", choices=["U", "L", "S", "C", "Z"])
     ap.add_argument("--n", type=int, default=0, help="samples per GPU per step (default: BASELINE config)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps for the host-fed leg (default min(steps, 5))")
@@ -221,10 +221,14 @@ def workload_config(a, n_per_gpu, n_gpus, sample_of=None):
         name = ("BASELINE configs[1]: 1 GPU, 1 histogram, 1e9-sample synthetic float64 stream" if n_gpus == 1 else
                 "BASELINE configs[3] slice: %d GPU(s), 1 histogram, %d samples per GPU, bucket-array all-reduce "
                 "before percentiles" % (n_gpus, n_per_gpu))
+    elif a.workload == "c5":
+        name = ("BASELINE configs[4]: mixed ops, 50% Histogram (u16 id, f64) / 25% Timer (u16 id, int64 ns) / 25% Counter "
+                "(u16 id, u64 amount 1..16) over 1024 names, one percentile snapshot per batch of ops "
+                "(1e8 ops = 100 ms of traffic at the nominal 1e9 ops/s)")
     else:
         name = "BASELINE configs[2]: 1024 keyed histograms, (uint16 id, float64 value) pairs"
     cfg = {"workload": name, "stream": a.stream, "samples_per_gpu_per_step": n_per_gpu,
-           "histograms": 1024 if a.workload == "c3" else 1, "percentiles": len(PERCENTILES),
+           "histograms": 1 if a.workload == "c2" else 1024, "percentiles": len(PERCENTILES),
            "l2": "inputs (%.1f GB per GPU) are larger than the 126 MB L2; no flush needed" % (n_per_gpu * 8 / 1e9),
            "published_ref": "readme.md:34 (2014, unnamed CPU, Timer path incl. two time.Now() per sample)"}
     if sample_of:
@@ -255,12 +259,13 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     keyed = a.workload == "c3"
-    n = a.n or (1_000_000_000 if (world == 1 or keyed) else 1_250_000_000)
-    H = 1024 if keyed else 1
+    mixed = a.workload == "c5"
+    n = a.n or (100_000_000 if mixed else 1_000_000_000 if (world == 1 or keyed) else 1_250_000_000)
+    H = 1 if a.workload == "c2" else 1024
     kind = {"U": 0, "L": 1, "S": 2, "C": 3, "Z": 4}[a.stream]
-    bytes_per_sample = 10 if keyed else 8
+    bytes_per_sample = 8 if a.workload == "c2" else 10
 
-    eng = lh.Engine(device=local, max_histograms=H, max_counters=1)
+    eng = lh.Engine(device=local, max_histograms=H, max_counters=1024 if mixed else 1)
     if a.k1_grid_mult:
         eng.tune("k1_grid_mult", a.k1_grid_mult)
     if a.k1_variant >= 0:
@@ -269,7 +274,15 @@ def run_b200(a):
     # other streams); torch only wraps it so that torch.cuda.Event can time the region on the launching stream
     stream = torch.cuda.ExternalStream(eng.ingest_stream, device=local)
     d_vals = eng.gen_stream(kind, n, SEED, start=rank * n, stream=stream)
-    d_ids = eng.gen_ids_u16(0, n, H, SEED, start=rank * n, stream=stream) if keyed else None
+    d_ids = eng.gen_ids_u16(0, n, H, SEED, start=rank * n, stream=stream) if (keyed or mixed) else None
+    if mixed:
+        # one batch = n ops: [0, n/2) Histogram, [n/2, 3n/4) Timer (int64 ns), [3n/4, n) Counter; ids cover all three
+        nh, nt = n // 2, n // 4
+        nc = n - nh - nt
+        d_ns = eng.alloc(nt, np.int64)
+        eng._check(eng.lib.lh_gen_stream_f64(eng.h, 6, SEED, rank * n + nh, nt, d_ns.ptr, stream.cuda_stream))
+        d_amt = eng.alloc(nc, np.uint64)
+        eng._check(eng.lib.lh_gen_stream_f64(eng.h, 7, SEED, rank * n + nh + nt, nc, d_amt.ptr, stream.cuda_stream))
     torch.cuda.synchronize()
 
     from loghisto_b200.distributed import ShardedEngine
@@ -278,6 +291,11 @@ def run_b200(a):
     allreduce_ms = []
 
     def ingest(host_src=None):
+        if mixed:
+            eng.ingest_keyed_f64_u16(d_ids, d_vals, nh, stream=stream)
+            eng.ingest_keyed_i64ns_u16(d_ids.offset(nh), d_ns, nt, stream=stream)
+            eng.counter_add_u16(d_ids.offset(nh + nt), d_amt, nc, stream=stream)
+            return
         if host_src is None:
             if keyed:
                 eng.ingest_keyed_f64_u16(d_ids, d_vals, n, stream=stream)
@@ -304,7 +322,8 @@ def run_b200(a):
                 ingest(host_src)
             red = sharded.result(h)
             if record and host_src is None:
-                kernel_ms.append(eng.kernel_ms(seq))      # CUDA events around batch i's ingest kernel
+                # CUDA events around batch i's ingest kernel(s); the mixed batch is three launches
+                kernel_ms.append(sum(eng.kernel_ms(seq - j) for j in range(3 if mixed else 1)))
                 if world > 1:
                     allreduce_ms.append(sharded.last_allreduce_ms())
         return red
@@ -340,11 +359,11 @@ def run_b200(a):
     total_ms = float(t.item())
     kms = sum(kernel_ms) / len(kernel_ms)
     ar_ms = (sum(allreduce_ms) / len(allreduce_ms)) if allreduce_ms else 0.0
-    count_ok = int(red.counts.sum()) == n * world
+    count_ok = int(red.counts.sum()) == (n - nc if mixed else n) * world
 
     # ---- host-fed leg (e2e)
     e2e = None
-    if not a.no_e2e:
+    if not a.no_e2e and not mixed:
         ksteps = a.e2e_steps or min(a.steps, 5)
         hv = eng.pinned(n, np.float64)
         eng._check(eng.lib.lh_memcpy_d2h(eng.h, hv.ptr, d_vals.ptr, n * 8))
@@ -378,7 +397,8 @@ def run_b200(a):
         achieved = n * bytes_per_sample / (kms / 1e3) / 1e9
         value = n * world * a.steps / (total_ms / 1e3)
         line = {
-            "metric": "histogram ingest throughput (samples/s)", "value": value, "unit": "samples/s",
+            "metric": "mixed op throughput (ops/s)" if mixed else "histogram ingest throughput (samples/s)",
+            "value": value, "unit": "ops/s" if mixed else "samples/s",
             "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": total_ms / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": value / PUBLISHED_SAMPLES_PER_S,
             "dtype": "f64", "data": "synthetic",
@@ -386,13 +406,13 @@ def run_b200(a):
             "gpu_launches": launches, "count_ok": count_ok, "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
-                         "kernel": "k_ingest_keyed" if keyed else "k_ingest_single (%s)" % eng.k1_variant_name(),
+                         "kernel": "k_ingest_keyed_vec x2 + k_counter_add_smem" if mixed else "k_ingest_keyed_vec" if keyed else "k_ingest_single (%s)" % eng.k1_variant_name(),
                          "kernel_ms": kms, "bytes_per_sample": bytes_per_sample},
             "allreduce_ms": ar_ms,
         }
         if e2e:
             line["e2e"] = e2e
-        if world == 1 and not a.no_cpu_baseline:
+        if world == 1 and not a.no_cpu_baseline and not mixed:
             rate, threads, ns, dense, ladder = cpu_port_rate(H, kind, a.cpu_seconds)
             line["cpu_baseline"] = {
                 "value": rate, "unit": "samples/s", "cores": threads, "kind": "port",

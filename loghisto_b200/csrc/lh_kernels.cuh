@@ -812,6 +812,11 @@ __device__ __forceinline__ uint64_t stream_bits(int kind, uint64_t seed, uint64_
     case 4:
         if (u >> 63) return 0x40F86A0000000000ull;
         return ((uint64_t)(1023 + c_streamL_exp[(u >> 52) & 15]) << 52) | mant;
+    case 6: {   // timer durations as int64 nanoseconds: the L stream truncated toward zero
+        double d = u64_as_f64(((uint64_t)(1023 + c_streamL_exp[(u >> 52) & 15]) << 52) | mant);
+        return (uint64_t)__double2ll_rz(d);
+    }
+    case 7: return 1 + (u >> 60);   // counter amounts 1..16
     default: return u;
     }
 }

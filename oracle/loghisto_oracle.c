@@ -370,6 +370,12 @@ LHO_EXPORT uint64_t lho_stream_bits(int kind, uint64_t seed, uint64_t i) {
         if (u >> 63) return 0x40F86A0000000000ull;
         return ((uint64_t)(1023 + kStreamLExp[(u >> 52) & 15]) << 52) | mant;
     }
+    case 6: { /* T: timer durations as int64 nanoseconds (bit pattern of an int64): the L stream truncated */
+        double d = bits_to_f64(((uint64_t)(1023 + kStreamLExp[(u >> 52) & 15]) << 52) | mant);
+        return (uint64_t)(int64_t)d;
+    }
+    case 7: /* A: counter amounts 1..16 */
+        return 1 + (u >> 60);
     default:
         return u;
     }

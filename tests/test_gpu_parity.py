@@ -385,3 +385,47 @@ def test_full_size_properties(lh, oracle):
             got[k & 0xFFFF] = c
         assert (got == want).all()
         d.free()
+
+
+def test_mixed_ops_interval_pipeline(lh, oracle):
+    """BASELINE config 5 in miniature: Histogram + Timer + Counter batches over 1024 names, one snapshot per batch,
+    snapshots pipelined behind the next batch; every interval must equal the oracle on exactly its own ops."""
+    H, C, n = 1024, 1024, 400_000
+    nh, nt = n // 2, n // 4
+    nc = n - nh - nt
+    with lh.Engine(device=0, max_histograms=H, max_counters=C) as e:
+        handles, wants = [], []
+        for it in range(3):
+            base = it * n
+            d_ids = e.gen_ids_u16(0, n, H, SEED, start=base)
+            d_v = e.gen_stream(lh.STREAM_L, nh, SEED, start=base)
+            d_ns = e.gen_stream(lh.STREAM_TIMER_NS, nt, SEED, start=base + nh)
+            d_amt = e.gen_stream(lh.STREAM_AMOUNTS, nc, SEED, start=base + nh + nt)
+            e.ingest_keyed_f64_u16(d_ids, d_v, nh)
+            e.ingest_keyed_i64ns_u16(d_ids.offset(nh), d_ns, nt)
+            e.counter_add_u16(d_ids.offset(nh + nt), d_amt, nc)
+            e.snapshot_begin()
+            handles.append(e.snapshot_reduce_async(PS))
+            sp = e.snapshot_export() if it == 2 else None
+            e.snapshot_end()
+            ids = oracle.gen_ids(0, n, H, SEED, start=base)
+            want = oracle.ingest_keyed(ids[:nh], oracle.gen_stream(oracle.STREAM_L, nh, SEED, start=base), H)
+            ns = oracle.gen_stream(oracle.STREAM_TIMER_NS, nt, SEED, start=base + nh).view(np.int64)
+            oracle.ingest_keyed_i64(ids[nh:nh + nt], ns, H, counts=want)
+            amounts = oracle.gen_stream(oracle.STREAM_AMOUNTS, nc, SEED, start=base + nh + nt).view(np.uint64)
+            wc = oracle.counter_add(ids[nh + nt:], amounts, C)
+            wants.append((want, wc))
+            for x in (d_ids, d_v, d_ns, d_amt):
+                pass   # buffers stay alive until the launches have run (freed after the loop via GC + sync)
+            e.sync()
+        for it in (1, 2):
+            red = e.snapshot_result(handles[it])
+            want, _ = wants[it]
+            assert (red.counts == want.sum(axis=1)).all()
+            for h in (0, 500, 1023):
+                ref = oracle.process_histogram(want[h], PS)
+                assert (red.pkeys[h] == ref["pkeys"]).all()
+        want, wc = wants[2]
+        assert (sp.counter_deltas == wc).all()
+        for h in (0, 77, 1023):
+            assert (dense_from_sparse(sp, h) == want[h]).all()
