@@ -309,23 +309,35 @@ def run_b200(a):
 
     def run_steps(k, host_src=None, record=False):
         """k steps.  Step i = ingest of batch i, then its snapshot (buffer swap, all-reduce, percentile
-        reduction, D2H of the results).  The snapshot of step i is only enqueued (high-priority stream, spare
-        buffer) before batch i+1 is launched, as loghisto's reaper overlaps processing with the next interval
-        (metrics.go:583-587); its results are collected on the host before step i+1's snapshot begins.  All k
-        ingests and all k snapshots complete inside the call."""
+        reduction, D2H of the results).  Snapshots are only ENQUEUED (high-priority stream, the frozen one of the
+        two buffers); the host launches batch i+1 right away and collects snapshot i-1's results, so the GPU
+        never idles on a host round trip -- the same overlap loghisto's reaper gets by handing processMetrics
+        to a worker (metrics.go:583-587).  Device-side ordering keeps the semantics exact: batch i+2 waits
+        (event) until snapshot i has drained and zeroed its buffer.  All k ingests and all k snapshots complete
+        inside the call."""
         red = None
+        pending = []          # (handle, ingest seq) of snapshots whose results are still on their way
         ingest(host_src)
-        for i in range(k):
-            seq = eng.ingest_seq()
-            h = sharded.snapshot_async(PERCENTILES)
-            if i + 1 < k:
-                ingest(host_src)
-            red = sharded.result(h)
+
+        def collect(entry):
+            h, seq = entry
+            r = sharded.result(h)
             if record and host_src is None:
-                # CUDA events around batch i's ingest kernel(s); the mixed batch is three launches
+                # CUDA events around that batch's ingest kernel(s); the mixed batch is three launches
                 kernel_ms.append(sum(eng.kernel_ms(seq - j) for j in range(3 if mixed else 1)))
                 if world > 1:
                     allreduce_ms.append(sharded.last_allreduce_ms())
+            return r
+
+        for i in range(k):
+            seq = eng.ingest_seq()
+            pending.append((sharded.snapshot_async(PERCENTILES), seq))
+            if i + 1 < k:
+                ingest(host_src)
+            if len(pending) > 1:
+                red = collect(pending.pop(0))
+        while pending:
+            red = collect(pending.pop(0))
         return red
 
     def barrier():

@@ -53,6 +53,7 @@ class ShardedEngine:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.last_allreduce_events = None
+        self._ar_events = []
         self._views = {}     # device pointer -> cached zero-copy tensor
         self._ext = None
 
@@ -80,6 +81,9 @@ class ShardedEngine:
                 allreduce_sum_u64(self._tensor(int(v.d_counters), int(v.n_counter_words)), self.group)
             e1.record(ext)
         self.last_allreduce_events = (e0, e1)
+        self._ar_events.append((e0, e1))
+        if len(self._ar_events) > 8:
+            self._ar_events.pop(0)
 
     def snapshot(self, percentiles, export: bool = False, counters: bool = False):
         eng = self.engine
@@ -109,8 +113,9 @@ class ShardedEngine:
         return self.engine.snapshot_result(handle)
 
     def last_allreduce_ms(self) -> float:
-        if not self.last_allreduce_events:
+        """Device time of the oldest all-reduce not yet reported (FIFO, matching result() order)."""
+        if not self._ar_events:
             return 0.0
-        e0, e1 = self.last_allreduce_events
+        e0, e1 = self._ar_events.pop(0)
         e1.synchronize()
         return float(e0.elapsed_time(e1))
