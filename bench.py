@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--k1-grid-mult", type=int, default=0, help="override the K1 waves-per-launch tuning")
     ap.add_argument("--k1-variant", type=int, default=-1)
+    ap.add_argument("--reserve-sms", type=int, default=-1, help="SMs K1 leaves free for the snapshot stream (default: 0 at N=1, 2 at N>1)")
     return ap.parse_args()
 
 
@@ -255,6 +256,7 @@ def run_b200(a):
     dist = None
     if world > 1:
         os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")   # the bucket all-reduce outranks the ingest kernel
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")          # 512 KiB payload: latency-bound, keep its CTAs few
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -270,6 +272,9 @@ def run_b200(a):
         eng.tune("k1_grid_mult", a.k1_grid_mult)
     if a.k1_variant >= 0:
         eng.tune("k1", a.k1_variant)
+    reserve = a.reserve_sms if a.reserve_sms >= 0 else (2 if world > 1 else 0)
+    if reserve:
+        eng.tune("k1_reserve_sms", reserve)
     # launch on the context's own non-blocking ingest stream (torch's legacy default stream serialises against
     # other streams); torch only wraps it so that torch.cuda.Event can time the region on the launching stream
     stream = torch.cuda.ExternalStream(eng.ingest_stream, device=local)

@@ -152,6 +152,7 @@ struct lh_ctx {
     // tuning
     int k1_variant = kDefaultK1Variant;
     int k1_grid_mult = 1;
+    int k1_reserve_sms = 0;   // SMs left free for concurrent snapshot / collective kernels
     int keyed_blocks_per_sm = 8;
     K1Variant k1[kNumK1Variants];
     // timing of the most recent ingest kernel
@@ -241,7 +242,7 @@ lh_status launch_single(lh_ctx *ctx, uint32_t hid, const double *d_values, size_
         const double *tail = body + nvec * 4;
         int ntail = (int)(m - nhead - nvec * 4);
         size_t consumed = m;
-        int grid = ctx->sm_count * kv.blocks_per_sm * ctx->k1_grid_mult;
+        int grid = std::max(1, ctx->sm_count - ctx->k1_reserve_sms) * kv.blocks_per_sm * ctx->k1_grid_mult;
         kv.launch(grid, kv.smem, s, body, nvec, head, nhead, tail, ntail, counts);
         LH_CUDA(ctx, cudaGetLastError());
         ctx->stats.kernel_launches++;
@@ -998,6 +999,11 @@ extern "C" lh_status lh_tune(lh_ctx *ctx, const char *key, int64_t value) {
     if (!strcmp(key, "k1_grid_mult")) {
         if (value < 1 || value > 64) return fail(ctx, LH_ERR_RANGE, "k1_grid_mult out of range");
         ctx->k1_grid_mult = (int)value;
+        return LH_OK;
+    }
+    if (!strcmp(key, "k1_reserve_sms")) {
+        if (value < 0 || value >= ctx->sm_count) return fail(ctx, LH_ERR_RANGE, "k1_reserve_sms out of range");
+        ctx->k1_reserve_sms = (int)value;
         return LH_OK;
     }
     if (!strcmp(key, "keyed_blocks_per_sm")) {
