@@ -272,7 +272,7 @@ def run_b200(a):
         eng.tune("k1_grid_mult", a.k1_grid_mult)
     if a.k1_variant >= 0:
         eng.tune("k1", a.k1_variant)
-    reserve = a.reserve_sms if a.reserve_sms >= 0 else (2 if world > 1 else 0)
+    reserve = a.reserve_sms if a.reserve_sms >= 0 else (2 if world > 1 else 1)
     if reserve:
         eng.tune("k1_reserve_sms", reserve)
     # launch on the context's own non-blocking ingest stream (torch's legacy default stream serialises against
@@ -336,9 +336,8 @@ def run_b200(a):
 
         for i in range(k):
             seq = eng.ingest_seq()
-            pending.append((sharded.snapshot_async(PERCENTILES), seq))
-            if i + 1 < k:
-                ingest(host_src)
+            nxt = (lambda: ingest(host_src)) if i + 1 < k else None     # batch i+1 goes out right after the swap
+            pending.append((sharded.snapshot_async(PERCENTILES, after_swap=nxt), seq))
             if len(pending) > 1:
                 red = collect(pending.pop(0))
         while pending:

@@ -97,11 +97,17 @@ class ShardedEngine:
             eng.snapshot_end()
         return red, sp
 
-    def snapshot_async(self, percentiles, counters: bool = False):
-        """begin + all-reduce + reduce + end, all enqueued; returns a handle for result()."""
+    def snapshot_async(self, percentiles, counters: bool = False, after_swap=None):
+        """begin + all-reduce + reduce + end, all enqueued; returns a handle for result().
+
+        `after_swap` (optional callable) runs right after the buffer swap and before the collective is issued:
+        pipelined callers launch the next interval's ingest there, so that it is already queued on the device
+        should the collective's host call take time."""
         eng = self.engine
         eng.snapshot_begin()
         try:
+            if after_swap is not None:
+                after_swap()
             if self.world > 1:
                 self._allreduce_frozen(counters)
             h = eng.snapshot_reduce_async(percentiles)
