@@ -233,7 +233,8 @@ LH_API lh_status lh_memcpy_h2d(lh_ctx *ctx, void *d_dst, const void *h_src, size
 LH_API lh_status lh_memcpy_d2h(lh_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
 /* kernel-variant selection for profiling: key "k1" -> variant number,
  * "k1_grid_mult", "k1_reserve_sms" (SMs the single-histogram kernel leaves free so that a concurrent
- * snapshot / all-reduce kernel can run beside it), "keyed_blocks_per_sm" */
+ * snapshot / all-reduce kernel can run beside it), "keyed_blocks_per_sm", "keyed_mode" (0 auto, 1 L2-atomic
+ * kernel, 2 owner-partitioned kernel), "kp_chunk" (samples per chunk of the owner-partitioned kernel) */
 LH_API lh_status lh_tune(lh_ctx *ctx, const char *key, int64_t value);
 LH_API int32_t lh_k1_variant_count(void);
 LH_API int32_t lh_k1_variant_current(lh_ctx *ctx);

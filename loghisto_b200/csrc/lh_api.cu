@@ -154,6 +154,13 @@ struct lh_ctx {
     int k1_grid_mult = 1;
     int k1_reserve_sms = 0;   // SMs left free for concurrent snapshot / collective kernels
     int keyed_blocks_per_sm = 8;
+    int keyed_mode = 0;                 // 0 auto, 1 force L2-atomic kernel, 2 force owner-partitioned kernel
+    int64_t kp_chunk = 16 << 20;        // samples per chunk of the partitioned kernel
+    // owner-partitioned keyed kernel scratch (allocated on first use)
+    unsigned short *d_kp_queues = nullptr;
+    unsigned int *d_kp_tail = nullptr;    // [2][P] tails, then the barrier word
+    size_t kp_cap = 0;
+    int kp_parts = 0;
     K1Variant k1[kNumK1Variants];
     // timing of the most recent ingest kernel
     // CUDA events bracket every ingest launch; a ring keeps the last kTimingRing of them
@@ -264,6 +271,41 @@ lh_status fold_hot(lh_ctx *ctx, int b, cudaStream_t s) {
     return LH_OK;
 }
 
+// Owner-partitioned keyed kernel: worth it (and possible) when there are enough histograms that they cannot
+// be privatised per CTA, few enough that P owners can hold them (ids_per <= 10), and enough samples.
+template <typename IdT, typename ValT>
+lh_status launch_keyed_part(lh_ctx *ctx, int b, const IdT *ids, const ValT *vals, size_t n4x4, cudaStream_t s, bool *used) {
+    *used = false;
+    const int P = std::min(ctx->sm_count - ctx->k1_reserve_sms, KP_MAX_PARTS);
+    if (P < 8) return LH_OK;
+    const uint32_t ids_per = (ctx->H + P - 1) / P;
+    const bool eligible = ids_per <= 10 && ctx->H >= 16 && n4x4 >= ((size_t)1 << 22);
+    if (ctx->keyed_mode == 1 || (ctx->keyed_mode == 0 && !eligible) || ids_per > 10) return LH_OK;
+    const size_t slice_tiles = std::max<size_t>(1, ((size_t)ctx->kp_chunk + (size_t)P * KP_TILE - 1) / ((size_t)P * KP_TILE));
+    const size_t cap = ((slice_tiles * KP_TILE * 2 + 7) / 8) * 8;          // 2x the expected records per owner per chunk
+    if (!ctx->d_kp_queues || ctx->kp_cap != cap || ctx->kp_parts != P) {
+        cudaFree(ctx->d_kp_queues); cudaFree(ctx->d_kp_tail);
+        ctx->d_kp_queues = nullptr; ctx->d_kp_tail = nullptr;
+        LH_CUDA(ctx, cudaMalloc(&ctx->d_kp_queues, (size_t)2 * P * cap * sizeof(unsigned short)));
+        LH_CUDA(ctx, cudaMalloc(&ctx->d_kp_tail, ((size_t)2 * P + 1) * sizeof(unsigned int)));
+        ctx->kp_cap = cap; ctx->kp_parts = P;
+    }
+    const size_t smem = (size_t)ids_per * LH_WIN * 4 + 3 * KP_MAX_PARTS * 4 + (size_t)KP_TILE * 6;
+    const void *fn = (const void *)k_ingest_keyed_part<IdT, ValT>;
+    LH_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LH_CUDA(ctx, cudaMemsetAsync(ctx->d_kp_tail, 0, ((size_t)2 * P + 1) * sizeof(unsigned int), s));
+    KpParams prm{};
+    prm.ids = ids; prm.vals = vals; prm.n = n4x4; prm.H = ctx->H; prm.ids_per = ids_per; prm.cap = (uint32_t)cap;
+    prm.slice_tiles = (uint32_t)slice_tiles; prm.queues = ctx->d_kp_queues; prm.q_tail = ctx->d_kp_tail;
+    prm.barrier = ctx->d_kp_tail + 2 * P; prm.hot = ctx->buf[b].d_hot; prm.buckets = ctx->buf[b].d_buckets;
+    prm.dropped = ctx->d_dropped;
+    void *args[] = {&prm};
+    LH_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(P), dim3(KP_THREADS), args, smem, s));
+    ctx->stats.kernel_launches++;
+    *used = true;
+    return LH_OK;
+}
+
 template <typename IdT, typename ValT>
 lh_status launch_keyed(lh_ctx *ctx, const IdT *d_ids, const ValT *d_vals, size_t n, cudaStream_t s) {
     if (((uintptr_t)d_vals & 7u) || ((uintptr_t)d_ids & (sizeof(IdT) - 1)))
@@ -293,10 +335,15 @@ lh_status launch_keyed(lh_ctx *ctx, const IdT *d_ids, const ValT *d_vals, size_t
             ctx->stats.kernel_launches++;
         }
         if (n4) {
-            int grid = grid_1d(ctx, n4, T, 1, ctx->keyed_blocks_per_sm);
-            k_ingest_keyed_vec<IdT, ValT, T><<<grid, T, 0, s>>>(ids + head, vals + head, n4, ctx->H, ctx->buf[b].d_hot,
-                                                                ctx->buf[b].d_buckets, ctx->d_dropped);
-            ctx->stats.kernel_launches++;
+            bool used = false;
+            st = launch_keyed_part<IdT, ValT>(ctx, b, ids + head, vals + head, n4 * 4, s, &used);
+            if (st != LH_OK) return st;
+            if (!used) {
+                int grid = grid_1d(ctx, n4, T, 1, ctx->keyed_blocks_per_sm);
+                k_ingest_keyed_vec<IdT, ValT, T><<<grid, T, 0, s>>>(ids + head, vals + head, n4, ctx->H, ctx->buf[b].d_hot,
+                                                                    ctx->buf[b].d_buckets, ctx->d_dropped);
+                ctx->stats.kernel_launches++;
+            }
         }
         if (tail_off < m) {
             size_t r = m - tail_off;
@@ -490,6 +537,7 @@ extern "C" lh_status lh_destroy(lh_ctx *ctx) {
         for (auto &w : ctx->buf[b].writers) cudaEventDestroy(w.ev);
     }
     cudaFree(ctx->d_decomp); cudaFree(ctx->d_dropped);
+    cudaFree(ctx->d_kp_queues); cudaFree(ctx->d_kp_tail);
     for (int i = 0; i < 2; i++) {
         cudaFree(ctx->d_ps[i]); cudaFree(ctx->d_res[i]);
         if (ctx->h_res[i]) cudaFreeHost(ctx->h_res[i]);
@@ -1004,6 +1052,16 @@ extern "C" lh_status lh_tune(lh_ctx *ctx, const char *key, int64_t value) {
     if (!strcmp(key, "k1_reserve_sms")) {
         if (value < 0 || value >= ctx->sm_count) return fail(ctx, LH_ERR_RANGE, "k1_reserve_sms out of range");
         ctx->k1_reserve_sms = (int)value;
+        return LH_OK;
+    }
+    if (!strcmp(key, "keyed_mode")) {
+        if (value < 0 || value > 2) return fail(ctx, LH_ERR_RANGE, "keyed_mode is 0 (auto), 1 (L2 atomics) or 2 (owner-partitioned)");
+        ctx->keyed_mode = (int)value;
+        return LH_OK;
+    }
+    if (!strcmp(key, "kp_chunk")) {
+        if (value < (1 << 16) || value > ((int64_t)1 << 28)) return fail(ctx, LH_ERR_RANGE, "kp_chunk out of range");
+        ctx->kp_chunk = value;
         return LH_OK;
     }
     if (!strcmp(key, "keyed_blocks_per_sm")) {

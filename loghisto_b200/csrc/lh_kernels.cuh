@@ -529,6 +529,221 @@ k_ingest_keyed(const IdT *__restrict__ ids, const ValT *__restrict__ vals, size_
         keyed_one<ValT>((uint32_t)ids[i], vals[i], H, hot, buckets, dropped, pol);
 }
 
+// ------------------------------------------------------------- K1k/partitioned
+// Gets the keyed path past the L2 atomic rate (one RED sector per sample).  One persistent cooperative CTA per
+// SM; CTA p OWNS the histogram ids {p, p+P, p+2P, ...} and keeps their positive windows (uint32[ids_per][4368])
+// in shared memory for the whole launch.  The stream is processed in chunks; per chunk
+//   phase A  every CTA bins its slice: bucket index via the fast path, a 16-bit record (lid*4368 + slot) per
+//            sample, counting-sorted by owner in shared memory and appended to the owner's queue in global
+//            memory as contiguous runs (queues are sized to stay L2-resident);
+//   barrier  grid-wide;
+//   phase B  every CTA drains its own queue into its shared-memory windows with shared atomics.
+// Queues are double-buffered by chunk parity, so one grid barrier per chunk suffices.  Samples the window does
+// not cover (negative, |v| >= 2^63, NaN/Inf), ids >= H and records that would overflow a queue take the
+// L2-atomic route of k_ingest_keyed.  At the end each CTA adds its windows into the uint32 hot window.
+constexpr int KP_THREADS = 1024;
+constexpr int KP_TILE = 8192;                 // samples per binning tile (8 per thread)
+constexpr int KP_MAX_PARTS = 160;
+
+struct KpParams {
+    const void *ids;                 // IdT[n], 4*sizeof(IdT)-aligned
+    const void *vals;                // ValT[n], 32-byte aligned
+    size_t n;                        // multiple of 4
+    uint32_t H;
+    uint32_t ids_per;                // ceil(H / P)
+    uint32_t cap;                    // records per queue per parity
+    uint32_t slice_tiles;            // tiles per CTA per chunk
+    unsigned short *queues;          // [2][P][cap]
+    unsigned int *q_tail;            // [2][P]
+    unsigned int *barrier;           // grid barrier counter (monotonic)
+    unsigned int *hot;               // [H][LH_SUBHIST]
+    unsigned long long *buckets;     // [H][65536]
+    unsigned long long *dropped;
+};
+
+__device__ __forceinline__ void kp_grid_barrier(unsigned int *bar, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+template <typename IdT, typename ValT>
+__global__ void __launch_bounds__(KP_THREADS, 1)
+k_ingest_keyed_part(KpParams prm) {
+    extern __shared__ __align__(16) unsigned char kp_smem[];
+    const int P = gridDim.x, p = blockIdx.x, tid = threadIdx.x;
+    unsigned int *s_hist = reinterpret_cast<unsigned int *>(kp_smem);                       // [ids_per][LH_WIN]
+    const size_t hist_words = (size_t)prm.ids_per * LH_WIN;
+    unsigned int *s_cnt = s_hist + hist_words;                                              // [KP_MAX_PARTS]
+    unsigned int *s_start = s_cnt + KP_MAX_PARTS;                                           // exclusive scan
+    unsigned int *s_gbase = s_start + KP_MAX_PARTS;                                         // global base per owner, or ~0
+    unsigned int *s_dst = s_gbase + KP_MAX_PARTS;                                           // [KP_TILE] global record index
+    unsigned short *s_rec = reinterpret_cast<unsigned short *>(s_dst + KP_TILE);            // [KP_TILE]
+
+    for (size_t i = tid; i < hist_words; i += KP_THREADS) s_hist[i] = 0;
+    for (unsigned int i = tid; i < KP_TILE; i += KP_THREADS) s_dst[i] = 0xFFFFFFFFu;
+    const uint64_t pol = policy_evict_last();
+    __syncthreads();
+
+    const size_t tiles_total = (prm.n + KP_TILE - 1) / KP_TILE;
+    const size_t chunk_tiles = (size_t)prm.slice_tiles * P;
+    const size_t nchunks = (tiles_total + chunk_tiles - 1) / chunk_tiles;
+    const IdT *ids = reinterpret_cast<const IdT *>(prm.ids);
+    const char *vals = reinterpret_cast<const char *>(prm.vals);
+
+    for (size_t c = 0; c < nchunks; c++) {
+        const int par = (int)(c & 1);
+        unsigned short *qset = prm.queues + (size_t)par * P * prm.cap;
+        unsigned int *tails = prm.q_tail + (size_t)par * P;
+        // ---------------- phase A: bin my slice of chunk c
+        for (uint32_t t = 0; t < prm.slice_tiles; t++) {
+            const size_t tile = c * chunk_tiles + (size_t)p * prm.slice_tiles + t;
+            if (tile >= tiles_total) break;                       // uniform per CTA
+            const size_t s0 = tile * KP_TILE;
+            if (tid < KP_MAX_PARTS) s_cnt[tid] = 0;
+            __syncthreads();
+            uint32_t part[8], pos[8], rec[8];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const size_t g = s0 + (size_t)h * (KP_TILE / 2) + (size_t)tid * 4;   // 4 consecutive samples
+                uint32_t id4[4];
+                unsigned long long raw[4];
+                const bool in = g < prm.n;                         // n is a multiple of 4
+                if (in) {
+                    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
+                                 : "=l"(raw[0]), "=l"(raw[1]), "=l"(raw[2]), "=l"(raw[3]) : "l"(vals + g * 8));
+                    if (sizeof(IdT) == 2) {
+                        unsigned int lo, hi;
+                        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi)
+                                     : "l"(reinterpret_cast<const char *>(ids) + g * 2));
+                        id4[0] = lo & 0xFFFFu; id4[1] = lo >> 16; id4[2] = hi & 0xFFFFu; id4[3] = hi >> 16;
+                    } else {
+                        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(id4[0]), "=r"(id4[1]), "=r"(id4[2]), "=r"(id4[3])
+                                     : "l"(reinterpret_cast<const char *>(ids) + g * 4));
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int q = h * 4 + j;
+                    part[q] = 0xFFFFFFFFu;                          // "no record"
+                    if (!in) continue;
+                    const uint32_t id = id4[j];
+                    if (id >= prm.H) { atomicAdd(prm.dropped, 1ull); continue; }
+                    ValT rv;
+                    memcpy(&rv, &raw[j], 8);
+                    const double v = sample_to_f64<ValT>(rv);
+                    uint32_t idx; bool slow;
+                    fast_candidate(v, idx, slow);
+                    if (slow) {
+                        const uint32_t key = exact_key16(v);
+                        idx = key16_to_slot(key);
+                        if (idx == 0xFFFFFFFFu) { atomicAdd(&prm.buckets[(size_t)id * 65536u + key], 1ull); continue; }
+                    }
+                    if (idx >= (uint32_t)LH_WIN) {                  // negative window: L2 route
+                        red_add_u32_keep(&prm.hot[(size_t)id * LH_SUBHIST + idx], 1u, pol);
+                        continue;
+                    }
+                    const uint32_t owner = id % (uint32_t)P, lid = id / (uint32_t)P;
+                    part[q] = owner;
+                    rec[q] = lid * (uint32_t)LH_WIN + idx;
+                    pos[q] = atomicAdd(&s_cnt[owner], 1u);
+                }
+            }
+            __syncthreads();
+            // exclusive scan of the per-owner counts (P <= 160: one warp, 5 per lane) + global reservations
+            if (tid < 32) {
+                unsigned int loc[5], sum = 0;
+#pragma unroll
+                for (int k = 0; k < 5; k++) { int o = tid * 5 + k; loc[k] = (o < P) ? s_cnt[o] : 0; sum += loc[k]; }
+                unsigned int incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { unsigned int y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (tid >= o) incl += y; }
+                unsigned int run = incl - sum;
+#pragma unroll
+                for (int k = 0; k < 5; k++) { int o = tid * 5 + k; if (o < P) s_start[o] = run; run += loc[k]; }
+            }
+            if (tid >= 32 && tid < 32 + P) {
+                const int o = tid - 32;
+                const unsigned int cnt = s_cnt[o];
+                unsigned int base = 0xFFFFFFFFu;
+                if (cnt) {
+                    base = atomicAdd(&tails[o], cnt);
+                    if (base + cnt > prm.cap) base = 0xFFFFFFFFu;   // queue full: these records take the L2 route
+                }
+                s_gbase[o] = base;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (part[q] == 0xFFFFFFFFu) continue;
+                const uint32_t o = part[q];
+                const unsigned int gb = s_gbase[o];
+                if (gb == 0xFFFFFFFFu) {                            // overflow fallback
+                    const uint32_t lid = rec[q] / (uint32_t)LH_WIN, slot = rec[q] - lid * (uint32_t)LH_WIN;
+                    red_add_u32_keep(&prm.hot[(size_t)(lid * (uint32_t)P + o) * LH_SUBHIST + slot], 1u, pol);
+                    continue;
+                }
+                const unsigned int si = s_start[o] + pos[q];
+                s_rec[si] = (unsigned short)rec[q];
+                s_dst[si] = o * prm.cap + gb + pos[q];
+            }
+            __syncthreads();
+            // copy out: consecutive threads write consecutive records of one owner's run
+            {
+                unsigned int total = s_start[P - 1] + s_cnt[P - 1];
+                for (unsigned int i = tid; i < total; i += KP_THREADS) {
+                    // entries of overflowed owners were never written: mark by dst sentinel
+                    const unsigned int d = s_dst[i];
+                    if (d != 0xFFFFFFFFu) qset[d] = s_rec[i];
+                }
+            }
+            __syncthreads();
+            // reset the staging marks for overflow detection on the next tile
+            for (unsigned int i = tid; i < KP_TILE; i += KP_THREADS) s_dst[i] = 0xFFFFFFFFu;
+        }
+        // ---------------- barrier: every record of chunk c is in its owner's queue
+        kp_grid_barrier(prm.barrier, (unsigned int)((c + 1) * (size_t)P));
+        // ---------------- phase B: drain my queue
+        {
+            unsigned int nrec;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(nrec) : "l"(&tails[p]) : "memory");
+            if (nrec > prm.cap) nrec = prm.cap;
+            const unsigned short *q = qset + (size_t)p * prm.cap;
+            const unsigned int nvec = nrec / 8;
+            for (unsigned int i = tid; i < nvec; i += KP_THREADS) {
+                uint4 w = __ldcg(reinterpret_cast<const uint4 *>(q) + i);
+                const unsigned int ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    atomicAdd(&s_hist[ww[k] & 0xFFFFu], 1u);
+                    atomicAdd(&s_hist[ww[k] >> 16], 1u);
+                }
+            }
+            for (unsigned int i = nvec * 8 + tid; i < nrec; i += KP_THREADS)
+                atomicAdd(&s_hist[__ldcg(q + i)], 1u);
+            __syncthreads();
+            if (tid == 0) tails[p] = 0;      // this parity is written again two chunks from now, after another barrier
+        }
+    }
+    __syncthreads();
+    // ---------------- flush my windows into the uint32 hot window
+    for (size_t i = tid; i < hist_words; i += KP_THREADS) {
+        const unsigned int cnt = s_hist[i];
+        if (!cnt) continue;
+        const uint32_t lid = (uint32_t)(i / LH_WIN), slot = (uint32_t)(i - (size_t)lid * LH_WIN);
+        const uint32_t id = lid * (uint32_t)P + (uint32_t)p;
+        if (id < prm.H) atomicAdd(&prm.hot[(size_t)id * LH_SUBHIST + slot], cnt);
+    }
+}
+
 // Drain the hot window into the uint64 buckets.  atomicExch/atomicAdd so that ingest on other
 // streams may keep running against the same buffer.
 __global__ void k_fold_hot(unsigned int *__restrict__ hot, unsigned long long *__restrict__ buckets, size_t cells) {

@@ -429,3 +429,48 @@ def test_mixed_ops_interval_pipeline(lh, oracle):
         assert (sp.counter_deltas == wc).all()
         for h in (0, 77, 1023):
             assert (dense_from_sparse(sp, h) == want[h]).all()
+
+
+@pytest.mark.parametrize("chunk", [65536, 1 << 20])
+def test_keyed_owner_partitioned_kernel(lh, oracle, chunk):
+    """The owner-partitioned keyed kernel (bin -> per-owner queues -> shared-memory windows) against the oracle:
+    several chunks (grid barriers, queue parity), signed/edge values, skewed ids, out-of-range ids, and a
+    single-id stream that overflows one owner's queue and must fall back without losing a sample."""
+    H, n = 1024, 1_500_001
+    with lh.Engine(device=0, max_histograms=H, max_counters=1) as e:
+        e.tune("keyed_mode", 2)
+        e.tune("kp_chunk", chunk)
+        for stream, idkind in ((lh.STREAM_S, 0), (lh.STREAM_U, 1), (lh.STREAM_L, 0)):
+            vals = oracle.gen_stream(stream, n, SEED ^ 0x31)
+            ids = oracle.gen_ids(idkind, n, H, SEED ^ 0x31)
+            want = oracle.ingest_keyed(ids, vals, H)
+            d_v, d_i16, d_i32 = e.upload(vals), e.upload(ids.astype(np.uint16)), e.upload(ids)
+            e.ingest_keyed_f64_u16(d_i16, d_v, n)
+            red, sp = e.snapshot(PS)
+            assert (red.counts == want.sum(axis=1)).all(), (stream, idkind)
+            for h in (0, 1, 147, 148, 500, 1023):
+                assert (dense_from_sparse(sp, h) == want[h]).all(), (stream, h)
+            e.ingest_keyed_f64_u32(d_i32, d_v, n)
+            red2, sp2 = e.snapshot(PS)
+            assert (sp2.counts == sp.counts).all() and (sp2.keys == sp.keys).all()
+            for x in (d_v, d_i16, d_i32):
+                x.free()
+        # timer samples through the same kernel
+        ns = oracle.gen_stream(oracle.STREAM_TIMER_NS, n, SEED).view(np.int64)
+        ids = oracle.gen_ids(0, n, H, SEED)
+        want = oracle.ingest_keyed_i64(ids, ns, H)
+        d_n, d_i = e.upload(ns), e.upload(ids.astype(np.uint16))
+        e.ingest_keyed_i64ns_u16(d_i, d_n, n)
+        red, _ = e.snapshot(PS)
+        assert (red.counts == want.sum(axis=1)).all()
+        # one id only: its owner's queue overflows, the surplus takes the L2 route; ids >= H are dropped
+        vals = oracle.gen_stream(lh.STREAM_U, n, SEED ^ 5)
+        ids = np.full(n, 777, dtype=np.uint32)
+        ids[::1000] = 60000
+        d_v, d_i = e.upload(vals), e.upload(ids.astype(np.uint16))
+        before = e.stats()["dropped"]
+        e.ingest_keyed_f64_u16(d_i, d_v, n)
+        red, sp = e.snapshot(PS)
+        keep = ids == 777
+        assert (dense_from_sparse(sp, 777) == oracle.ingest(vals[keep])).all()
+        assert int(red.counts.sum()) == int(keep.sum()) and e.stats()["dropped"] - before == int((~keep).sum())
