@@ -282,22 +282,25 @@ lh_status launch_keyed_part(lh_ctx *ctx, int b, const IdT *ids, const ValT *vals
     const bool eligible = ids_per <= 10 && ctx->H >= 16 && n4x4 >= ((size_t)1 << 22);
     if (ctx->keyed_mode == 1 || (ctx->keyed_mode == 0 && !eligible) || ids_per > 10) return LH_OK;
     const size_t slice_tiles = std::max<size_t>(1, ((size_t)ctx->kp_chunk + (size_t)P * KP_TILE - 1) / ((size_t)P * KP_TILE));
-    const size_t cap = ((slice_tiles * KP_TILE * 2 + 7) / 8) * 8;          // 2x the expected records per owner per chunk
+    // every (owner, writer) pair has its own sub-queue: 2x the expected records per pair per chunk, plus slack
+    const size_t expect = slice_tiles * KP_TILE / P;
+    const size_t cap = ((expect * 2 + 256 + 7) / 8) * 8;
     if (!ctx->d_kp_queues || ctx->kp_cap != cap || ctx->kp_parts != P) {
         cudaFree(ctx->d_kp_queues); cudaFree(ctx->d_kp_tail);
         ctx->d_kp_queues = nullptr; ctx->d_kp_tail = nullptr;
-        LH_CUDA(ctx, cudaMalloc(&ctx->d_kp_queues, (size_t)2 * P * cap * sizeof(unsigned short)));
-        LH_CUDA(ctx, cudaMalloc(&ctx->d_kp_tail, ((size_t)2 * P + 1) * sizeof(unsigned int)));
+        LH_CUDA(ctx, cudaMalloc(&ctx->d_kp_queues, (size_t)2 * P * P * cap * sizeof(unsigned short)));
+        LH_CUDA(ctx, cudaMalloc(&ctx->d_kp_tail, ((size_t)2 * P * P + 1) * sizeof(unsigned int)));
         ctx->kp_cap = cap; ctx->kp_parts = P;
     }
     const size_t smem = (size_t)ids_per * LH_WIN * 4 + 3 * KP_MAX_PARTS * 4 + (size_t)KP_TILE * 6;
     const void *fn = (const void *)k_ingest_keyed_part<IdT, ValT>;
     LH_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LH_CUDA(ctx, cudaMemsetAsync(ctx->d_kp_tail, 0, ((size_t)2 * P + 1) * sizeof(unsigned int), s));
+    unsigned int *d_barrier = ctx->d_kp_tail + (size_t)2 * P * P;
+    LH_CUDA(ctx, cudaMemsetAsync(d_barrier, 0, sizeof(unsigned int), s));
     KpParams prm{};
     prm.ids = ids; prm.vals = vals; prm.n = n4x4; prm.H = ctx->H; prm.ids_per = ids_per; prm.cap = (uint32_t)cap;
-    prm.slice_tiles = (uint32_t)slice_tiles; prm.queues = ctx->d_kp_queues; prm.q_tail = ctx->d_kp_tail;
-    prm.barrier = ctx->d_kp_tail + 2 * P; prm.hot = ctx->buf[b].d_hot; prm.buckets = ctx->buf[b].d_buckets;
+    prm.slice_tiles = (uint32_t)slice_tiles; prm.queues = ctx->d_kp_queues; prm.q_cnt = ctx->d_kp_tail;
+    prm.barrier = d_barrier; prm.hot = ctx->buf[b].d_hot; prm.buckets = ctx->buf[b].d_buckets;
     prm.dropped = ctx->d_dropped;
     void *args[] = {&prm};
     LH_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(P), dim3(KP_THREADS), args, smem, s));

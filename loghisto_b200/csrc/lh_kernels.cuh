@@ -533,14 +533,15 @@ k_ingest_keyed(const IdT *__restrict__ ids, const ValT *__restrict__ vals, size_
 // Gets the keyed path past the L2 atomic rate (one RED sector per sample).  One persistent cooperative CTA per
 // SM; CTA p OWNS the histogram ids {p, p+P, p+2P, ...} and keeps their positive windows (uint32[ids_per][4368])
 // in shared memory for the whole launch.  The stream is processed in chunks; per chunk
-//   phase A  every CTA bins its slice: bucket index via the fast path, a 16-bit record (lid*4368 + slot) per
-//            sample, counting-sorted by owner in shared memory and appended to the owner's queue in global
-//            memory as contiguous runs (queues are sized to stay L2-resident);
-//   barrier  grid-wide;
-//   phase B  every CTA drains its own queue into its shared-memory windows with shared atomics.
-// Queues are double-buffered by chunk parity, so one grid barrier per chunk suffices.  Samples the window does
-// not cover (negative, |v| >= 2^63, NaN/Inf), ids >= H and records that would overflow a queue take the
-// L2-atomic route of k_ingest_keyed.  At the end each CTA adds its windows into the uint32 hot window.
+//   phase A  every CTA ("writer" w) bins its slice: bucket index via the fast path, a 16-bit record
+//            (lid*4368 + slot) per sample, counting-sorted by owner in shared memory and appended as contiguous
+//            runs to the (owner, writer) sub-queue in global memory -- every pair has its own region, so the
+//            append offsets live in shared memory and no global atomic is needed; at the end of the slice the
+//            writer publishes its P record counts;
+//   barrier  grid-wide (one per chunk; sub-queues are double-buffered by chunk parity);
+//   phase B  every owner drains its P sub-queues (L2 hits) into its shared-memory windows with shared atomics.
+// Samples the window does not cover (negative, |v| >= 2^63, NaN/Inf), ids >= H and records that do not fit their
+// sub-queue take the L2-atomic route of k_ingest_keyed.  At the end each CTA adds its windows into the hot window.
 constexpr int KP_THREADS = 1024;
 constexpr int KP_TILE = 8192;                 // samples per binning tile (8 per thread)
 constexpr int KP_MAX_PARTS = 160;
@@ -551,11 +552,11 @@ struct KpParams {
     size_t n;                        // multiple of 4
     uint32_t H;
     uint32_t ids_per;                // ceil(H / P)
-    uint32_t cap;                    // records per queue per parity
+    uint32_t cap;                    // records per (owner, writer) sub-queue per parity, multiple of 8
     uint32_t slice_tiles;            // tiles per CTA per chunk
-    unsigned short *queues;          // [2][P][cap]
-    unsigned int *q_tail;            // [2][P]
-    unsigned int *barrier;           // grid barrier counter (monotonic)
+    unsigned short *queues;          // [2][P owners][P writers][cap]
+    unsigned int *q_cnt;             // [2][P owners][P writers]
+    unsigned int *barrier;           // grid barrier counter, zeroed by the host before the launch
     unsigned int *hot;               // [H][LH_SUBHIST]
     unsigned long long *buckets;     // [H][65536]
     unsigned long long *dropped;
@@ -578,13 +579,13 @@ template <typename IdT, typename ValT>
 __global__ void __launch_bounds__(KP_THREADS, 1)
 k_ingest_keyed_part(KpParams prm) {
     extern __shared__ __align__(16) unsigned char kp_smem[];
-    const int P = gridDim.x, p = blockIdx.x, tid = threadIdx.x;
+    const int P = gridDim.x, p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned int *s_hist = reinterpret_cast<unsigned int *>(kp_smem);                       // [ids_per][LH_WIN]
     const size_t hist_words = (size_t)prm.ids_per * LH_WIN;
-    unsigned int *s_cnt = s_hist + hist_words;                                              // [KP_MAX_PARTS]
-    unsigned int *s_start = s_cnt + KP_MAX_PARTS;                                           // exclusive scan
-    unsigned int *s_gbase = s_start + KP_MAX_PARTS;                                         // global base per owner, or ~0
-    unsigned int *s_dst = s_gbase + KP_MAX_PARTS;                                           // [KP_TILE] global record index
+    unsigned int *s_cnt = s_hist + hist_words;                                              // per-owner count, this tile
+    unsigned int *s_start = s_cnt + KP_MAX_PARTS;                                           // exclusive scan of s_cnt
+    unsigned int *s_off = s_start + KP_MAX_PARTS;                                           // records appended this chunk
+    unsigned int *s_dst = s_off + KP_MAX_PARTS;                                             // [KP_TILE] global record index
     unsigned short *s_rec = reinterpret_cast<unsigned short *>(s_dst + KP_TILE);            // [KP_TILE]
 
     for (size_t i = tid; i < hist_words; i += KP_THREADS) s_hist[i] = 0;
@@ -597,12 +598,14 @@ k_ingest_keyed_part(KpParams prm) {
     const size_t nchunks = (tiles_total + chunk_tiles - 1) / chunk_tiles;
     const IdT *ids = reinterpret_cast<const IdT *>(prm.ids);
     const char *vals = reinterpret_cast<const char *>(prm.vals);
+    const unsigned int cap = prm.cap;
 
     for (size_t c = 0; c < nchunks; c++) {
-        const int par = (int)(c & 1);
-        unsigned short *qset = prm.queues + (size_t)par * P * prm.cap;
-        unsigned int *tails = prm.q_tail + (size_t)par * P;
-        // ---------------- phase A: bin my slice of chunk c
+        const size_t par = c & 1;
+        unsigned short *qset = prm.queues + par * (size_t)P * P * cap;      // [owner][writer][cap]
+        unsigned int *cset = prm.q_cnt + par * (size_t)P * P;              // [owner][writer]
+        if (tid < KP_MAX_PARTS) s_off[tid] = 0;
+        // ---------------- phase A: bin my slice of chunk c (I am writer p)
         for (uint32_t t = 0; t < prm.slice_tiles; t++) {
             const size_t tile = c * chunk_tiles + (size_t)p * prm.slice_tiles + t;
             if (tile >= tiles_total) break;                       // uniform per CTA
@@ -658,80 +661,67 @@ k_ingest_keyed_part(KpParams prm) {
                 }
             }
             __syncthreads();
-            // exclusive scan of the per-owner counts (P <= 160: one warp, 5 per lane) + global reservations
-            if (tid < 32) {
+            // exclusive scan of the per-owner counts (P <= 160: one warp, 5 per lane)
+            if (warp == 0) {
                 unsigned int loc[5], sum = 0;
 #pragma unroll
-                for (int k = 0; k < 5; k++) { int o = tid * 5 + k; loc[k] = (o < P) ? s_cnt[o] : 0; sum += loc[k]; }
+                for (int k = 0; k < 5; k++) { int o = lane * 5 + k; loc[k] = (o < P) ? s_cnt[o] : 0; sum += loc[k]; }
                 unsigned int incl = sum;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { unsigned int y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (tid >= o) incl += y; }
+                for (int o = 1; o < 32; o <<= 1) { unsigned int y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
                 unsigned int run = incl - sum;
 #pragma unroll
-                for (int k = 0; k < 5; k++) { int o = tid * 5 + k; if (o < P) s_start[o] = run; run += loc[k]; }
-            }
-            if (tid >= 32 && tid < 32 + P) {
-                const int o = tid - 32;
-                const unsigned int cnt = s_cnt[o];
-                unsigned int base = 0xFFFFFFFFu;
-                if (cnt) {
-                    base = atomicAdd(&tails[o], cnt);
-                    if (base + cnt > prm.cap) base = 0xFFFFFFFFu;   // queue full: these records take the L2 route
-                }
-                s_gbase[o] = base;
+                for (int k = 0; k < 5; k++) { int o = lane * 5 + k; if (o < P) s_start[o] = run; run += loc[k]; }
             }
             __syncthreads();
 #pragma unroll
             for (int q = 0; q < 8; q++) {
                 if (part[q] == 0xFFFFFFFFu) continue;
                 const uint32_t o = part[q];
-                const unsigned int gb = s_gbase[o];
-                if (gb == 0xFFFFFFFFu) {                            // overflow fallback
+                const unsigned int at = s_off[o] + pos[q];          // position inside my sub-queue for owner o
+                if (at >= cap) {                                    // sub-queue full: L2 route
                     const uint32_t lid = rec[q] / (uint32_t)LH_WIN, slot = rec[q] - lid * (uint32_t)LH_WIN;
                     red_add_u32_keep(&prm.hot[(size_t)(lid * (uint32_t)P + o) * LH_SUBHIST + slot], 1u, pol);
                     continue;
                 }
                 const unsigned int si = s_start[o] + pos[q];
                 s_rec[si] = (unsigned short)rec[q];
-                s_dst[si] = o * prm.cap + gb + pos[q];
+                s_dst[si] = (o * (unsigned int)P + (unsigned int)p) * cap + at;
             }
             __syncthreads();
-            // copy out: consecutive threads write consecutive records of one owner's run
-            {
-                unsigned int total = s_start[P - 1] + s_cnt[P - 1];
+            {   // copy out: consecutive threads write consecutive records of one owner's run
+                const unsigned int total = s_start[P - 1] + s_cnt[P - 1];
                 for (unsigned int i = tid; i < total; i += KP_THREADS) {
-                    // entries of overflowed owners were never written: mark by dst sentinel
                     const unsigned int d = s_dst[i];
-                    if (d != 0xFFFFFFFFu) qset[d] = s_rec[i];
+                    if (d != 0xFFFFFFFFu) { qset[d] = s_rec[i]; s_dst[i] = 0xFFFFFFFFu; }
                 }
             }
+            if (tid < P) s_off[tid] += s_cnt[tid];
             __syncthreads();
-            // reset the staging marks for overflow detection on the next tile
-            for (unsigned int i = tid; i < KP_TILE; i += KP_THREADS) s_dst[i] = 0xFFFFFFFFu;
         }
-        // ---------------- barrier: every record of chunk c is in its owner's queue
+        // publish my P counts (zero for owners I sent nothing to), then the grid-wide barrier
+        if (tid < P) cset[(size_t)tid * P + p] = min(s_off[tid], cap);
         kp_grid_barrier(prm.barrier, (unsigned int)((c + 1) * (size_t)P));
-        // ---------------- phase B: drain my queue
-        {
-            unsigned int nrec;
-            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(nrec) : "l"(&tails[p]) : "memory");
-            if (nrec > prm.cap) nrec = prm.cap;
-            const unsigned short *q = qset + (size_t)p * prm.cap;
+        // ---------------- phase B: drain the P sub-queues I own; warp w takes writers w, w+32, ...
+        for (int w = warp; w < P; w += KP_THREADS / 32) {
+            unsigned int nrec = 0;
+            if (lane == 0) nrec = __ldcg(&cset[(size_t)p * P + w]);
+            nrec = __shfl_sync(0xFFFFFFFFu, nrec, 0);
+            const unsigned short *q = qset + ((size_t)p * P + w) * cap;
             const unsigned int nvec = nrec / 8;
-            for (unsigned int i = tid; i < nvec; i += KP_THREADS) {
-                uint4 w = __ldcg(reinterpret_cast<const uint4 *>(q) + i);
-                const unsigned int ww[4] = {w.x, w.y, w.z, w.w};
+            for (unsigned int i = lane; i < nvec; i += 32) {
+                const uint4 v4 = __ldcg(reinterpret_cast<const uint4 *>(q) + i);
+                const unsigned int ww[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     atomicAdd(&s_hist[ww[k] & 0xFFFFu], 1u);
                     atomicAdd(&s_hist[ww[k] >> 16], 1u);
                 }
             }
-            for (unsigned int i = nvec * 8 + tid; i < nrec; i += KP_THREADS)
-                atomicAdd(&s_hist[__ldcg(q + i)], 1u);
-            __syncthreads();
-            if (tid == 0) tails[p] = 0;      // this parity is written again two chunks from now, after another barrier
+            for (unsigned int i = nvec * 8 + lane; i < nrec; i += 32) atomicAdd(&s_hist[__ldcg(q + i)], 1u);
         }
+        // no barrier here: the next chunk writes the other parity; this parity is rewritten only after the
+        // next grid barrier, which every CTA reaches after finishing this drain
     }
     __syncthreads();
     // ---------------- flush my windows into the uint32 hot window
