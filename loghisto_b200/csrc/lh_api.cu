@@ -279,8 +279,10 @@ lh_status launch_keyed_part(lh_ctx *ctx, int b, const IdT *ids, const ValT *vals
     const int P = std::min(ctx->sm_count - ctx->k1_reserve_sms, KP_MAX_PARTS);
     if (P < 8) return LH_OK;
     const uint32_t ids_per = (ctx->H + P - 1) / P;
-    const bool eligible = ids_per <= 10 && ctx->H >= 16 && n4x4 >= ((size_t)1 << 22);
-    if (ctx->keyed_mode == 1 || (ctx->keyed_mode == 0 && !eligible) || ids_per > 10) return LH_OK;
+    // Opt-in only (lh_tune "keyed_mode" = 2): measured 141 G samples/s against 167 G/s for the L2-atomic kernel
+    // (profiles/r01/keyed_modes.txt) -- phase A is latency-bound without a prefetch stage -- so "auto" keeps the
+    // L2-atomic kernel until that is fixed.
+    if (ctx->keyed_mode != 2 || ids_per > 10 || n4x4 == 0) return LH_OK;
     const size_t slice_tiles = std::max<size_t>(1, ((size_t)ctx->kp_chunk + (size_t)P * KP_TILE - 1) / ((size_t)P * KP_TILE));
     // every (owner, writer) pair has its own sub-queue: 2x the expected records per pair per chunk, plus slack
     const size_t expect = slice_tiles * KP_TILE / P;
