@@ -155,6 +155,7 @@ struct lh_ctx {
     int k1_reserve_sms = 0;   // SMs left free for concurrent snapshot / collective kernels
     int keyed_blocks_per_sm = 8;
     int keyed_mode = 0;                 // 0 auto, 1 force L2-atomic kernel, 2 force owner-partitioned kernel
+    int kp_shape = 1;                   // owner-partitioned kernel: 0 = 1x1024 threads per SM, 1 = 2x512
     int64_t kp_chunk = 16 << 20;        // samples per chunk of the partitioned kernel
     // owner-partitioned keyed kernel scratch (allocated on first use)
     unsigned short *d_kp_queues = nullptr;
@@ -276,16 +277,19 @@ lh_status fold_hot(lh_ctx *ctx, int b, cudaStream_t s) {
 template <typename IdT, typename ValT>
 lh_status launch_keyed_part(lh_ctx *ctx, int b, const IdT *ids, const ValT *vals, size_t n4x4, cudaStream_t s, bool *used) {
     *used = false;
-    const int P = std::min(ctx->sm_count - ctx->k1_reserve_sms, KP_MAX_PARTS);
+    // kp_shape 0: one 1024-thread CTA per SM; 1: two 512-thread CTAs per SM (stalls of one overlap the other)
+    const bool two = ctx->kp_shape == 1;
+    const int threads = two ? 512 : 1024, tile = threads * 8;
+    const int P = std::min((ctx->sm_count - ctx->k1_reserve_sms) * (two ? 2 : 1), KP_MAX_PARTS);
     if (P < 8) return LH_OK;
     const uint32_t ids_per = (ctx->H + P - 1) / P;
     // Opt-in only (lh_tune "keyed_mode" = 2): measured 141 G samples/s against 167 G/s for the L2-atomic kernel
     // (profiles/r01/keyed_modes.txt) -- phase A is latency-bound without a prefetch stage -- so "auto" keeps the
     // L2-atomic kernel until that is fixed.
     if (ctx->keyed_mode != 2 || ids_per > 10 || n4x4 == 0) return LH_OK;
-    const size_t slice_tiles = std::max<size_t>(1, ((size_t)ctx->kp_chunk + (size_t)P * KP_TILE - 1) / ((size_t)P * KP_TILE));
+    const size_t slice_tiles = std::max<size_t>(1, ((size_t)ctx->kp_chunk + (size_t)P * tile - 1) / ((size_t)P * tile));
     // every (owner, writer) pair has its own sub-queue: 2x the expected records per pair per chunk, plus slack
-    const size_t expect = slice_tiles * KP_TILE / P;
+    const size_t expect = slice_tiles * tile / P;
     const size_t cap = ((expect * 2 + 256 + 7) / 8) * 8;
     if (!ctx->d_kp_queues || ctx->kp_cap != cap || ctx->kp_parts != P) {
         cudaFree(ctx->d_kp_queues); cudaFree(ctx->d_kp_tail);
@@ -294,8 +298,8 @@ lh_status launch_keyed_part(lh_ctx *ctx, int b, const IdT *ids, const ValT *vals
         LH_CUDA(ctx, cudaMalloc(&ctx->d_kp_tail, ((size_t)2 * P * P + 1) * sizeof(unsigned int)));
         ctx->kp_cap = cap; ctx->kp_parts = P;
     }
-    const size_t smem = (size_t)ids_per * LH_WIN * 4 + 3 * KP_MAX_PARTS * 4 + (size_t)KP_TILE * 6;
-    const void *fn = (const void *)k_ingest_keyed_part<IdT, ValT>;
+    const size_t smem = (size_t)ids_per * LH_WIN * 4 + 3 * KP_MAX_PARTS * 4 + (size_t)tile * 6;
+    const void *fn = two ? (const void *)k_ingest_keyed_part<IdT, ValT, 512, 2> : (const void *)k_ingest_keyed_part<IdT, ValT, 1024, 1>;
     LH_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned int *d_barrier = ctx->d_kp_tail + (size_t)2 * P * P;
     LH_CUDA(ctx, cudaMemsetAsync(d_barrier, 0, sizeof(unsigned int), s));
@@ -305,7 +309,7 @@ lh_status launch_keyed_part(lh_ctx *ctx, int b, const IdT *ids, const ValT *vals
     prm.barrier = d_barrier; prm.hot = ctx->buf[b].d_hot; prm.buckets = ctx->buf[b].d_buckets;
     prm.dropped = ctx->d_dropped;
     void *args[] = {&prm};
-    LH_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(P), dim3(KP_THREADS), args, smem, s));
+    LH_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(P), dim3(threads), args, smem, s));
     ctx->stats.kernel_launches++;
     *used = true;
     return LH_OK;
@@ -1062,6 +1066,11 @@ extern "C" lh_status lh_tune(lh_ctx *ctx, const char *key, int64_t value) {
     if (!strcmp(key, "keyed_mode")) {
         if (value < 0 || value > 2) return fail(ctx, LH_ERR_RANGE, "keyed_mode is 0 (auto), 1 (L2 atomics) or 2 (owner-partitioned)");
         ctx->keyed_mode = (int)value;
+        return LH_OK;
+    }
+    if (!strcmp(key, "kp_shape")) {
+        if (value < 0 || value > 1) return fail(ctx, LH_ERR_RANGE, "kp_shape is 0 or 1");
+        ctx->kp_shape = (int)value;
         return LH_OK;
     }
     if (!strcmp(key, "kp_chunk")) {

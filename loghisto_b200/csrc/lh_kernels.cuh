@@ -542,9 +542,8 @@ k_ingest_keyed(const IdT *__restrict__ ids, const ValT *__restrict__ vals, size_
 //   phase B  every owner drains its P sub-queues (L2 hits) into its shared-memory windows with shared atomics.
 // Samples the window does not cover (negative, |v| >= 2^63, NaN/Inf), ids >= H and records that do not fit their
 // sub-queue take the L2-atomic route of k_ingest_keyed.  At the end each CTA adds its windows into the hot window.
-constexpr int KP_THREADS = 1024;
-constexpr int KP_TILE = 8192;                 // samples per binning tile (8 per thread)
-constexpr int KP_MAX_PARTS = 160;
+constexpr int KP_MAX_PARTS = 320;             // owners = CTAs: up to 2 per SM
+constexpr int KP_SCAN_PER_LANE = KP_MAX_PARTS / 32;
 
 struct KpParams {
     const void *ids;                 // IdT[n], 4*sizeof(IdT)-aligned
@@ -575,9 +574,10 @@ __device__ __forceinline__ void kp_grid_barrier(unsigned int *bar, unsigned int 
     __syncthreads();
 }
 
-template <typename IdT, typename ValT>
-__global__ void __launch_bounds__(KP_THREADS, 1)
+template <typename IdT, typename ValT, int KP_THREADS, int KP_MINB>
+__global__ void __launch_bounds__(KP_THREADS, KP_MINB)
 k_ingest_keyed_part(KpParams prm) {
+    constexpr int KP_TILE = KP_THREADS * 8;       // samples per binning tile (8 per thread)
     extern __shared__ __align__(16) unsigned char kp_smem[];
     const int P = gridDim.x, p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned int *s_hist = reinterpret_cast<unsigned int *>(kp_smem);                       // [ids_per][LH_WIN]
@@ -661,17 +661,17 @@ k_ingest_keyed_part(KpParams prm) {
                 }
             }
             __syncthreads();
-            // exclusive scan of the per-owner counts (P <= 160: one warp, 5 per lane)
+            // exclusive scan of the per-owner counts (one warp, KP_SCAN_PER_LANE owners per lane)
             if (warp == 0) {
-                unsigned int loc[5], sum = 0;
+                unsigned int loc[KP_SCAN_PER_LANE], sum = 0;
 #pragma unroll
-                for (int k = 0; k < 5; k++) { int o = lane * 5 + k; loc[k] = (o < P) ? s_cnt[o] : 0; sum += loc[k]; }
+                for (int k = 0; k < KP_SCAN_PER_LANE; k++) { int o = lane * KP_SCAN_PER_LANE + k; loc[k] = (o < P) ? s_cnt[o] : 0; sum += loc[k]; }
                 unsigned int incl = sum;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { unsigned int y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
                 unsigned int run = incl - sum;
 #pragma unroll
-                for (int k = 0; k < 5; k++) { int o = lane * 5 + k; if (o < P) s_start[o] = run; run += loc[k]; }
+                for (int k = 0; k < KP_SCAN_PER_LANE; k++) { int o = lane * KP_SCAN_PER_LANE + k; if (o < P) s_start[o] = run; run += loc[k]; }
             }
             __syncthreads();
 #pragma unroll

@@ -431,14 +431,15 @@ def test_mixed_ops_interval_pipeline(lh, oracle):
             assert (dense_from_sparse(sp, h) == want[h]).all()
 
 
-@pytest.mark.parametrize("chunk", [65536, 1 << 20])
-def test_keyed_owner_partitioned_kernel(lh, oracle, chunk):
+@pytest.mark.parametrize("chunk,shape", [(65536, 0), (1 << 20, 0), (65536, 1), (1 << 20, 1)])
+def test_keyed_owner_partitioned_kernel(lh, oracle, chunk, shape):
     """The owner-partitioned keyed kernel (bin -> per-owner queues -> shared-memory windows) against the oracle:
     several chunks (grid barriers, queue parity), signed/edge values, skewed ids, out-of-range ids, and a
     single-id stream that overflows one owner's queue and must fall back without losing a sample."""
     H, n = 1024, 1_500_001
     with lh.Engine(device=0, max_histograms=H, max_counters=1) as e:
         e.tune("keyed_mode", 2)
+        e.tune("kp_shape", shape)
         e.tune("kp_chunk", chunk)
         for stream, idkind in ((lh.STREAM_S, 0), (lh.STREAM_U, 1), (lh.STREAM_L, 0)):
             vals = oracle.gen_stream(stream, n, SEED ^ 0x31)

@@ -66,11 +66,12 @@ def main():
         for idkind in (0, 1):
             ids = eng.gen_ids_u16(idkind, nk, a.keyed, lh.DEFAULT_SEED)
             eng.gen_stream(KINDS["U"], nk, lh.DEFAULT_SEED, out=d)
-            for mode, bps in ((1, 8), (2, 8), (2, 9), (2, 10)):
+            for mode, bps in ((1, 8), (2, 8), (2, 10), (2, 18), (2, 20)):
                 eng.tune("keyed_mode", mode)
                 eng.tune("keyed_blocks_per_sm", 8)
                 if mode == 2:
-                    eng.tune("kp_chunk", {8: 16 << 20, 9: 8 << 20, 10: 32 << 20}[bps])
+                    eng.tune("kp_shape", 1 if bps >= 18 else 0)
+                    eng.tune("kp_chunk", {8: 16 << 20, 10: 32 << 20, 18: 16 << 20, 20: 32 << 20}[bps])
                 times = []
                 for it in range(a.iters + 2):
                     eng.ingest_keyed_f64_u16(ids, d, nk)
@@ -80,7 +81,8 @@ def main():
                 red, _ = eng.snapshot([0.5], export=False)
                 med = sorted(times)[len(times) // 2]
                 rec = {"kernel": "keyed_f64_u16", "ids": idkind, "H": a.keyed, "n": nk, "mode": mode,
-                       "kp_chunk": {8: 16 << 20, 9: 8 << 20, 10: 32 << 20}[bps] if mode == 2 else None,
+                       "kp_chunk": {8: 16 << 20, 10: 32 << 20, 18: 16 << 20, 20: 32 << 20}[bps] if mode == 2 else None,
+                       "kp_shape": (1 if bps >= 18 else 0) if mode == 2 else None,
                        "ms_median": med, "gsamples_s": nk / med / 1e6, "gb_s": nk * 10 / med / 1e6,
                        "count_ok": int(red.counts.sum()) == nk * (a.iters + 2)}
                 print(json.dumps(rec), flush=True)
