@@ -305,6 +305,7 @@ lh_status launch_keyed_part(lh_ctx *ctx, int b, const IdT *ids, const ValT *vals
     LH_CUDA(ctx, cudaMemsetAsync(d_barrier, 0, sizeof(unsigned int), s));
     KpParams prm{};
     prm.ids = ids; prm.vals = vals; prm.n = n4x4; prm.H = ctx->H; prm.ids_per = ids_per; prm.cap = (uint32_t)cap;
+    prm.inv_p = (uint32_t)(((uint64_t)1 << 32) / (uint64_t)P) + 1u;
     prm.slice_tiles = (uint32_t)slice_tiles; prm.queues = ctx->d_kp_queues; prm.q_cnt = ctx->d_kp_tail;
     prm.barrier = d_barrier; prm.hot = ctx->buf[b].d_hot; prm.buckets = ctx->buf[b].d_buckets;
     prm.dropped = ctx->d_dropped;

@@ -553,6 +553,7 @@ struct KpParams {
     uint32_t ids_per;                // ceil(H / P)
     uint32_t cap;                    // records per (owner, writer) sub-queue per parity, multiple of 8
     uint32_t slice_tiles;            // tiles per CTA per chunk
+    uint32_t inv_p;                  // floor(2^32 / P) + 1: id / P == __umulhi(id, inv_p) for id < 65536
     unsigned short *queues;          // [2][P owners][P writers][cap]
     unsigned int *q_cnt;             // [2][P owners][P writers]
     unsigned int *barrier;           // grid barrier counter, zeroed by the host before the launch
@@ -654,7 +655,7 @@ k_ingest_keyed_part(KpParams prm) {
                         red_add_u32_keep(&prm.hot[(size_t)id * LH_SUBHIST + idx], 1u, pol);
                         continue;
                     }
-                    const uint32_t owner = id % (uint32_t)P, lid = id / (uint32_t)P;
+                    const uint32_t lid = __umulhi(id, prm.inv_p), owner = id - lid * (uint32_t)P;   // id / P, id % P
                     part[q] = owner;
                     rec[q] = lid * (uint32_t)LH_WIN + idx;
                     pos[q] = atomicAdd(&s_cnt[owner], 1u);
