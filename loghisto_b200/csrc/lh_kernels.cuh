@@ -613,13 +613,18 @@ k_ingest_keyed_part(KpParams prm) {
             const size_t s0 = tile * KP_TILE;
             if (tid < KP_MAX_PARTS) s_cnt[tid] = 0;
             __syncthreads();
+            // Common path is branch-free: owner/record/position for every sample; samples that need anything
+            // else (id >= H, estimate too close to a boundary, |v| >= 2^63 / NaN / Inf, negative) raise one flag
+            // and are handled -- entirely, on the L2 route -- in a warp-voted fix-up.
             uint32_t part[8], pos[8], rec[8];
+            bool any_rare = false;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const size_t g = s0 + (size_t)h * (KP_TILE / 2) + (size_t)tid * 4;   // 4 consecutive samples
                 uint32_t id4[4];
-                unsigned long long raw[4];
+                unsigned long long raw[4] = {0, 0, 0, 0};
                 const bool in = g < prm.n;                         // n is a multiple of 4
+                id4[0] = id4[1] = id4[2] = id4[3] = 0;
                 if (in) {
                     asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
                                  : "=l"(raw[0]), "=l"(raw[1]), "=l"(raw[2]), "=l"(raw[3]) : "l"(vals + g * 8));
@@ -637,28 +642,32 @@ k_ingest_keyed_part(KpParams prm) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const int q = h * 4 + j;
-                    part[q] = 0xFFFFFFFFu;                          // "no record"
-                    if (!in) continue;
                     const uint32_t id = id4[j];
-                    if (id >= prm.H) { atomicAdd(prm.dropped, 1ull); continue; }
                     ValT rv;
                     memcpy(&rv, &raw[j], 8);
                     const double v = sample_to_f64<ValT>(rv);
                     uint32_t idx; bool slow;
                     fast_candidate(v, idx, slow);
-                    if (slow) {
-                        const uint32_t key = exact_key16(v);
-                        idx = key16_to_slot(key);
-                        if (idx == 0xFFFFFFFFu) { atomicAdd(&prm.buckets[(size_t)id * 65536u + key], 1ull); continue; }
-                    }
-                    if (idx >= (uint32_t)LH_WIN) {                  // negative window: L2 route
-                        red_add_u32_keep(&prm.hot[(size_t)id * LH_SUBHIST + idx], 1u, pol);
-                        continue;
-                    }
+                    const bool rare = slow | (idx >= (uint32_t)LH_WIN) | (id >= prm.H);
                     const uint32_t lid = __umulhi(id, prm.inv_p), owner = id - lid * (uint32_t)P;   // id / P, id % P
-                    part[q] = owner;
                     rec[q] = lid * (uint32_t)LH_WIN + idx;
-                    pos[q] = atomicAdd(&s_cnt[owner], 1u);
+                    // 0xFFFFFFFF = no record; 0xFFFFFFFE = rare (pending fix-up)
+                    part[q] = !in ? 0xFFFFFFFFu : rare ? 0xFFFFFFFEu : owner;
+                    any_rare |= in & rare;
+                    pos[q] = 0;
+                    if (in & !rare) pos[q] = atomicAdd(&s_cnt[owner], 1u);
+                }
+                if (__any_sync(0xFFFFFFFFu, any_rare)) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int q = h * 4 + j;
+                        if (part[q] != 0xFFFFFFFEu) continue;
+                        part[q] = 0xFFFFFFFFu;
+                        ValT rv;
+                        memcpy(&rv, &raw[j], 8);
+                        keyed_one<ValT>(id4[j], rv, prm.H, prm.hot, prm.buckets, prm.dropped, pol);
+                    }
+                    any_rare = false;
                 }
             }
             __syncthreads();
@@ -675,19 +684,33 @@ k_ingest_keyed_part(KpParams prm) {
                 for (int k = 0; k < KP_SCAN_PER_LANE; k++) { int o = lane * KP_SCAN_PER_LANE + k; if (o < P) s_start[o] = run; run += loc[k]; }
             }
             __syncthreads();
+            {
+                const unsigned int wbase = (unsigned int)p * cap;
+                bool any_full = false;
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-                if (part[q] == 0xFFFFFFFFu) continue;
-                const uint32_t o = part[q];
-                const unsigned int at = s_off[o] + pos[q];          // position inside my sub-queue for owner o
-                if (at >= cap) {                                    // sub-queue full: L2 route
-                    const uint32_t lid = rec[q] / (uint32_t)LH_WIN, slot = rec[q] - lid * (uint32_t)LH_WIN;
-                    red_add_u32_keep(&prm.hot[(size_t)(lid * (uint32_t)P + o) * LH_SUBHIST + slot], 1u, pol);
-                    continue;
+                for (int q = 0; q < 8; q++) {
+                    const uint32_t o = part[q];
+                    if (o < (uint32_t)KP_MAX_PARTS) {                   // has a record
+                        const unsigned int at = s_off[o] + pos[q];      // position inside my sub-queue for owner o
+                        const bool full = at >= cap;
+                        any_full |= full;
+                        if (!full) {
+                            const unsigned int si = s_start[o] + pos[q];
+                            s_rec[si] = (unsigned short)rec[q];
+                            s_dst[si] = o * ((unsigned int)P * cap) + wbase + at;
+                        }
+                    }
                 }
-                const unsigned int si = s_start[o] + pos[q];
-                s_rec[si] = (unsigned short)rec[q];
-                s_dst[si] = (o * (unsigned int)P + (unsigned int)p) * cap + at;
+                if (__any_sync(0xFFFFFFFFu, any_full)) {                // sub-queue full: those records take the L2 route
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const uint32_t o = part[q];
+                        if (o < (uint32_t)KP_MAX_PARTS && s_off[o] + pos[q] >= cap) {
+                            const uint32_t lid = rec[q] / (uint32_t)LH_WIN, slot = rec[q] - lid * (uint32_t)LH_WIN;
+                            red_add_u32_keep(&prm.hot[(size_t)(lid * (uint32_t)P + o) * LH_SUBHIST + slot], 1u, pol);
+                        }
+                    }
+                }
             }
             __syncthreads();
             {   // copy out: consecutive threads write consecutive records of one owner's run
