@@ -849,8 +849,8 @@ k_reduce(const unsigned long long *__restrict__ buckets, const double *__restric
     unsigned long long mine = 0;
     double msum = 0.0;
     unsigned int nnz = 0;
-#pragma unroll 4
-    for (int r = 0; r < K3_WARP_KEYS / 32; r++) {
+#pragma unroll 16
+    for (int r = 0; r < K3_WARP_KEYS / 32; r++) {      // 16 independent 256-byte rows in flight per warp
         unsigned int slot = (unsigned int)(key0 + r * 32 + lane) & 0xFFFFu;
         unsigned long long c = hb[slot];
         if (c) { mine += c; msum += decomp[slot] * (double)c; nnz++; }
