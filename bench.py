@@ -257,6 +257,7 @@ def run_b200(a):
     if world > 1:
         os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")   # the bucket all-reduce outranks the ingest kernel
         os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")          # 512 KiB payload: latency-bound, keep its CTAs few
+        os.environ.setdefault("NCCL_CGA_CLUSTER_SIZE", "0")       # no CTA clusters: its CTAs must fit the reserved SMs
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 

