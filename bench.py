@@ -53,6 +53,18 @@ def parse_args():
     return ap.parse_args()
 
 
+def measured_traffic(workload, n):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if one matches this run."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(workload)
+        if t and int(t["samples"]) == int(n):
+            return int(t["bytes"]), t["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 def peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -412,6 +424,7 @@ def run_b200(a):
     if rank == 0:
         peak, peak_src = peak_hbm()
         achieved = n * bytes_per_sample / (kms / 1e3) / 1e9
+        traffic, traffic_src = measured_traffic(a.workload, n)
         value = n * world * a.steps / (total_ms / 1e3)
         line = {
             "metric": "mixed op throughput (ops/s)" if mixed else "histogram ingest throughput (samples/s)",
@@ -422,7 +435,8 @@ def run_b200(a):
             "config": workload_config(a, n, world),
             "gpu_launches": launches, "count_ok": count_ok, "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": n * bytes_per_sample,
+                         "peak_source": peak_src,
                          "kernel": "k_ingest_keyed_vec x2 + k_counter_add_smem" if mixed else "k_ingest_keyed_vec" if keyed else "k_ingest_single (%s)" % eng.k1_variant_name(),
                          "kernel_ms": kms, "bytes_per_sample": bytes_per_sample},
             "allreduce_ms": ar_ms,

@@ -32,7 +32,8 @@ struct Buffer {
 enum SlotState { SLOT_FREE = 0, SLOT_ACQUIRED = 1, SLOT_INFLIGHT = 2 };
 struct Slot {
     void *h = nullptr; void *d = nullptr;
-    cudaEvent_t done = nullptr;
+    cudaEvent_t done = nullptr;      // kernel that consumed the slot has finished
+    cudaEvent_t copied = nullptr;    // H2D copy into the slot has landed
     int state = SLOT_FREE;
     uint64_t seq = 0;
 };
@@ -127,7 +128,7 @@ struct lh_ctx {
     int active = 0;
     bool frozen = false;
     bool nnz_valid = false;
-    cudaStream_t ingest_stream = nullptr, snap_stream = nullptr;
+    cudaStream_t ingest_stream = nullptr, snap_stream = nullptr, copy_stream = nullptr;
     double *d_decomp = nullptr;
     unsigned long long *d_dropped = nullptr;
     // reduce / export scratch
@@ -477,6 +478,7 @@ extern "C" lh_status lh_create(const lh_config *cfg, lh_ctx **out) {
     }
     ctx->sm_count = prop.multiProcessorCount;
     LH_CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->ingest_stream, cudaStreamNonBlocking));
+    LH_CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     {   // the snapshot stream outranks ingest: its small kernels slot in as soon as any ingest CTA retires
         int least = 0, greatest = 0;
         LH_CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
@@ -520,6 +522,7 @@ extern "C" lh_status lh_create(const lh_config *cfg, lh_ctx **out) {
         LH_CREATE_CUDA(cudaMallocHost(&sl.h, ctx->staging_bytes));
         LH_CREATE_CUDA(cudaMalloc(&sl.d, ctx->staging_bytes));
         LH_CREATE_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        LH_CREATE_CUDA(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
     }
 
     LH_CREATE_CUDA(cudaFuncSetAttribute((const void *)k_counter_add_smem<unsigned short, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_COUNTERS * 8));
@@ -563,12 +566,14 @@ extern "C" lh_status lh_destroy(lh_ctx *ctx) {
         if (sl.h) cudaFreeHost(sl.h);
         cudaFree(sl.d);
         if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.copied) cudaEventDestroy(sl.copied);
     }
     for (int i = 0; i < lh_ctx::kTimingRing; i++) {
         if (ctx->ev_t0s[i]) cudaEventDestroy(ctx->ev_t0s[i]);
         if (ctx->ev_t1s[i]) cudaEventDestroy(ctx->ev_t1s[i]);
     }
     if (ctx->ingest_stream) cudaStreamDestroy(ctx->ingest_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->snap_stream) cudaStreamDestroy(ctx->snap_stream);
     cudaGetLastError();
     delete ctx;
@@ -637,17 +642,24 @@ lh_status ingest_host(lh_ctx *ctx, HostKind kind, uint32_t hid, const void *h_a 
         const char *src_a = (const char *)h_a + done * 8;
         char *d_a = (char *)sl.d;
         char *d_i = (char *)sl.d + per * 8;
+        // copies run on their own stream so that chunk k+1's DMA overlaps chunk k's kernel; the slot's device
+        // buffer is free again once the kernel that read it last is done (slot_wait_free already waited on the host
+        // for a recycled slot, the event wait covers the rest)
+        cudaStream_t cs = ctx->copy_stream;
+        if (sl.seq) LH_CUDA(ctx, cudaStreamWaitEvent(cs, sl.done, 0));
         if (pinned) {
-            LH_CUDA(ctx, cudaMemcpyAsync(d_a, src_a, m * 8, cudaMemcpyHostToDevice, s));
-            if (h_ids) LH_CUDA(ctx, cudaMemcpyAsync(d_i, h_ids + done, m * 2, cudaMemcpyHostToDevice, s));
+            LH_CUDA(ctx, cudaMemcpyAsync(d_a, src_a, m * 8, cudaMemcpyHostToDevice, cs));
+            if (h_ids) LH_CUDA(ctx, cudaMemcpyAsync(d_i, h_ids + done, m * 2, cudaMemcpyHostToDevice, cs));
         } else {
             memcpy(sl.h, src_a, m * 8);
-            LH_CUDA(ctx, cudaMemcpyAsync(d_a, sl.h, m * 8, cudaMemcpyHostToDevice, s));
+            LH_CUDA(ctx, cudaMemcpyAsync(d_a, sl.h, m * 8, cudaMemcpyHostToDevice, cs));
             if (h_ids) {
                 memcpy((char *)sl.h + per * 8, h_ids + done, m * 2);
-                LH_CUDA(ctx, cudaMemcpyAsync(d_i, (char *)sl.h + per * 8, m * 2, cudaMemcpyHostToDevice, s));
+                LH_CUDA(ctx, cudaMemcpyAsync(d_i, (char *)sl.h + per * 8, m * 2, cudaMemcpyHostToDevice, cs));
             }
         }
+        LH_CUDA(ctx, cudaEventRecord(sl.copied, cs));
+        LH_CUDA(ctx, cudaStreamWaitEvent(s, sl.copied, 0));
         ctx->stats.h2d_bytes += m * item;
         if (kind == HK_SINGLE) st = launch_single(ctx, hid, (const double *)d_a, m, s);
         else if (kind == HK_KEYED_U16) st = launch_keyed<unsigned short, double>(ctx, (const unsigned short *)d_i, (const double *)d_a, m, s);
@@ -714,12 +726,16 @@ lh_status staging_commit(lh_ctx *ctx, const lh_staging *sg, HostKind kind, uint3
     cudaStream_t s = ctx->ingest_stream;
     lh_status st = LH_OK;
     if (n) {
-        LH_CUDA(ctx, cudaMemcpyAsync(sl.d, sl.h, item_bytes, cudaMemcpyHostToDevice, s));
+        cudaStream_t cs = ctx->copy_stream;
+        if (sl.seq) LH_CUDA(ctx, cudaStreamWaitEvent(cs, sl.done, 0));
+        LH_CUDA(ctx, cudaMemcpyAsync(sl.d, sl.h, item_bytes, cudaMemcpyHostToDevice, cs));
         ctx->stats.h2d_bytes += item_bytes;
         if (kind != HK_SINGLE) {
-            LH_CUDA(ctx, cudaMemcpyAsync((char *)sl.d + ids_offset, (char *)sl.h + ids_offset, n * 2, cudaMemcpyHostToDevice, s));
+            LH_CUDA(ctx, cudaMemcpyAsync((char *)sl.d + ids_offset, (char *)sl.h + ids_offset, n * 2, cudaMemcpyHostToDevice, cs));
             ctx->stats.h2d_bytes += n * 2;
         }
+        LH_CUDA(ctx, cudaEventRecord(sl.copied, cs));
+        LH_CUDA(ctx, cudaStreamWaitEvent(s, sl.copied, 0));
         if (kind == HK_SINGLE) st = launch_single(ctx, hid, (const double *)sl.d, n, s);
         else if (kind == HK_KEYED_U16) st = launch_keyed<unsigned short, double>(ctx, (const unsigned short *)((char *)sl.d + ids_offset), (const double *)sl.d, n, s);
         else st = launch_counter<unsigned short>(ctx, (const unsigned short *)((char *)sl.d + ids_offset), (const uint64_t *)sl.d, n, s);
