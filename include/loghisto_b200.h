@@ -109,6 +109,13 @@ LH_API lh_status lh_ingest_keyed_f64_u16_host(lh_ctx *ctx, const uint16_t *h_ids
 LH_API lh_status lh_counter_add_u16_host(lh_ctx *ctx, const uint16_t *h_ids, const uint64_t *h_amounts,
                                   size_t n);
 
+/* ---- merging snapshots --------------------------------------------------
+ * Adds n sparse (histogram id, int16 key, uint64 count) triples -- the format lh_snapshot_export returns -- into
+ * the ACTIVE bucket arrays.  Bucket counts are a commutative monoid, so snapshots taken on other hosts or GPUs
+ * merge exactly; it also lets a caller re-reduce a RawMetricSet it holds. */
+LH_API lh_status lh_merge_counts_host(lh_ctx *ctx, const uint32_t *h_ids, const int16_t *h_keys,
+                                      const uint64_t *h_counts, size_t n);
+
 /* ---- pinned staging ring (the cgo-friendly feed) ------------------------
  * cgo forbids C code from keeping Go pointers after a call returns, so the
  * shim fills C-owned pinned memory instead.  A slot of `staging_bytes` is laid

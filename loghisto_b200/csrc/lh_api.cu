@@ -696,6 +696,35 @@ extern "C" lh_status lh_counter_add_u16_host(lh_ctx *ctx, const uint16_t *h_ids,
     return ingest_host(ctx, HK_COUNTER_U16, 0, h_amounts, h_ids, n);
 }
 
+// Merge sparse bucket counts held in host memory (e.g. another process's lh_snapshot_export) into the ACTIVE arrays.
+extern "C" lh_status lh_merge_counts_host(lh_ctx *ctx, const uint32_t *h_ids, const int16_t *h_keys, const uint64_t *h_counts, size_t n) {
+    LH_ENTER(ctx);
+    if (n && (!h_ids || !h_keys || !h_counts)) return fail(ctx, LH_ERR_INVALID, "NULL input");
+    if (!n) return LH_OK;
+    cudaStream_t s = ctx->ingest_stream;
+    const int b = ctx->active;
+    lh_status st = before_write(ctx, b, s);
+    if (st != LH_OK) return st;
+    char *d = nullptr;
+    const size_t off_keys = n * 4, off_counts = ((n * 6 + 7) / 8) * 8, total = off_counts + n * 8;
+    LH_CUDA(ctx, cudaMallocAsync((void **)&d, total, s));
+    cudaError_t e = cudaMemcpyAsync(d, h_ids, n * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + off_keys, h_keys, n * 2, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + off_counts, h_counts, n * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        int grid = grid_1d(ctx, n, 256, 1, 8);
+        k_merge_sparse<<<grid, 256, 0, s>>>((const uint32_t *)d, (const short *)(d + off_keys), (const unsigned long long *)(d + off_counts),
+                                            n, ctx->H, ctx->buf[b].d_buckets, ctx->d_dropped);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(d, s);
+    if (e != cudaSuccess) return fail(ctx, LH_ERR_CUDA, "lh_merge_counts_host", e);
+    ctx->stats.kernel_launches++;
+    ctx->stats.h2d_bytes += n * 14;
+    LH_CUDA(ctx, cudaStreamSynchronize(s));   // the host arrays may be pageable: they have been read by now
+    return after_write(ctx, b, s);
+}
+
 // =========================================================== staging ring
 extern "C" lh_status lh_staging_acquire(lh_ctx *ctx, lh_staging *out) {
     LH_ENTER(ctx);

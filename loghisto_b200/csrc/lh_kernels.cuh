@@ -819,6 +819,20 @@ k_counter_add(const IdT *__restrict__ ids, const unsigned long long *__restrict_
     }
 }
 
+// ------------------------------------------------------------------- merge
+// Adds sparse (histogram id, int16 key, uint64 count) triples -- the wire format lh_snapshot_export produces --
+// into the bucket arrays: merging snapshots from other hosts / GPUs is the same commutative uint64 sum.
+__global__ void k_merge_sparse(const uint32_t *__restrict__ ids, const short *__restrict__ keys,
+                               const unsigned long long *__restrict__ counts, size_t n, uint32_t H,
+                               unsigned long long *__restrict__ buckets, unsigned long long *__restrict__ dropped) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t id = ids[i];
+        if (id >= H) { atomicAdd(dropped, 1ull); continue; }
+        atomicAdd(&buckets[(size_t)id * 65536u + ((uint32_t)(int)keys[i] & 0xFFFFu)], counts[i]);
+    }
+}
+
 // ---------------------------------------------------------------------- K3
 // One CTA per histogram, 32 warps.  Warp w owns the 2048 consecutive keys
 // [-32768 + 2048 w, +2047] (ascending key == ascending value, the order

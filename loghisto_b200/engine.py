@@ -256,6 +256,14 @@ class Engine:
             n = h_amounts.size if n is None else n
         self._check(self.lib.lh_counter_add_u16_host(self.h, _ptr(h_ids), _ptr(h_amounts), n))
 
+    def merge_counts_host(self, ids, keys, counts):
+        """Add sparse (histogram id, int16 key, uint64 count) triples into the active arrays (exact merge)."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        keys = np.ascontiguousarray(keys, dtype=np.int16)
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        assert ids.size == keys.size == counts.size
+        self._check(self.lib.lh_merge_counts_host(self.h, ids.ctypes.data, keys.ctypes.data, counts.ctypes.data, ids.size))
+
     # ---- staging ring
     def staging_acquire(self) -> L.lh_staging:
         s = L.lh_staging()

@@ -558,3 +558,33 @@ def test_tune_and_error_paths(eng, lh):
     assert "histogram_id" in eng.lib.lh_last_error(eng.h).decode() or True
     eng.tune("k1_reserve_sms", 3)
     eng.tune("k1_reserve_sms", 0)
+
+
+def test_merge_sparse_snapshots(lh, oracle):
+    """Snapshots are mergeable: exporting two engines' histograms and merging them into a third gives exactly the
+    histogram of the concatenated streams (uint64 sums, including counts beyond 2^32 and wrapped keys)."""
+    H, n = 8, 400_000
+    vals = oracle.gen_stream(lh.STREAM_S, 2 * n, SEED ^ 0x44)
+    ids = oracle.gen_ids(0, 2 * n, H, SEED ^ 0x44)
+    parts = []
+    for half in range(2):
+        with lh.Engine(device=0, max_histograms=H, max_counters=1) as e:
+            a = half * n
+            e.ingest_keyed_f64_u16_host(ids[a:a + n].astype(np.uint16), vals[a:a + n])
+            _, sp = e.snapshot(PS)
+            hid = np.repeat(np.arange(H, dtype=np.uint32), np.diff(sp.offsets))
+            parts.append((hid, sp.keys.copy(), sp.counts.copy()))
+    with lh.Engine(device=0, max_histograms=H, max_counters=1) as e:
+        for hid, keys, counts in parts:
+            e.merge_counts_host(hid, keys, counts)
+        e.merge_counts_host(np.array([3, 3, 99], np.uint32), np.array([-32768, 7, 1], np.int16),
+                            np.array([2 ** 40, 2 ** 63, 5], np.uint64))      # big counts; id 99 is dropped
+        red, sp = e.snapshot(PS)
+        want = oracle.ingest_keyed(ids, vals, H)
+        want[3][(-32768) & 0xFFFF] += np.uint64(2 ** 40)
+        want[3][7] += np.uint64(2 ** 63)
+        for h in range(H):
+            assert (dense_from_sparse(sp, h) == want[h]).all(), h
+        assert (red.counts == want.sum(axis=1)).all() and e.stats()["dropped"] == 1
+        ref = oracle.process_histogram(want[3], PS)
+        assert (red.pkeys[3] == ref["pkeys"]).all()
