@@ -529,6 +529,113 @@ k_ingest_keyed(const IdT *__restrict__ ids, const ValT *__restrict__ vals, size_
         keyed_one<ValT>((uint32_t)ids[i], vals[i], H, hot, buckets, dropped, pol);
 }
 
+// ------------------------------------------------------------------ K1k/small
+// Keyed ingest when only a few histograms are configured (H <= KS_MAX_H): all their positive windows
+// (uint32[H][4368]) are privatised per CTA in shared memory, exactly like K1, so the kernel is HBM-bound
+// (10 B/sample) instead of L2-atomic-bound.  Same packed-FP32 bucket arithmetic as bucket_samples_v2; the ONE
+// flag per sample also covers id >= H, and flagged samples (boundary-close estimates, negatives, |v| >= 2^63,
+// NaN/Inf, bad ids) take the L2 route of keyed_one().  Windows are added into the uint32 hot window at the end.
+constexpr int KS_MAX_H = 11;                 // 11 * 4368 * 4 B = 192 KB of shared memory
+constexpr int KS_THREADS = 1024;
+
+template <typename IdT, typename ValT>
+__global__ void __launch_bounds__(KS_THREADS, 1)
+k_ingest_keyed_small(const IdT *__restrict__ ids, const ValT *__restrict__ vals, size_t n4, uint32_t H,
+                     unsigned int *__restrict__ hot, unsigned long long *__restrict__ buckets,
+                     unsigned long long *__restrict__ dropped) {
+    extern __shared__ __align__(16) uint32_t ks_hist[];          // [H][LH_WIN] + trash word
+    const uint32_t words = H * (uint32_t)LH_WIN;
+    for (uint32_t i = threadIdx.x; i <= words; i += KS_THREADS) ks_hist[i] = 0;
+    __syncthreads();
+    const uint64_t pol = policy_evict_last();
+    uint32_t one_bits;
+    asm volatile("mov.b32 %0, 0x3F800000;" : "=r"(one_bits));
+    constexpr float C1 = 69.31471805599453f, C2 = 0.31471805599453f;
+    constexpr float KB = (float)(-1023.0 * (double)C2);
+    constexpr float MAGIC = 12582912.0f;
+    constexpr uint32_t COFF = 0u - (1023u * 69u * 4u) - (0x4B400000u << 2);
+    const uint32_t trash_off = words * 4u;
+
+    const size_t stride = (size_t)gridDim.x * KS_THREADS;
+    size_t g = (size_t)blockIdx.x * KS_THREADS + threadIdx.x;
+    unsigned long long cur[4], nxt[4];
+    uint32_t cur_id[4], nxt_id[4];
+    auto load = [&](unsigned long long(&raw)[4], uint32_t(&id4)[4], size_t gi) {
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
+                     : "=l"(raw[0]), "=l"(raw[1]), "=l"(raw[2]), "=l"(raw[3]) : "l"(reinterpret_cast<const char *>(vals) + gi * 32));
+        if (sizeof(IdT) == 2) {
+            unsigned int lo, hi;
+            asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi)
+                         : "l"(reinterpret_cast<const char *>(ids) + gi * 8));
+            id4[0] = lo & 0xFFFFu; id4[1] = lo >> 16; id4[2] = hi & 0xFFFFu; id4[3] = hi >> 16;
+        } else {
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(id4[0]), "=r"(id4[1]), "=r"(id4[2]), "=r"(id4[3])
+                         : "l"(reinterpret_cast<const char *>(ids) + gi * 16));
+        }
+    };
+    if (g < n4) load(cur, cur_id, g);
+    while (g < n4) {
+        const size_t gn = g + stride;
+        if (gn < n4) load(nxt, nxt_id, gn);
+        uint32_t off[4];
+        bool flag[4];
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < 4; i += 2) {
+            ValT r0, r1;
+            memcpy(&r0, &cur[i], 8); memcpy(&r1, &cur[i + 1], 8);
+            const double v0 = sample_to_f64<ValT>(r0), v1 = sample_to_f64<ValT>(r1);
+            const double x0 = __dadd_rn(1.0, fabs(v0)), x1 = __dadd_rn(1.0, fabs(v1));
+            const uint32_t h0 = (uint32_t)__double2hiint(x0), h1 = (uint32_t)__double2hiint(x1);
+            const uint32_t t0 = __funnelshift_l((uint32_t)__double2loint(x0), h0, 3);
+            const uint32_t t1 = __funnelshift_l((uint32_t)__double2loint(x1), h1, 3);
+            uint32_t m0, m1;
+            asm("lop3.b32 %0, %1, 0x007FFFFF, %2, 0xEA;" : "=r"(m0) : "r"(t0), "r"(one_bits));
+            asm("lop3.b32 %0, %1, 0x007FFFFF, %2, 0xEA;" : "=r"(m1) : "r"(t1), "r"(one_bits));
+            float2 lg;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg.x) : "f"(__uint_as_float(m0)));
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg.y) : "f"(__uint_as_float(m1)));
+            const uint32_t e0 = h0 >> 20, e1 = h1 >> 20;
+            const float2 ef = make_float2(__uint2float_rn(e0), __uint2float_rn(e1));
+            const float2 a = __ffma2_rn(ef, make_float2(C2, C2), make_float2(KB, KB));
+            const float2 w = __ffma2_rn(lg, make_float2(C1, C1), a);
+            const float2 r = __fadd2_rn(w, make_float2(MAGIC, MAGIC));
+            const float2 sv = __fadd2_rn(r, make_float2(-MAGIC, -MAGIC));
+            const float2 d = __ffma2_rn(sv, make_float2(-1.0f, -1.0f), w);
+            // v's high word >= 0x43E00000 unsigned: |v| >= 2^63, Inf, NaN and every negative value
+            flag[i] = (fabsf(d.x) > 0.5f - LH_FAST_EPS) | ((uint32_t)__double2hiint(v0) >= 0x43E00000u) | (cur_id[i] >= H);
+            flag[i + 1] = (fabsf(d.y) > 0.5f - LH_FAST_EPS) | ((uint32_t)__double2hiint(v1) >= 0x43E00000u) | (cur_id[i + 1] >= H);
+            off[i] = e0 * 276u + (__float_as_uint(r.x) << 2) + COFF + cur_id[i] * (uint32_t)(LH_WIN * 4);
+            off[i + 1] = e1 * 276u + (__float_as_uint(r.y) << 2) + COFF + cur_id[i + 1] * (uint32_t)(LH_WIN * 4);
+            any |= flag[i] | flag[i + 1];
+        }
+        if (__any_sync(0xFFFFFFFFu, any)) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (!flag[i]) continue;
+                ValT rv;
+                memcpy(&rv, &cur[i], 8);
+                // uncertain-but-positive samples of a valid id could stay in shared memory; the L2 route is exact too
+                // and keeps this path trivial (it handles ~0.05 % of the samples)
+                keyed_one<ValT>(cur_id[i], rv, H, hot, buckets, dropped, pol);
+                off[i] = trash_off;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(ks_hist) + off[i]), 1u);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { cur[i] = nxt[i]; cur_id[i] = nxt_id[i]; }
+        g = gn;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < words; i += KS_THREADS) {
+        const uint32_t c = ks_hist[i];
+        if (!c) continue;
+        const uint32_t id = i / (uint32_t)LH_WIN, slot = i - id * (uint32_t)LH_WIN;
+        atomicAdd(&hot[(size_t)id * LH_SUBHIST + slot], c);
+    }
+}
+
 // ------------------------------------------------------------- K1k/partitioned
 // Gets the keyed path past the L2 atomic rate (one RED sector per sample).  One persistent cooperative CTA per
 // SM; CTA p OWNS the histogram ids {p, p+P, p+2P, ...} and keeps their positive windows (uint32[ids_per][4368])

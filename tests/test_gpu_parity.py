@@ -588,3 +588,39 @@ def test_merge_sparse_snapshots(lh, oracle):
         assert (red.counts == want.sum(axis=1)).all() and e.stats()["dropped"] == 1
         ref = oracle.process_histogram(want[3], PS)
         assert (red.pkeys[3] == ref["pkeys"]).all()
+
+
+@pytest.mark.parametrize("H", [1, 5, 11, 12])
+def test_keyed_small_h_privatized_kernel(lh, oracle, H):
+    """H <= 11 histograms: windows privatised in shared memory (k_ingest_keyed_small); H = 12 takes the L2 route.
+    Either way every bucket must match the oracle, for f64 and int64-ns samples, u16 and u32 ids, bad ids dropped."""
+    n = 1_200_003
+    vals = oracle.gen_stream(lh.STREAM_S, n, SEED ^ H)
+    ids = oracle.gen_ids(0, n, H, SEED ^ H)
+    ids_bad = ids.copy()
+    ids_bad[::997] = H + 3                       # out of range: dropped and counted
+    keep = ids_bad < H
+    with lh.Engine(device=0, max_histograms=H, max_counters=1) as e:
+        d_v, d_i16, d_i32 = e.upload(vals), e.upload(ids_bad.astype(np.uint16)), e.upload(ids_bad)
+        e.ingest_keyed_f64_u16(d_i16, d_v, n)
+        red, sp = e.snapshot(PS)
+        want = oracle.ingest_keyed(ids_bad[keep], vals[keep], H)
+        for h in range(H):
+            assert (dense_from_sparse(sp, h) == want[h]).all(), h
+        assert e.stats()["dropped"] == int((~keep).sum())
+        e.ingest_keyed_f64_u32(d_i32, d_v.offset(1), n - 1)          # misaligned values: scalar fallback path
+        red, sp = e.snapshot(PS)
+        keep1 = keep[:n - 1]
+        want1 = oracle.ingest_keyed(ids_bad[:n - 1][keep1], vals[1:][keep1], H)
+        for h in range(H):
+            assert (dense_from_sparse(sp, h) == want1[h]).all(), h
+        ns = oracle.gen_stream(oracle.STREAM_TIMER_NS, n, SEED ^ H).view(np.int64).copy()
+        ns[::3] *= -1
+        d_n = e.upload(ns)
+        e.ingest_keyed_i64ns_u16(d_i16, d_n, n)
+        red, sp = e.snapshot(PS)
+        want2 = oracle.ingest_keyed_i64(ids_bad[keep], ns[keep], H)
+        for h in range(H):
+            assert (dense_from_sparse(sp, h) == want2[h]).all(), h
+            ref = oracle.process_histogram(want2[h], PS)
+            assert (red.pkeys[h] == ref["pkeys"]).all()
