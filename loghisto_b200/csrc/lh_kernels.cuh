@@ -556,10 +556,12 @@ k_ingest_keyed_small(const IdT *__restrict__ ids, const ValT *__restrict__ vals,
     constexpr uint32_t COFF = 0u - (1023u * 69u * 4u) - (0x4B400000u << 2);
     const uint32_t trash_off = words * 4u;
 
+    // The loop bound is warp-uniform (base index of the CTA's row of groups); lanes past the end are predicated
+    // off, because the fix-up below votes with the full warp mask.
     const size_t stride = (size_t)gridDim.x * KS_THREADS;
-    size_t g = (size_t)blockIdx.x * KS_THREADS + threadIdx.x;
-    unsigned long long cur[4], nxt[4];
-    uint32_t cur_id[4], nxt_id[4];
+    size_t base = (size_t)blockIdx.x * KS_THREADS;
+    unsigned long long cur[4] = {0, 0, 0, 0}, nxt[4] = {0, 0, 0, 0};
+    uint32_t cur_id[4] = {0, 0, 0, 0}, nxt_id[4] = {0, 0, 0, 0};
     auto load = [&](unsigned long long(&raw)[4], uint32_t(&id4)[4], size_t gi) {
         asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
                      : "=l"(raw[0]), "=l"(raw[1]), "=l"(raw[2]), "=l"(raw[3]) : "l"(reinterpret_cast<const char *>(vals) + gi * 32));
@@ -573,9 +575,10 @@ k_ingest_keyed_small(const IdT *__restrict__ ids, const ValT *__restrict__ vals,
                          : "l"(reinterpret_cast<const char *>(ids) + gi * 16));
         }
     };
-    if (g < n4) load(cur, cur_id, g);
-    while (g < n4) {
-        const size_t gn = g + stride;
+    if (base + threadIdx.x < n4) load(cur, cur_id, base + threadIdx.x);
+    for (; base < n4; base += stride) {
+        const bool valid = base + threadIdx.x < n4;
+        const size_t gn = base + stride + threadIdx.x;
         if (gn < n4) load(nxt, nxt_id, gn);
         uint32_t off[4];
         bool flag[4];
@@ -603,10 +606,10 @@ k_ingest_keyed_small(const IdT *__restrict__ ids, const ValT *__restrict__ vals,
             const float2 sv = __fadd2_rn(r, make_float2(-MAGIC, -MAGIC));
             const float2 d = __ffma2_rn(sv, make_float2(-1.0f, -1.0f), w);
             // v's high word >= 0x43E00000 unsigned: |v| >= 2^63, Inf, NaN and every negative value
-            flag[i] = (fabsf(d.x) > 0.5f - LH_FAST_EPS) | ((uint32_t)__double2hiint(v0) >= 0x43E00000u) | (cur_id[i] >= H);
-            flag[i + 1] = (fabsf(d.y) > 0.5f - LH_FAST_EPS) | ((uint32_t)__double2hiint(v1) >= 0x43E00000u) | (cur_id[i + 1] >= H);
-            off[i] = e0 * 276u + (__float_as_uint(r.x) << 2) + COFF + cur_id[i] * (uint32_t)(LH_WIN * 4);
-            off[i + 1] = e1 * 276u + (__float_as_uint(r.y) << 2) + COFF + cur_id[i + 1] * (uint32_t)(LH_WIN * 4);
+            flag[i] = valid & ((fabsf(d.x) > 0.5f - LH_FAST_EPS) | ((uint32_t)__double2hiint(v0) >= 0x43E00000u) | (cur_id[i] >= H));
+            flag[i + 1] = valid & ((fabsf(d.y) > 0.5f - LH_FAST_EPS) | ((uint32_t)__double2hiint(v1) >= 0x43E00000u) | (cur_id[i + 1] >= H));
+            off[i] = valid ? e0 * 276u + (__float_as_uint(r.x) << 2) + COFF + cur_id[i] * (uint32_t)(LH_WIN * 4) : trash_off;
+            off[i + 1] = valid ? e1 * 276u + (__float_as_uint(r.y) << 2) + COFF + cur_id[i + 1] * (uint32_t)(LH_WIN * 4) : trash_off;
             any |= flag[i] | flag[i + 1];
         }
         if (__any_sync(0xFFFFFFFFu, any)) {
@@ -625,7 +628,6 @@ k_ingest_keyed_small(const IdT *__restrict__ ids, const ValT *__restrict__ vals,
         for (int i = 0; i < 4; i++) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(ks_hist) + off[i]), 1u);
 #pragma unroll
         for (int i = 0; i < 4; i++) { cur[i] = nxt[i]; cur_id[i] = nxt_id[i]; }
-        g = gn;
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < words; i += KS_THREADS) {
