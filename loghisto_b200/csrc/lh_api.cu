@@ -23,7 +23,7 @@ struct WriterEvent { cudaStream_t stream; cudaEvent_t ev; };
 struct Buffer {
     unsigned long long *d_buckets = nullptr;   // [H][65536]
     unsigned long long *d_counters = nullptr;  // [C]
-    unsigned int *d_hot = nullptr;             // [H][LH_SUBHIST] uint32 window of the keyed path
+    unsigned int *d_hot = nullptr;             // [hot_replicas][H][LH_SUBHIST] uint32 window of the keyed path
     unsigned long long hot_pending = 0;        // samples added to d_hot since it was last drained
     cudaEvent_t cleared = nullptr;             // zeroing finished
     std::vector<WriterEvent> writers;          // last ingest per stream
@@ -155,6 +155,7 @@ struct lh_ctx {
     int k1_grid_mult = 1;
     int k1_reserve_sms = 0;   // SMs left free for concurrent snapshot / collective kernels
     int keyed_blocks_per_sm = 8;
+    uint32_t hot_replicas = 1;          // copies of the hot window (all L2-resident); only the vector RED kernel spreads over them
     int keyed_mode = 0;                 // 0 auto, 1 force L2-atomic kernel, 2 force owner-partitioned kernel
     int kp_shape = 1;                   // owner-partitioned kernel: 0 = 1x1024 threads per SM, 1 = 2x512
     int64_t kp_chunk = 16 << 20;        // samples per chunk of the partitioned kernel
@@ -266,7 +267,7 @@ lh_status launch_single(lh_ctx *ctx, uint32_t hid, const double *d_values, size_
 lh_status fold_hot(lh_ctx *ctx, int b, cudaStream_t s) {
     const size_t cells = (size_t)ctx->H * LH_SUBHIST;
     int grid = (int)std::min<size_t>((cells + 255) / 256, (size_t)ctx->sm_count * 16);
-    k_fold_hot<<<grid, 256, 0, s>>>(ctx->buf[b].d_hot, ctx->buf[b].d_buckets, cells);
+    k_fold_hot<<<grid, 256, 0, s>>>(ctx->buf[b].d_hot, ctx->buf[b].d_buckets, cells, ctx->hot_replicas);
     LH_CUDA(ctx, cudaGetLastError());
     ctx->stats.kernel_launches++;
     ctx->buf[b].hot_pending = 0;
@@ -365,7 +366,7 @@ lh_status launch_keyed(lh_ctx *ctx, const IdT *d_ids, const ValT *d_vals, size_t
             if (!used) {
                 int grid = grid_1d(ctx, n4, T, 1, ctx->keyed_blocks_per_sm);
                 k_ingest_keyed_vec<IdT, ValT, T><<<grid, T, 0, s>>>(ids + head, vals + head, n4, ctx->H, ctx->buf[b].d_hot,
-                                                                    ctx->buf[b].d_buckets, ctx->d_dropped);
+                                                                    ctx->hot_replicas, ctx->buf[b].d_buckets, ctx->d_dropped);
                 ctx->stats.kernel_launches++;
             }
         }
@@ -467,6 +468,10 @@ extern "C" lh_status lh_create(const lh_config *cfg, lh_ctx **out) {
     ctx->device = cfg->device;
     ctx->H = cfg->max_histograms;
     ctx->C = cfg->max_counters;
+    {   // replicas of the keyed hot window: as many as keep all copies within ~48 MB (L2-resident), at most 32
+        const size_t one = (size_t)ctx->H * LH_SUBHIST * 4u;
+        ctx->hot_replicas = (uint32_t)std::max<size_t>(1, std::min<size_t>(32, ((size_t)48 << 20) / one));
+    }
     ctx->staging_bytes = cfg->staging_bytes ? (size_t)cfg->staging_bytes : ((size_t)32 << 20);
     ctx->staging_bytes = (ctx->staging_bytes + 255) & ~(size_t)255;
     const uint32_t nslots = cfg->staging_slots ? cfg->staging_slots : 3;
@@ -508,8 +513,8 @@ extern "C" lh_status lh_create(const lh_config *cfg, lh_ctx **out) {
         LH_CREATE_CUDA(cudaMalloc(&ctx->buf[b].d_counters, counter_bytes));
         LH_CREATE_CUDA(cudaMemsetAsync(ctx->buf[b].d_buckets, 0, bucket_bytes, ctx->snap_stream));
         LH_CREATE_CUDA(cudaMemsetAsync(ctx->buf[b].d_counters, 0, counter_bytes, ctx->snap_stream));
-        LH_CREATE_CUDA(cudaMalloc(&ctx->buf[b].d_hot, (size_t)ctx->H * LH_SUBHIST * 4u));
-        LH_CREATE_CUDA(cudaMemsetAsync(ctx->buf[b].d_hot, 0, (size_t)ctx->H * LH_SUBHIST * 4u, ctx->snap_stream));
+        LH_CREATE_CUDA(cudaMalloc(&ctx->buf[b].d_hot, (size_t)ctx->hot_replicas * ctx->H * LH_SUBHIST * 4u));
+        LH_CREATE_CUDA(cudaMemsetAsync(ctx->buf[b].d_hot, 0, (size_t)ctx->hot_replicas * ctx->H * LH_SUBHIST * 4u, ctx->snap_stream));
         LH_CREATE_CUDA(cudaEventCreateWithFlags(&ctx->buf[b].cleared, cudaEventDisableTiming));
         LH_CREATE_CUDA(cudaEventRecord(ctx->buf[b].cleared, ctx->snap_stream));
     }

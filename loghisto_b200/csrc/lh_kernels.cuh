@@ -487,11 +487,15 @@ __device__ __forceinline__ void keyed_one(uint32_t id, ValT raw, uint32_t H, uns
 
 // Vector body: every thread takes 4 consecutive pairs (one 256-bit value load, one 64/128-bit id load).
 // vals must be 32-byte aligned and ids 4*sizeof(IdT)-aligned; n4 = number of 4-sample groups.
+// `hot` holds `replicas` copies of the window ([replicas][H][LH_SUBHIST]); CTA b updates copy b % replicas, which
+// divides the same-address pressure on hot cells (clustered, latency-like data) by the replica count while every
+// copy stays L2-resident.  k_fold_hot sums the copies.
 template <typename IdT, typename ValT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_ingest_keyed_vec(const IdT *__restrict__ ids, const ValT *__restrict__ vals, size_t n4, uint32_t H,
-                   unsigned int *__restrict__ hot, unsigned long long *__restrict__ buckets,
+                   unsigned int *__restrict__ hot, uint32_t replicas, unsigned long long *__restrict__ buckets,
                    unsigned long long *__restrict__ dropped) {
+    hot += (size_t)(blockIdx.x % replicas) * H * LH_SUBHIST;
     const uint64_t pol = policy_evict_last();
     const size_t stride = (size_t)gridDim.x * THREADS;
     for (size_t g = (size_t)blockIdx.x * THREADS + threadIdx.x; g < n4; g += stride) {
@@ -869,15 +873,19 @@ k_ingest_keyed_part(KpParams prm) {
 
 // Drain the hot window into the uint64 buckets.  atomicExch/atomicAdd so that ingest on other
 // streams may keep running against the same buffer.
-__global__ void k_fold_hot(unsigned int *__restrict__ hot, unsigned long long *__restrict__ buckets, size_t cells) {
+__global__ void k_fold_hot(unsigned int *__restrict__ hot, unsigned long long *__restrict__ buckets, size_t cells,
+                           uint32_t replicas) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += stride) {
-        unsigned int v = hot[i];
-        if (v) {
-            v = atomicExch(&hot[i], 0u);
+        unsigned long long sum = 0;
+        for (uint32_t r = 0; r < replicas; r++) {
+            unsigned int *cell = hot + (size_t)r * cells + i;
+            if (*cell) sum += atomicExch(cell, 0u);
+        }
+        if (sum) {
             size_t h = i / LH_SUBHIST;
             uint32_t slot = (uint32_t)(i - h * LH_SUBHIST);
-            if (v) atomicAdd(&buckets[h * 65536u + slot_to_key16(slot)], (unsigned long long)v);
+            atomicAdd(&buckets[h * 65536u + slot_to_key16(slot)], sum);
         }
     }
 }
