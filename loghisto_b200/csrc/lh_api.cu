@@ -348,17 +348,24 @@ lh_status launch_keyed(lh_ctx *ctx, const IdT *d_ids, const ValT *d_vals, size_t
         }
         if (n4) {
             bool used = false;
-            if (ctx->H <= (uint32_t)KS_MAX_H && ctx->keyed_mode == 0 && n4 >= 4096) {
-                // few histograms: their windows fit in shared memory (K1-style privatisation)
-                const size_t smem = ((size_t)ctx->H * LH_WIN + 4) * 4;
+            // few histograms: their windows fit in shared memory (K1-style privatisation).  Up to KS_MAX_PASSES
+            // passes over id sub-ranges still beat the L2-atomic kernel (each pass is HBM-bound at 10 B/sample).
+            constexpr uint32_t KS_MAX_PASSES = 3;
+            const uint32_t passes = (ctx->H + KS_MAX_H - 1) / KS_MAX_H;
+            if (passes <= KS_MAX_PASSES && ctx->keyed_mode == 0 && n4 >= 4096) {
+                const uint32_t per = (ctx->H + passes - 1) / passes;
+                const size_t smem = ((size_t)per * LH_WIN + 4) * 4;
                 const void *fn = (const void *)k_ingest_keyed_small<IdT, ValT>;
                 LH_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 // one CTA per SM; fewer when the batch is small, so that the per-CTA flush stays negligible
                 int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)(ctx->sm_count - ctx->k1_reserve_sms),
                                                                       n4 / (KS_THREADS * 16)));
-                k_ingest_keyed_small<IdT, ValT><<<grid, KS_THREADS, smem, s>>>(ids + head, vals + head, n4, ctx->H, ctx->buf[b].d_hot,
-                                                                              ctx->buf[b].d_buckets, ctx->d_dropped);
-                ctx->stats.kernel_launches++;
+                for (uint32_t lo = 0; lo < ctx->H; lo += per) {
+                    const uint32_t cnt = std::min(per, ctx->H - lo);
+                    k_ingest_keyed_small<IdT, ValT><<<grid, KS_THREADS, smem, s>>>(ids + head, vals + head, n4, ctx->H, lo, cnt,
+                                                                                  ctx->buf[b].d_hot, ctx->buf[b].d_buckets, ctx->d_dropped);
+                    ctx->stats.kernel_launches++;
+                }
                 used = true;
             }
             if (!used) st = launch_keyed_part<IdT, ValT>(ctx, b, ids + head, vals + head, n4 * 4, s, &used);

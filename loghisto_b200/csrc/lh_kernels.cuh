@@ -545,10 +545,13 @@ constexpr int KS_THREADS = 1024;
 template <typename IdT, typename ValT>
 __global__ void __launch_bounds__(KS_THREADS, 1)
 k_ingest_keyed_small(const IdT *__restrict__ ids, const ValT *__restrict__ vals, size_t n4, uint32_t H,
-                     unsigned int *__restrict__ hot, unsigned long long *__restrict__ buckets,
-                     unsigned long long *__restrict__ dropped) {
-    extern __shared__ __align__(16) uint32_t ks_hist[];          // [H][LH_WIN] + trash word
-    const uint32_t words = H * (uint32_t)LH_WIN;
+                     uint32_t id_lo, uint32_t id_cnt, unsigned int *__restrict__ hot,
+                     unsigned long long *__restrict__ buckets, unsigned long long *__restrict__ dropped) {
+    // This launch owns ids [id_lo, id_lo + id_cnt) (id_cnt <= KS_MAX_H); with more histograms than fit, the host
+    // runs one pass per id sub-range over the same batch.  Samples of other valid ids are skipped; ids >= H are
+    // dropped (and counted) by the pass that starts at id 0.
+    extern __shared__ __align__(16) uint32_t ks_hist[];          // [id_cnt][LH_WIN] + trash word
+    const uint32_t words = id_cnt * (uint32_t)LH_WIN;
     for (uint32_t i = threadIdx.x; i <= words; i += KS_THREADS) ks_hist[i] = 0;
     __syncthreads();
     const uint64_t pol = policy_evict_last();
@@ -610,10 +613,13 @@ k_ingest_keyed_small(const IdT *__restrict__ ids, const ValT *__restrict__ vals,
             const float2 sv = __fadd2_rn(r, make_float2(-MAGIC, -MAGIC));
             const float2 d = __ffma2_rn(sv, make_float2(-1.0f, -1.0f), w);
             // v's high word >= 0x43E00000 unsigned: |v| >= 2^63, Inf, NaN and every negative value
-            flag[i] = valid & ((fabsf(d.x) > 0.5f - LH_FAST_EPS) | ((uint32_t)__double2hiint(v0) >= 0x43E00000u) | (cur_id[i] >= H));
-            flag[i + 1] = valid & ((fabsf(d.y) > 0.5f - LH_FAST_EPS) | ((uint32_t)__double2hiint(v1) >= 0x43E00000u) | (cur_id[i + 1] >= H));
-            off[i] = valid ? e0 * 276u + (__float_as_uint(r.x) << 2) + COFF + cur_id[i] * (uint32_t)(LH_WIN * 4) : trash_off;
-            off[i + 1] = valid ? e1 * 276u + (__float_as_uint(r.y) << 2) + COFF + cur_id[i + 1] * (uint32_t)(LH_WIN * 4) : trash_off;
+            const uint32_t l0 = cur_id[i] - id_lo, l1 = cur_id[i + 1] - id_lo;          // local ids (wrap when below id_lo)
+            const bool mine0 = valid & (l0 < id_cnt), mine1 = valid & (l1 < id_cnt);
+            const bool bad0 = valid & (cur_id[i] >= H) & (id_lo == 0), bad1 = valid & (cur_id[i + 1] >= H) & (id_lo == 0);
+            flag[i] = (mine0 & ((fabsf(d.x) > 0.5f - LH_FAST_EPS) | ((uint32_t)__double2hiint(v0) >= 0x43E00000u))) | bad0;
+            flag[i + 1] = (mine1 & ((fabsf(d.y) > 0.5f - LH_FAST_EPS) | ((uint32_t)__double2hiint(v1) >= 0x43E00000u))) | bad1;
+            off[i] = mine0 ? e0 * 276u + (__float_as_uint(r.x) << 2) + COFF + l0 * (uint32_t)(LH_WIN * 4) : trash_off;
+            off[i + 1] = mine1 ? e1 * 276u + (__float_as_uint(r.y) << 2) + COFF + l1 * (uint32_t)(LH_WIN * 4) : trash_off;
             any |= flag[i] | flag[i + 1];
         }
         if (__any_sync(0xFFFFFFFFu, any)) {
@@ -637,8 +643,8 @@ k_ingest_keyed_small(const IdT *__restrict__ ids, const ValT *__restrict__ vals,
     for (uint32_t i = threadIdx.x; i < words; i += KS_THREADS) {
         const uint32_t c = ks_hist[i];
         if (!c) continue;
-        const uint32_t id = i / (uint32_t)LH_WIN, slot = i - id * (uint32_t)LH_WIN;
-        atomicAdd(&hot[(size_t)id * LH_SUBHIST + slot], c);
+        const uint32_t lid = i / (uint32_t)LH_WIN, slot = i - lid * (uint32_t)LH_WIN;
+        atomicAdd(&hot[(size_t)(id_lo + lid) * LH_SUBHIST + slot], c);
     }
 }
 

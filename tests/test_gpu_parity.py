@@ -590,9 +590,10 @@ def test_merge_sparse_snapshots(lh, oracle):
         assert (red.pkeys[3] == ref["pkeys"]).all()
 
 
-@pytest.mark.parametrize("H", [1, 5, 11, 12])
+@pytest.mark.parametrize("H", [1, 5, 11, 12, 23, 33, 34])
 def test_keyed_small_h_privatized_kernel(lh, oracle, H):
-    """H <= 11 histograms: windows privatised in shared memory (k_ingest_keyed_small); H = 12 takes the L2 route.
+    """H <= 11 histograms: windows privatised in shared memory (k_ingest_keyed_small); up to 33 in two or three
+    passes over id sub-ranges; H = 34 takes the L2 route.
     Either way every bucket must match the oracle, for f64 and int64-ns samples, u16 and u32 ids, bad ids dropped."""
     n = 1_200_003
     vals = oracle.gen_stream(lh.STREAM_S, n, SEED ^ H)
