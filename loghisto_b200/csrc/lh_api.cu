@@ -349,8 +349,9 @@ lh_status launch_keyed(lh_ctx *ctx, const IdT *d_ids, const ValT *d_vals, size_t
         if (n4) {
             bool used = false;
             // few histograms: their windows fit in shared memory (K1-style privatisation).  Up to KS_MAX_PASSES
-            // passes over id sub-ranges still beat the L2-atomic kernel (each pass is HBM-bound at 10 B/sample).
-            constexpr uint32_t KS_MAX_PASSES = 3;
+            // passes over id sub-ranges match or beat the L2-atomic kernel (each pass is HBM-bound at 10 B/sample) and,
+            // unlike it, do not depend on how clustered the values are.
+            constexpr uint32_t KS_MAX_PASSES = 4;
             const uint32_t passes = (ctx->H + KS_MAX_H - 1) / KS_MAX_H;
             if (passes <= KS_MAX_PASSES && ctx->keyed_mode == 0 && n4 >= 4096) {
                 const uint32_t per = (ctx->H + passes - 1) / passes;
