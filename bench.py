@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--k1-grid-mult", type=int, default=0, help="override the K1 waves-per-launch tuning")
     ap.add_argument("--k1-variant", type=int, default=-1)
+    ap.add_argument("--pipeline-depth", type=int, default=-1,
+                    help="snapshots in flight behind the next ingest: 0 = blocking snapshot after every batch, 1, 2 (default: 2 up to 4 GPUs, 0 beyond)")
+    ap.add_argument("--nccl-defaults", action="store_true", help="do not set NCCL_MAX_NCHANNELS / NCCL_CGA_CLUSTER_SIZE")
     ap.add_argument("--reserve-sms", type=int, default=-1, help="SMs K1 leaves free for the snapshot stream (default: 0 at N=1, 2 at N>1)")
     return ap.parse_args()
 
@@ -271,8 +274,9 @@ def run_b200(a):
     dist = None
     if world > 1:
         os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")   # the bucket all-reduce outranks the ingest kernel
-        os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")          # 512 KiB payload: latency-bound, keep its CTAs few
-        os.environ.setdefault("NCCL_CGA_CLUSTER_SIZE", "0")       # no CTA clusters: its CTAs must fit the reserved SMs
+        if not a.nccl_defaults:
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")      # 512 KiB payload: latency-bound, keep its CTAs few
+            os.environ.setdefault("NCCL_CGA_CLUSTER_SIZE", "0")   # no CTA clusters: its CTAs must fit the reserved SMs
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -288,7 +292,8 @@ def run_b200(a):
         eng.tune("k1_grid_mult", a.k1_grid_mult)
     if a.k1_variant >= 0:
         eng.tune("k1", a.k1_variant)
-    reserve = a.reserve_sms if a.reserve_sms >= 0 else (2 if world > 1 else 1)
+    depth = a.pipeline_depth if a.pipeline_depth >= 0 else (2 if world <= 4 else 0)
+    reserve = a.reserve_sms if a.reserve_sms >= 0 else (0 if depth == 0 else 2 if world > 1 else 1)
     if reserve:
         eng.tune("k1_reserve_sms", reserve)
     # launch on the context's own non-blocking ingest stream (torch's legacy default stream serialises against
@@ -338,6 +343,17 @@ def run_b200(a):
         inside the call."""
         red = None
         pending = []          # (handle, ingest seq) of snapshots whose results are still on their way
+        if depth == 0:
+            # blocking form: ingest, then the whole snapshot, then the next ingest (nothing overlaps)
+            for i in range(k):
+                ingest(host_src)
+                seq = eng.ingest_seq()
+                red, _ = sharded.snapshot(PERCENTILES)
+                if record and host_src is None:
+                    kernel_ms.append(sum(eng.kernel_ms(seq - j) for j in range(3 if mixed else 1)))
+                    if world > 1:
+                        allreduce_ms.append(sharded.last_allreduce_ms())
+            return red
         ingest(host_src)
 
         def collect(entry):
@@ -354,7 +370,7 @@ def run_b200(a):
             seq = eng.ingest_seq()
             nxt = (lambda: ingest(host_src)) if i + 1 < k else None     # batch i+1 goes out right after the swap
             pending.append((sharded.snapshot_async(PERCENTILES, after_swap=nxt), seq))
-            if len(pending) > 1:
+            if len(pending) >= depth:
                 red = collect(pending.pop(0))
         while pending:
             red = collect(pending.pop(0))
@@ -437,6 +453,7 @@ def run_b200(a):
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(a, n, world),
             "gpu_launches": launches, "count_ok": count_ok, "clocks": clk,
+            "pipeline": {"snapshots_in_flight": depth, "sms_left_free_by_ingest": reserve},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": n * bytes_per_sample,
                          "peak_source": peak_src,
