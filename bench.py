@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--k1-grid-mult", type=int, default=0, help="override the K1 waves-per-launch tuning")
     ap.add_argument("--k1-variant", type=int, default=-1)
     ap.add_argument("--pipeline-depth", type=int, default=-1,
-                    help="snapshots in flight behind the next ingest: 0 = blocking snapshot after every batch, 1, 2 (default: 2 up to 4 GPUs, 0 beyond)")
+                    help="snapshots in flight behind the next ingest: 0 = blocking snapshot after every batch, 1, 2 (default 2)")
     ap.add_argument("--nccl-defaults", action="store_true", help="do not set NCCL_MAX_NCHANNELS / NCCL_CGA_CLUSTER_SIZE")
     ap.add_argument("--reserve-sms", type=int, default=-1, help="SMs K1 leaves free for the snapshot stream (default: 0 at N=1, 2 at N>1)")
     return ap.parse_args()
@@ -274,9 +274,12 @@ def run_b200(a):
     dist = None
     if world > 1:
         os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")   # the bucket all-reduce outranks the ingest kernel
-        if not a.nccl_defaults:
-            os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")      # 512 KiB payload: latency-bound, keep its CTAs few
-            os.environ.setdefault("NCCL_CGA_CLUSTER_SIZE", "0")   # no CTA clusters: its CTAs must fit the reserved SMs
+        # Measured (profiles/r01/scaling_r01.txt): up to 4 ranks the 512 KiB all-reduce is fastest with few channels
+        # and no CTA clusters (its CTAs then fit the 2 SMs the ingest kernel leaves free); with 8 ranks those limits
+        # turn pathological (3.37 ms/step) and NCCL's own choices plus 8 free SMs are best (1.58 ms/step).
+        if not a.nccl_defaults and world <= 4:
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
+            os.environ.setdefault("NCCL_CGA_CLUSTER_SIZE", "0")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -292,8 +295,8 @@ def run_b200(a):
         eng.tune("k1_grid_mult", a.k1_grid_mult)
     if a.k1_variant >= 0:
         eng.tune("k1", a.k1_variant)
-    depth = a.pipeline_depth if a.pipeline_depth >= 0 else (2 if world <= 4 else 0)
-    reserve = a.reserve_sms if a.reserve_sms >= 0 else (0 if depth == 0 else 2 if world > 1 else 1)
+    depth = a.pipeline_depth if a.pipeline_depth >= 0 else 2
+    reserve = a.reserve_sms if a.reserve_sms >= 0 else (0 if depth == 0 else 1 if world == 1 else 2 if world <= 4 else 8)
     if reserve:
         eng.tune("k1_reserve_sms", reserve)
     # launch on the context's own non-blocking ingest stream (torch's legacy default stream serialises against
