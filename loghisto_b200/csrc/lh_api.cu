@@ -235,8 +235,10 @@ lh_status launch_single(lh_ctx *ctx, uint32_t hid, const double *d_values, size_
     if (st != LH_OK) return st;
     unsigned long long *counts = ctx->buf[b].d_buckets + (size_t)hid * 65536u;
     const K1Variant &kv = ctx->k1[ctx->k1_variant];
-    // a CTA's uint32 sub-histogram must not overflow: bound samples per launch
-    const size_t kMaxPerLaunch = (size_t)1 << 36;
+    // a CTA's uint32 sub-histogram must not overflow: tiles are dealt round-robin, so bounding a launch to
+    // 2^31 samples per CTA keeps every cell below 2^32 whatever the grid size (reserved SMs shrink it)
+    const int grid = std::max(1, ctx->sm_count - ctx->k1_reserve_sms) * kv.blocks_per_sm * ctx->k1_grid_mult;
+    const size_t kMaxPerLaunch = std::min((size_t)1 << 36, (size_t)grid << 31);
     size_t done = 0;
     next_timing_slot(ctx);
     LH_CUDA(ctx, cudaEventRecord(ctx->ev_t0, s));
@@ -252,7 +254,6 @@ lh_status launch_single(lh_ctx *ctx, uint32_t hid, const double *d_values, size_
         const double *tail = body + nvec * 4;
         int ntail = (int)(m - nhead - nvec * 4);
         size_t consumed = m;
-        int grid = std::max(1, ctx->sm_count - ctx->k1_reserve_sms) * kv.blocks_per_sm * ctx->k1_grid_mult;
         kv.launch(grid, kv.smem, s, body, nvec, head, nhead, tail, ntail, counts);
         LH_CUDA(ctx, cudaGetLastError());
         ctx->stats.kernel_launches++;
