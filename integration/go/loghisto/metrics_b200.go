@@ -19,6 +19,7 @@ import "C"
 
 import (
 	"fmt"
+	"math"
 	"runtime"
 	"sync"
 	"sync/atomic"
@@ -121,7 +122,26 @@ func (ms *MetricSystem) Histogram(name string, value float64) {
 	s.mu.Unlock()
 }
 
-// Counter (metrics.go:251) batches the same way into lh_staging_commit_counter_u16; elided for brevity.
+// Counter keeps metrics.go:251's signature; amounts ride in a second staging slot per shard and are committed with
+// lh_staging_commit_counter_u16 (uint64 amounts at offset 0, uint16 ids at idsOff), exactly like Histogram.
+func (ms *MetricSystem) Counter(name string, amount uint64) {
+	e := ms.b200
+	id := e.counterID(name) // same interning idiom as histoID, over counterIDs / counterNames
+	s := e.counterShards[atomic.AddUint32(&shardPick, 1)%uint32(len(e.counterShards))]
+	s.mu.Lock()
+	if s.amounts == nil {
+		e.acquireCounter(s)
+	}
+	s.amounts[s.n], s.ids[s.n] = amount, id
+	s.n++
+	if s.n == s.cap {
+		C.lh_staging_commit_counter_u16(e.ctx, &s.slot, C.size_t(s.n), C.uint64_t(s.idsOff))
+		s.amounts, s.ids, s.n = nil, nil, 0
+	}
+	s.mu.Unlock()
+}
+
+// StartTimer / TimerToken.Stop (metrics.go:232-246) are unchanged Go: Stop() calls Histogram(name, float64(ns)).
 
 // collectRawMetrics keeps metrics.go:420's contract: interval-delta histograms (absent when untouched),
 // Rates = interval deltas, Counters = cumulative store.
@@ -157,7 +177,29 @@ func (ms *MetricSystem) collectRawMetrics() *RawMetricSet {
 	return &RawMetricSet{Histograms: histograms /* Time, Counters, Rates, Gauges as before */}
 }
 
-// processHistograms (metrics.go:336) becomes a lookup into the arrays lh_snapshot_reduce filled:
+// processHistograms keeps metrics.go:336's signature and output keys; the numbers come from lh_snapshot_reduce,
+// which collectRawMetrics called once for the whole snapshot (results cached per histogram id in ms.b200.reduced).
+func (ms *MetricSystem) processHistograms(name string, valuesToCounts map[int16]*uint64) map[string]float64 {
+	e := ms.b200
+	r := e.reduced[name] // {count uint64; sum, avg float64; pkeys []int32; pvals []float64}
+	output := map[string]float64{
+		fmt.Sprintf("%s_count", name): float64(r.count),
+		fmt.Sprintf("%s_sum", name):   r.sum,
+		fmt.Sprintf("%s_avg", name):   r.avg,
+	}
+	// aggregate store: unchanged Go (metrics.go:359-376), including uint64(totalSum)
+	ms.addToHistogramCountStore(name, uint64(r.sum), r.count)
+	i := 0
+	for label := range ms.percentiles { // e.percentileOrder fixes the label -> column mapping used at reduce time
+		if r.pkeys[i] != math.MinInt32 { // percentile() error (p > 1, NaN): logged and omitted, metrics.go:380-382
+			output[fmt.Sprintf(label, name)] = r.pvals[i]
+		}
+		i++
+	}
+	return output
+}
+
+// In words: processHistograms (metrics.go:336) becomes a lookup into the arrays lh_snapshot_reduce filled:
 // <name>_count, _sum, _avg and one entry per percentile label whose pkeys[] is not INT32_MIN
 // (percentile()'s error case: key omitted, metrics.go:380-382).  The cumulative store update
 // (uint64(totalSum), metrics.go:374) and the reaper's integer _agg_avg (metrics.go:601-606) stay in Go.

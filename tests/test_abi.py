@@ -73,3 +73,18 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"liblh_oracle|from oracle|import oracle|oracle[./]", text), \
                     f"{f} reaches into oracle/"
+
+
+def test_plain_c_client(tmp_path):
+    """The header compiles as C11 and the library links from a C program (no C++ runtime needed by the caller)."""
+    import subprocess
+    from loghisto_b200 import build
+    build.build()
+    exe = str(tmp_path / "c_abi_client")
+    libdir = os.path.dirname(build.LIB)
+    cmd = ["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c_abi_client.c"), "-o", exe, "-L", libdir, "-lloghisto_b200", "-Wl,-rpath," + libdir]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout + run.stderr
