@@ -1,18 +1,22 @@
 // lh_kernels.cuh -- sm_100a kernels of the loghisto hot path.
 //
-//   K1   ingest_single_*   one histogram, float64 stream -> bucket counts
-//                          (compress + Histogram increment, metrics.go:273-295, 316-322)
-//          _ldg   : vectorised ld.global.nc.v2.f64, software-pipelined registers
-//          _bulk  : cp.async.bulk (TMA 1-D, UBLKCP) into a shared-memory ring
-//                   guarded by mbarriers, one producer warp + N consumer warps
-//        both privatise the histogram in shared memory (uint32 sub-histograms,
-//        shared atomics) and flush once per CTA with one global 64-bit atomic
-//        per non-empty bucket.
-//   K1k  ingest_keyed      (id,value) pairs -> buckets[id][key]   (name dispatch path)
-//   K2   counter_add       (id,amount) pairs -> counters[id]      (metrics.go:251-269)
-//   K3   reduce            per histogram: count, sum, avg, percentiles
-//                          (processHistograms + percentile, metrics.go:336-418)
-//   K4   export            sparse (key,count) lists               (RawMetricSet.Histograms)
+//   K1   k_ingest_single_*  one histogram, float64 stream -> bucket counts
+//                           (compress + Histogram increment, metrics.go:273-295, 316-322)
+//          _bulk  : cp.async.bulk (TMA 1-D, UBLKCP) into a shared-memory ring guarded by mbarriers, one producer
+//                   warp + N consumer warps; with V2 = packed-FP32 bucket arithmetic this is the shipped default
+//          _ldg   : 256-bit ld.global.nc loads, software-pipelined in registers (first version)
+//          _v2/_v3: register-only variants of the lean arithmetic (kept for the comparison in profiles/)
+//        all privatise the histogram in shared memory (uint32 sub-histograms, ATOMS.POPC.INC) and flush once per
+//        CTA with one global 64-bit atomic per non-empty bucket.
+//   K1k  k_ingest_keyed_small   (id,value) pairs, <= 11 ids per pass privatised in shared memory (HBM-bound)
+//        k_ingest_keyed_vec     any number of ids: one L2 RED per sample into a compact, replicated uint32 window
+//        k_ingest_keyed_part    owner-partitioned cooperative kernel (opt-in experiment)
+//        k_ingest_keyed         scalar fallback for ragged / misaligned pieces;  k_fold_hot drains the window
+//   K2   k_counter_add{_smem}   (id,amount) pairs -> counters[id]        (metrics.go:251-269)
+//   K3   k_reduce               per histogram: count, sum, avg, percentiles (processHistograms + percentile,
+//                               metrics.go:336-418)
+//   K4   k_scan_nnz, k_export   sparse (key,count) lists (RawMetricSet.Histograms);  k_merge_sparse is the inverse
+//   misc k_fill_decompress, k_compress_probe, k_fastpath_margin, k_stream_probe, k_gen_stream, k_gen_ids_u16
 #pragma once
 #include "lh_device.cuh"
 
