@@ -208,6 +208,9 @@ LH_API lh_status lh_decompress_table(lh_ctx *ctx, double *h_out65536);
  * units, restricted to samples the fast path accepts; margin evidence for EPS */
 LH_API lh_status lh_fastpath_margin(lh_ctx *ctx, const double *d_values, size_t n, double *h_max_err,
                              uint64_t *h_n_slow, void *stream);
+/* the same per estimator (1: fast_candidate, 2: the packed-FP32 form of the single-histogram kernels), for the
+ * inputs of the last lh_fastpath_margin call */
+LH_API lh_status lh_fastpath_margin_detail(lh_ctx *ctx, double *h_err_estimator1, double *h_err_estimator2);
 
 /* ---- synthetic streams (bench / tests) ------------- */
 /* kind: 0=U log-uniform, 1=L latency-like, 2=S signed/edge mix, 3=C constant, 4=Z heavy hitter */

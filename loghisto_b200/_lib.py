@@ -93,6 +93,7 @@ SIGNATURES = {
     "lh_compress_f64": (_i32, [_vp, _vp, _sz, _vp, C.c_int, _vp]),
     "lh_decompress_table": (_i32, [_vp, _vp]),
     "lh_fastpath_margin": (_i32, [_vp, _vp, _sz, C.POINTER(C.c_double), C.POINTER(_u64), _vp]),
+    "lh_fastpath_margin_detail": (_i32, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "lh_gen_stream_f64": (_i32, [_vp, C.c_int, _u64, _u64, _sz, _vp, _vp]),
     "lh_gen_ids_u16": (_i32, [_vp, C.c_int, _u64, _u64, _sz, _u32, _vp, _vp]),
     "lh_get_stats": (_i32, [_vp, C.POINTER(lh_stats)]),

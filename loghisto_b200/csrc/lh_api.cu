@@ -151,6 +151,7 @@ struct lh_ctx {
     uint64_t slot_seq = 0;
     size_t staging_bytes = 0;
     // tuning
+    unsigned long long last_margin[2] = {0, 0};
     int k1_variant = kDefaultK1Variant;
     int k1_grid_mult = 1;
     int k1_reserve_sms = 0;   // SMs left free for concurrent snapshot / collective kernels
@@ -1033,16 +1034,27 @@ extern "C" lh_status lh_fastpath_margin(lh_ctx *ctx, const double *d_values, siz
     if (n && !d_values) return fail(ctx, LH_ERR_INVALID, "NULL input");
     cudaStream_t s = pick_stream(ctx, stream);
     unsigned long long *d = nullptr;
-    LH_CUDA(ctx, cudaMalloc(&d, 16));
-    LH_CUDA(ctx, cudaMemsetAsync(d, 0, 16, s));
-    if (n) k_fastpath_margin<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_values, n, d, d + 1);
-    unsigned long long h[2];
-    cudaError_t e = cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, s);
+    LH_CUDA(ctx, cudaMalloc(&d, 24));
+    LH_CUDA(ctx, cudaMemsetAsync(d, 0, 24, s));
+    if (n) k_fastpath_margin<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_values, n, d);
+    unsigned long long h[3];
+    cudaError_t e = cudaMemcpyAsync(h, d, 24, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     cudaFree(d);
     if (e != cudaSuccess) return fail(ctx, LH_ERR_CUDA, "lh_fastpath_margin", e);
-    if (h_max_err) memcpy(h_max_err, &h[0], 8);
+    // the larger of the two estimators' errors (positive doubles order like their bit patterns)
+    const unsigned long long worst = std::max(h[0], h[2]);
+    if (h_max_err) memcpy(h_max_err, &worst, 8);
     if (h_n_slow) *h_n_slow = h[1];
+    ctx->last_margin[0] = h[0]; ctx->last_margin[1] = h[2];
+    return LH_OK;
+}
+
+// the two estimators' errors of the last lh_fastpath_margin call, separately (bucket units)
+extern "C" lh_status lh_fastpath_margin_detail(lh_ctx *ctx, double *h_err_estimator1, double *h_err_estimator2) {
+    LH_ENTER(ctx);
+    if (h_err_estimator1) memcpy(h_err_estimator1, &ctx->last_margin[0], 8);
+    if (h_err_estimator2) memcpy(h_err_estimator2, &ctx->last_margin[1], 8);
     return LH_OK;
 }
 

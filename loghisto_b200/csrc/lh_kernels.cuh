@@ -1138,27 +1138,38 @@ __global__ void k_compress_probe(const double *__restrict__ v, size_t n, short *
     if (i < n) out[i] = (short)(mode == 1 ? exact_key16(v[i]) : key16_of(v[i]));
 }
 
-// max | (69 e + w) - 100 ln(x) | over samples inside the fast window, plus the slow-flag tally
-__global__ void k_fastpath_margin(const double *__restrict__ v, size_t n, unsigned long long *__restrict__ max_err_bits,
-                                  unsigned long long *__restrict__ n_slow) {
+// max | estimate - 100 ln(x) | over samples inside the fast window, for both estimators that ship:
+//   [0] fast_candidate()      (k_ingest_keyed*, probes, ragged tails)
+//   [2] bucket_samples_v2()   (packed-FP32 form with the -1023*c2 constant folded into the FMA; K1, keyed_small)
+// plus [1] the tally of samples fast_candidate() sends to the exact path.
+__global__ void k_fastpath_margin(const double *__restrict__ v, size_t n, unsigned long long *__restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double x = __dadd_rn(1.0, fabs(v[i]));
     uint32_t hi = (uint32_t)__double2hiint(x), lo = (uint32_t)__double2loint(x);
     uint32_t idx; bool slow;
     fast_candidate(v[i], idx, slow);
-    if (slow) atomicAdd(n_slow, 1ull);
+    if (slow) atomicAdd(&out[1], 1ull);
     if (hi >= 0x43E00000u) return;
     uint32_t t = __funnelshift_l(lo, hi, 3);
     float m = __uint_as_float((t & 0x007FFFFFu) | 0x3F800000u);
     float lg;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(m));
     uint32_t eb = hi >> 20;
-    float ef = __fadd_rn(__uint_as_float(0x4B000000u | eb), -(8388608.0f + 1023.0f));
-    float w = __fmaf_rn(lg, 69.31471805599453f, __fmul_rn(ef, 0.31471805599453f));
-    double est = (double)(int)(eb - 1023u) * 69.0 + (double)w;
-    double err = fabs(est - 100.0 * log(x));
-    atomicMax(max_err_bits, (unsigned long long)__double_as_longlong(err));
+    const double truth = 100.0 * log(x);
+    const double base = (double)(int)(eb - 1023u) * 69.0;
+    {   // estimator 1
+        float ef = __fadd_rn(__uint_as_float(0x4B000000u | eb), -(8388608.0f + 1023.0f));
+        float w = __fmaf_rn(lg, 69.31471805599453f, __fmul_rn(ef, 0.31471805599453f));
+        atomicMax(&out[0], (unsigned long long)__double_as_longlong(fabs(base + (double)w - truth)));
+    }
+    {   // estimator 2 (same constants as bucket_samples_v2 / k_ingest_keyed_small)
+        constexpr float C1 = 69.31471805599453f, C2 = 0.31471805599453f;
+        constexpr float KB = (float)(-1023.0 * (double)C2);
+        float a = __fmaf_rn(__uint2float_rn(eb), C2, KB);
+        float w = __fmaf_rn(lg, C1, a);
+        atomicMax(&out[2], (unsigned long long)__double_as_longlong(fabs(base + (double)w - truth)));
+    }
 }
 
 // ---------------------------------------------------------- synthetic streams

@@ -379,6 +379,11 @@ class Engine:
         self._check(self.lib.lh_fastpath_margin(self.h, _ptr(d_values), n, C.byref(err), C.byref(slow), 0))
         return float(err.value), int(slow.value)
 
+    def fastpath_margin_detail(self):
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.lh_fastpath_margin_detail(self.h, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
+
     def gen_stream(self, kind: int, n: int, seed: int, start: int = 0, out: DeviceArray | None = None,
                    stream=None) -> DeviceArray:
         if out is None:

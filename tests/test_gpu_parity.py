@@ -115,7 +115,11 @@ def test_fast_path_margin(eng, lh):
     for kind in (lh.STREAM_U, lh.STREAM_L, lh.STREAM_S):
         d = eng.gen_stream(kind, n, SEED ^ 0x55)
         err, slow = eng.fastpath_margin(d, n)
+        e1, e2 = eng.fastpath_margin_detail()          # fast_candidate / packed-FP32 estimator of K1
         d.free()
+        print("fast-path estimate error, stream %d: estimator1 %.3e estimator2 %.3e bucket units (EPS = %.3e)"
+              % (kind, e1, e2, 2.0 ** -12))
+        assert err == max(e1, e2)
         assert err < 2.0 ** -13, (kind, err)          # < EPS/2
         if kind != lh.STREAM_S:
             assert slow < n * 2.5 * 2.0 ** -12, (kind, slow)   # about 2*EPS of the samples fall back
@@ -625,3 +629,39 @@ def test_keyed_small_h_privatized_kernel(lh, oracle, H):
             assert (dense_from_sparse(sp, h) == want2[h]).all(), h
             ref = oracle.process_histogram(want2[h], PS)
             assert (red.pkeys[h] == ref["pkeys"]).all()
+
+
+def test_ingest_at_the_edge_of_the_epsilon_band(eng, lh, oracle):
+    """Inputs placed just inside and just outside the +-2^-12 band around every bucket boundary of the window: the
+    place where an estimator error (rather than a boundary) would flip a bucket without raising the flag.  Both
+    shipped estimators are exercised: K1 default (packed FP32) and the keyed kernels (fast_candidate)."""
+    T = thresholds(oracle, 4367).view(np.float64)                     # boundaries of buckets 1..4367
+    T = T[T > 0.02]
+    # 100*ln(1+v) moves by d when v moves by (1+v)*d/100: offsets of 0.6, 0.9, 1.1, 1.5 and 3 EPS on both sides
+    eps = 2.0 ** -12
+    vals = []
+    for mult in (0.6, 0.9, 1.1, 1.5, 3.0):
+        dv = (1.0 + T) * (mult * eps) / 100.0
+        vals += [T + dv, T - dv, -(T + dv), -(T - dv)]
+    vals = np.concatenate(vals)
+    vals = np.tile(vals, 8)[:1_000_000]
+    want = oracle.ingest(vals)
+    d = eng.upload(vals)
+    default = eng.lib.lh_k1_variant_current(eng.h)
+    for vi in (default, 0, 13, 21):
+        eng.tune("k1", vi)
+        eng.ingest_f64(0, d, vals.size)
+        _, sp = eng.snapshot(PS)
+        assert (dense_from_sparse(sp, 0) == want).all(), vi
+    eng.tune("k1", default)
+    ids = np.zeros(vals.size, dtype=np.uint16)
+    d_i = eng.upload(ids)
+    eng.ingest_keyed_f64_u16(d_i, d, vals.size)                       # H = 4: k_ingest_keyed_small (packed FP32)
+    _, sp = eng.snapshot(PS)
+    assert (dense_from_sparse(sp, 0) == want).all()
+    eng.tune("keyed_mode", 1)                                         # k_ingest_keyed_vec (fast_candidate)
+    eng.ingest_keyed_f64_u16(d_i, d, vals.size)
+    _, sp = eng.snapshot(PS)
+    assert (dense_from_sparse(sp, 0) == want).all()
+    eng.tune("keyed_mode", 0)
+    d.free(); d_i.free()
