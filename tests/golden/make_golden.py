@@ -11,7 +11,6 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-import numpy as np
 from oracle import oracle as o
 
 N = 1_000_000

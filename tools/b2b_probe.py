@@ -1,7 +1,6 @@
 """Is K1 slower back-to-back?  Launch K1 R times without host syncs, with/without concurrent snapshots."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import loghisto_b200 as lh
 
 n = 1_000_000_000

@@ -1,7 +1,6 @@
 """Which ingredient of bench.py slows K1 from 1.145 to 1.23 ms?"""
 import os, sys, time, threading
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import loghisto_b200 as lh
 
 n = 1_000_000_000

@@ -1,7 +1,6 @@
 """Runs the owner-partitioned keyed kernel a few times (for ncu)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import loghisto_b200 as lh
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
 shape = int(sys.argv[2]) if len(sys.argv) > 2 else 0

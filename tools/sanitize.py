@@ -1,7 +1,6 @@
 """Small end-to-end pass over every kernel, meant to run under compute-sanitizer (racecheck / memcheck / synccheck)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import loghisto_b200 as lh
 
 PS = [0.0, 0.5, 0.99, 1.0]
