@@ -19,7 +19,12 @@ def _load():
         return _lib
     if _build.needs_build() or _build.needs_build_host():
         _build.build_host()
-    L = C.CDLL(_build.HOST_LIB)
+    _lib = _bind(C.CDLL(_build.HOST_LIB))
+    return _lib
+
+
+def _bind(L):
+    """Declare the lhms_* signatures on a loaded host library."""
     vp = C.c_void_p
     L.lhms_new.restype = vp
     L.lhms_new.argtypes = [C.c_int64, C.c_int, C.c_uint32, C.c_uint32, C.c_char_p, C.c_int]
@@ -46,7 +51,6 @@ def _load():
         getattr(L, "lhms_recv_" + kind).restype = C.c_int
         getattr(L, "lhms_recv_" + kind).argtypes = [vp, C.c_int64, _EMIT, vp]
         getattr(L, "lhms_free_%s_channel" % kind).argtypes = [vp]
-    _lib = L
     return L
 
 

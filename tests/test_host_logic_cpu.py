@@ -1,0 +1,92 @@
+"""Host logic on CPU: the C++ MetricSystem mirror (loghisto_b200/host/metric_system.cc) compiled against a TEST-ONLY
+stub of the C ABI that is backed by the oracle (tests/stub_abi/lh_stub.c), then driven through the same replays of the
+reference's metrics_test.go that the GPU suite runs.  What this covers without a GPU: name interning, staging batches
+and flushes, RawMetricSet / ProcessedMetricSet reconstruction, counter store and rates, percentile labels, the reaper,
+channel back-pressure.  The product never loads the stub (it has no CPU fallback)."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "tests", "_build")
+
+
+@pytest.fixture(scope="module")
+def stub_host_lib():
+    os.makedirs(BUILD, exist_ok=True)
+    stub = os.path.join(BUILD, "liblh_stub.so")
+    host = os.path.join(BUILD, "libloghisto_host_stub.so")
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=gnu11", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-I", inc,
+                    os.path.join(ROOT, "tests", "stub_abi", "lh_stub.c"), os.path.join(ROOT, "oracle", "loghisto_oracle.c"),
+                    "-o", stub, "-lm", "-lpthread"], check=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I", inc,
+                    os.path.join(ROOT, "loghisto_b200", "host", "metric_system.cc"), "-o", host,
+                    "-L", BUILD, "-llh_stub", "-Wl,-rpath," + BUILD, "-lpthread"], check=True)
+    return host
+
+
+@pytest.fixture()
+def MS(stub_host_lib, monkeypatch):
+    import loghisto_b200.metric_system as m
+    monkeypatch.setattr(m, "_lib", m._bind(ctypes.CDLL(stub_host_lib)))
+    made = []
+
+    def make(interval_s=1e-6, **kw):
+        ms = m.MetricSystem(interval_s, False, max_histograms=kw.get("max_histograms", 64),
+                            max_counters=kw.get("max_counters", 64))
+        made.append(ms)
+        return ms
+    yield make
+    for ms in made:
+        ms.close()
+
+
+def _cases():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("host_ms_cases", os.path.join(ROOT, "tests", "test_host_metric_system.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_example_metric_system_keys(MS):
+    _cases().test_example_metric_system_keys(MS)
+
+
+def test_timer(MS):
+    _cases().test_timer(MS)
+
+
+def test_rate(MS):
+    _cases().test_rate(MS)
+
+
+def test_counter(MS):
+    _cases().test_counter(MS)
+
+
+def test_processed_broadcast(MS):
+    _cases().test_processed_broadcast(MS)
+
+
+def test_raw_broadcast(MS):
+    _cases().test_raw_broadcast(MS)
+
+
+def test_slow_subscriber_is_closed_not_blocked_on(MS):
+    _cases().test_slow_subscriber_is_closed_not_blocked_on(MS)
+
+
+def test_stop_is_idempotent_and_leaves_no_thread(MS):
+    _cases().test_stop_is_idempotent_and_leaves_no_thread(MS)
+
+
+def test_mixed_ops_match_oracle_port(MS, oracle):
+    _cases().test_mixed_ops_match_oracle_port(MS, oracle)
+
+
+def test_names_beyond_capacity_are_dropped_and_counted(MS):
+    _cases().test_names_beyond_capacity_are_dropped_and_counted(MS)
