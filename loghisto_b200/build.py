@@ -23,12 +23,13 @@ NVCC_FLAGS = [
 
 HOST_LIB = os.path.join(HERE, "libloghisto_host.so")
 HOST_SRC = os.path.join(HERE, "host", "metric_system.cc")
+HOST_SRCS = [HOST_SRC, os.path.join(HERE, "host", "print_benchmark.cc")]
 
 
 def needs_build_host() -> bool:
     if not os.path.exists(HOST_LIB):
         return True
-    deps = [HOST_SRC, os.path.join(HERE, "host", "metric_system.h"), os.path.join(ROOT, "include", "loghisto_b200.h"), LIB]
+    deps = HOST_SRCS + [os.path.join(HERE, "host", "metric_system.h"), os.path.join(ROOT, "include", "loghisto_b200.h"), LIB]
     return _newest([d for d in deps if os.path.exists(d)]) > os.path.getmtime(HOST_LIB)
 
 
@@ -39,7 +40,7 @@ def build_host(force: bool = False) -> str:
         return HOST_LIB
     gxx = shutil.which("g++") or "g++"
     cmd = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-Wextra",
-           "-I", os.path.join(ROOT, "include"), "-o", HOST_LIB, HOST_SRC,
+           "-I", os.path.join(ROOT, "include"), "-o", HOST_LIB] + HOST_SRCS + [
            "-L", HERE, "-lloghisto_b200", "-Wl,-rpath,$ORIGIN", "-lpthread"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -180,4 +180,10 @@ class MetricSystem {
     uint64_t dropped_over_limit_ = 0;
 };
 
+// print_benchmark.go:49: run `op` from `concurrency` threads between StartTimer/Stop and print every interval's
+// metrics; returns the last interval's <name>_count after `seconds` (the reference runs forever).
+double PrintBenchmark(const std::string &name, unsigned concurrency, std::function<void()> op, double seconds,
+                      std::chrono::nanoseconds interval = std::chrono::seconds(1), const Options &opt = Options(),
+                      bool print = true);
+
 }  // namespace loghisto

@@ -44,6 +44,8 @@ def _bind(L):
     L.lhms_stop.argtypes = [vp]
     L.lhms_dropped.restype = C.c_uint64
     L.lhms_dropped.argtypes = [vp]
+    L.lhms_print_benchmark.restype = C.c_double
+    L.lhms_print_benchmark.argtypes = [C.c_char_p, C.c_uint, C.c_double, C.c_int64, C.c_int, C.c_int]
     for kind in ("processed", "raw"):
         getattr(L, "lhms_subscribe_" + kind).restype = vp
         getattr(L, "lhms_subscribe_" + kind).argtypes = [vp, C.c_int]
@@ -171,3 +173,11 @@ class MetricSystem:
 
     def dropped(self) -> int:
         return int(self._lib.lhms_dropped(self._h))
+
+
+def PrintBenchmark(name: str, concurrency: int, seconds: float = 3.0, interval_s: float = 1.0, device: int = 0,
+                   print_metrics: bool = False) -> float:
+    """print_benchmark.go:49 with an empty op: `concurrency` threads loop StartTimer/Stop for `seconds`; returns the
+    last interval's <name>_count (timer samples ingested per interval -- the figure readme.md:34 quotes)."""
+    return float(_load().lhms_print_benchmark(name.encode(), concurrency, seconds, int(interval_s * 1e9), device,
+                                              1 if print_metrics else 0))

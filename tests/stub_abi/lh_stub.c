@@ -7,6 +7,7 @@
  * calls, and is never loaded by the product package (which has no CPU fallback).  Bucket arithmetic comes from
  * oracle/loghisto_oracle.c, compiled into the same shared object.
  */
+#include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -20,6 +21,10 @@ uint64_t lho_process_histogram(const uint64_t *counts65536, const double *ps, in
                                double *out_pvals, int32_t *out_pkeys);
 
 #define STUB_SLOTS 64
+
+/* one big lock: the real library is thread-safe, and the host mirror relies on that */
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+#define LOCKED(expr) do { pthread_mutex_lock(&g_mu); lh_status _st = (expr); pthread_mutex_unlock(&g_mu); return _st; } while (0)
 
 struct lh_ctx {
     lh_config cfg;
@@ -69,7 +74,7 @@ LH_API lh_status lh_destroy(lh_ctx *c) {
     return LH_OK;
 }
 
-LH_API lh_status lh_staging_acquire(lh_ctx *c, lh_staging *out) {
+static lh_status lh_staging_acquire_impl(lh_ctx *c, lh_staging *out) {
     for (uint32_t i = 0; i < c->nslots; i++)
         if (!c->slot_busy[i]) {
             c->slot_busy[i] = 1;
@@ -80,7 +85,7 @@ LH_API lh_status lh_staging_acquire(lh_ctx *c, lh_staging *out) {
     return LH_ERR_STATE;
 }
 
-LH_API lh_status lh_staging_commit_keyed_f64_u16(lh_ctx *c, const lh_staging *s, size_t n, uint64_t ids_offset) {
+static lh_status lh_staging_commit_keyed_f64_u16_impl(lh_ctx *c, const lh_staging *s, size_t n, uint64_t ids_offset) {
     const double *v = (const double *)c->slot_mem[s->slot];
     const uint16_t *ids = (const uint16_t *)((const char *)c->slot_mem[s->slot] + ids_offset);
     uint64_t *b = c->buckets[c->active];
@@ -93,7 +98,7 @@ LH_API lh_status lh_staging_commit_keyed_f64_u16(lh_ctx *c, const lh_staging *s,
     return LH_OK;
 }
 
-LH_API lh_status lh_staging_commit_counter_u16(lh_ctx *c, const lh_staging *s, size_t n, uint64_t ids_offset) {
+static lh_status lh_staging_commit_counter_u16_impl(lh_ctx *c, const lh_staging *s, size_t n, uint64_t ids_offset) {
     const uint64_t *a = (const uint64_t *)c->slot_mem[s->slot];
     const uint16_t *ids = (const uint16_t *)((const char *)c->slot_mem[s->slot] + ids_offset);
     for (size_t i = 0; i < n; i++) {
@@ -105,7 +110,7 @@ LH_API lh_status lh_staging_commit_counter_u16(lh_ctx *c, const lh_staging *s, s
     return LH_OK;
 }
 
-LH_API lh_status lh_snapshot_begin(lh_ctx *c) {
+static lh_status lh_snapshot_begin_impl(lh_ctx *c) {
     if (c->frozen) { snprintf(c->err, sizeof c->err, "previous snapshot not ended"); return LH_ERR_STATE; }
     c->active ^= 1;
     c->frozen = 1;
@@ -113,8 +118,8 @@ LH_API lh_status lh_snapshot_begin(lh_ctx *c) {
     return LH_OK;
 }
 
-LH_API lh_status lh_snapshot_reduce(lh_ctx *c, const double *ps, uint32_t np, uint64_t *counts, double *sums, double *avgs,
-                                    int32_t *pkeys, double *pvals) {
+static lh_status lh_snapshot_reduce_impl(lh_ctx *c, const double *ps, uint32_t np, uint64_t *counts, double *sums, double *avgs,
+                                         int32_t *pkeys, double *pvals) {
     if (!c->frozen) return LH_ERR_STATE;
     const uint64_t *fb = c->buckets[c->active ^ 1];
     for (uint32_t h = 0; h < c->cfg.max_histograms; h++) {
@@ -132,7 +137,7 @@ LH_API lh_status lh_snapshot_reduce(lh_ctx *c, const double *ps, uint32_t np, ui
     return LH_OK;
 }
 
-LH_API lh_status lh_snapshot_export(lh_ctx *c, lh_sparse *out) {
+static lh_status lh_snapshot_export_impl(lh_ctx *c, lh_sparse *out) {
     if (!c->frozen) return LH_ERR_STATE;
     const uint64_t *fb = c->buckets[c->active ^ 1];
     uint32_t pos = 0;
@@ -150,7 +155,7 @@ LH_API lh_status lh_snapshot_export(lh_ctx *c, lh_sparse *out) {
     return LH_OK;
 }
 
-LH_API lh_status lh_snapshot_end(lh_ctx *c) {
+static lh_status lh_snapshot_end_impl(lh_ctx *c) {
     if (!c->frozen) return LH_ERR_STATE;
     memset(c->buckets[c->active ^ 1], 0, (size_t)c->cfg.max_histograms * 65536u * 8);
     memset(c->counters[c->active ^ 1], 0, (size_t)c->cfg.max_counters * 8);
@@ -158,8 +163,27 @@ LH_API lh_status lh_snapshot_end(lh_ctx *c) {
     return LH_OK;
 }
 
-LH_API lh_status lh_get_stats(lh_ctx *c, lh_stats *out) {
+static lh_status lh_get_stats_impl(lh_ctx *c, lh_stats *out) {
     memset(out, 0, sizeof *out);
     out->samples = c->samples; out->counter_ops = c->counter_ops; out->dropped = c->dropped; out->snapshots = c->snapshots;
     return LH_OK;
+}
+
+LH_API lh_status lh_staging_acquire(lh_ctx *c, lh_staging *out) { LOCKED(lh_staging_acquire_impl(c, out)); }
+
+LH_API lh_status lh_staging_commit_keyed_f64_u16(lh_ctx *c, const lh_staging *s, size_t n, uint64_t ids_offset) { LOCKED(lh_staging_commit_keyed_f64_u16_impl(c, s, n, ids_offset)); }
+
+LH_API lh_status lh_staging_commit_counter_u16(lh_ctx *c, const lh_staging *s, size_t n, uint64_t ids_offset) { LOCKED(lh_staging_commit_counter_u16_impl(c, s, n, ids_offset)); }
+
+LH_API lh_status lh_snapshot_begin(lh_ctx *c) { LOCKED(lh_snapshot_begin_impl(c)); }
+
+LH_API lh_status lh_snapshot_end(lh_ctx *c) { LOCKED(lh_snapshot_end_impl(c)); }
+
+LH_API lh_status lh_snapshot_export(lh_ctx *c, lh_sparse *out) { LOCKED(lh_snapshot_export_impl(c, out)); }
+
+LH_API lh_status lh_get_stats(lh_ctx *c, lh_stats *out) { LOCKED(lh_get_stats_impl(c, out)); }
+
+LH_API lh_status lh_snapshot_reduce(lh_ctx *c, const double *ps, uint32_t np, uint64_t *counts, double *sums, double *avgs,
+                                    int32_t *pkeys, double *pvals) {
+    LOCKED(lh_snapshot_reduce_impl(c, ps, np, counts, sums, avgs, pkeys, pvals));
 }

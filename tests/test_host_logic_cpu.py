@@ -23,7 +23,8 @@ def stub_host_lib():
                     os.path.join(ROOT, "tests", "stub_abi", "lh_stub.c"), os.path.join(ROOT, "oracle", "loghisto_oracle.c"),
                     "-o", stub, "-lm", "-lpthread"], check=True)
     subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I", inc,
-                    os.path.join(ROOT, "loghisto_b200", "host", "metric_system.cc"), "-o", host,
+                    os.path.join(ROOT, "loghisto_b200", "host", "metric_system.cc"),
+                    os.path.join(ROOT, "loghisto_b200", "host", "print_benchmark.cc"), "-o", host,
                     "-L", BUILD, "-llh_stub", "-Wl,-rpath," + BUILD, "-lpthread"], check=True)
     return host
 
@@ -90,3 +91,11 @@ def test_mixed_ops_match_oracle_port(MS, oracle):
 
 def test_names_beyond_capacity_are_dropped_and_counted(MS):
     _cases().test_names_beyond_capacity_are_dropped_and_counted(MS)
+
+
+def test_print_benchmark_driver(stub_host_lib, monkeypatch):
+    """print_benchmark.go:49-70: concurrent StartTimer/Stop loops feed one histogram; every interval reports a count."""
+    import loghisto_b200.metric_system as m
+    monkeypatch.setattr(m, "_lib", m._bind(ctypes.CDLL(stub_host_lib)))
+    count = m.PrintBenchmark("benchmark1234", 4, seconds=0.6, interval_s=0.1)
+    assert count > 100

@@ -183,3 +183,4 @@ def test_names_beyond_capacity_are_dropped_and_counted(MS):
     raw, _ = ms.collect_and_process()
     assert len(raw["Histograms"]) == 4 and len(raw["Counters"]) == 4
     assert ms.dropped() == 4
+
