@@ -40,17 +40,26 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5", "c4x1"],
+                    help="c2 = configs[1] (default), c3 = configs[2] (1024 keyed), c5 = configs[4] (mixed ops), "
+                         "c4x1 = the north-star target: the 1e10-sample stream of configs[3] resident on ONE GPU (80 GB)")
     ap.add_argument("--stream", default="U", choices=["U", "L", "S", "C", "Z"])
     ap.add_argument("--n", type=int, default=0, help="samples per GPU per step (default: BASELINE config)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps for the host-fed leg (default min(steps, 5))")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the bucket-for-bucket oracle check after the timed legs")
+    ap.add_argument("--sustain-seconds", type=float, default=-1.0,
+                    help="extra leg of back-to-back steps for at least this long (default 2 s for c2/c4x1 at N=1, else 0)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--k1-grid-mult", type=int, default=0, help="override the K1 waves-per-launch tuning")
     ap.add_argument("--k1-variant", type=int, default=-1)
     ap.add_argument("--pipeline-depth", type=int, default=-1,
                     help="snapshots in flight behind the next ingest: 0 = blocking snapshot after every batch, 1, 2 (default 2)")
+    ap.add_argument("--collective", default="nccl", choices=["nccl", "peer"],
+                    help="N>1: nccl = torch.distributed all-reduce of the frozen arrays; peer = the library's own "
+                         "peer-memory all-reduce kernel behind the C ABI (lh_comm_*)")
+    ap.add_argument("--keyed-mode", type=int, default=-1)
     ap.add_argument("--nccl-defaults", action="store_true", help="do not set NCCL_MAX_NCHANNELS / NCCL_CGA_CLUSTER_SIZE")
     ap.add_argument("--reserve-sms", type=int, default=-1, help="SMs K1 leaves free for the snapshot stream (default: 0 at N=1, 2 at N>1)")
     return ap.parse_args()
@@ -201,7 +210,7 @@ def run_reference(a):
         return
     from oracle import oracle as o
     o.build()
-    n_hist = 1024 if a.workload == "c3" else 1
+    n_hist = 1024 if a.workload in ("c3", "c5") else 1
     kind = {"U": 0, "L": 1, "S": 2, "C": 3, "Z": 4}[a.stream]
     names = ["histogram%d" % i for i in range(n_hist)]
     rate, threads, ladder = _calibrate_cpu_port(o, kind, n_hist, names)
@@ -225,7 +234,10 @@ def run_reference(a):
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": value / PUBLISHED_SAMPLES_PER_S,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(a, n, a.gpus, sample_of="bounded sample of %d samples per step" % n),
+        # the same config object as the b200 arm prints for this N; the CPU arm processes a bounded sample of that
+        # workload per step and reports a RATE (samples/s), hence rate_normalised
+        "config": workload_config(a, a.n or default_n(a.workload, a.gpus), a.gpus),
+        "rate_normalised": True, "sample": "bounded sample of %d samples per step (about 1 s of CPU work)" % n,
         "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port",
                          "host_cpus": os.cpu_count(), "thread_ladder_samples_per_s": ladder,
                          "sample": "%d samples/step x %d steps, stream %s, %d name(s); C port of "
@@ -235,28 +247,107 @@ def run_reference(a):
     }))
 
 
-def workload_config(a, n_per_gpu, n_gpus, sample_of=None):
+def workload_config(a, n_per_gpu, n_gpus):
     if a.workload == "c2":
         name = ("BASELINE configs[1]: 1 GPU, 1 histogram, 1e9-sample synthetic float64 stream" if n_gpus == 1 else
                 "BASELINE configs[3] slice: %d GPU(s), 1 histogram, %d samples per GPU, bucket-array all-reduce "
                 "before percentiles" % (n_gpus, n_per_gpu))
+    elif a.workload == "c4x1":
+        name = ("north_star target: the 1e10-sample synthetic float64 stream of BASELINE configs[3] resident on ONE GPU "
+                "(80 GB), 1 histogram, bit-exact bucket counts")
     elif a.workload == "c5":
         name = ("BASELINE configs[4]: mixed ops, 50% Histogram (u16 id, f64) / 25% Timer (u16 id, int64 ns) / 25% Counter "
                 "(u16 id, u64 amount 1..16) over 1024 names, one percentile snapshot per batch of ops "
                 "(1e8 ops = 100 ms of traffic at the nominal 1e9 ops/s)")
     else:
         name = "BASELINE configs[2]: 1024 keyed histograms, (uint16 id, float64 value) pairs"
-    cfg = {"workload": name, "stream": a.stream, "samples_per_gpu_per_step": n_per_gpu,
-           "histograms": 1 if a.workload == "c2" else 1024, "percentiles": len(PERCENTILES),
-           "l2": "inputs (%.1f GB per GPU) are larger than the 126 MB L2; no flush needed" % (n_per_gpu * 8 / 1e9),
-           "published_ref": "readme.md:34 (2014, unnamed CPU, Timer path incl. two time.Now() per sample)"}
-    if sample_of:
-        cfg["sample"] = sample_of
-        cfg["l2"] = "n/a (CPU arm)"
-    return cfg
+    single = a.workload in ("c2", "c4x1")
+    return {"workload": name, "stream": a.stream, "samples_per_gpu_per_step": n_per_gpu,
+            "histograms": 1 if single else 1024, "percentiles": len(PERCENTILES),
+            "l2": "inputs (%.1f GB per GPU) are larger than the 126 MB L2; no flush needed"
+                  % (n_per_gpu * (8 if single else 10) / 1e9),
+            "published_ref": "readme.md:34 (2014, unnamed CPU, Timer path incl. two time.Now() per sample)"}
+
+
+# ----------------------------------------------------------------- parity
+def oracle_parity(a, eng, sharded, ingest, world, rank, n, H, kind, timed_red):
+    """Bucket-for-bucket check of the device path against the CPU oracle at the FULL size of this run, outside
+    every timed region.  All ranks ingest their batch once more and take a snapshot with export (the same
+    kernels, the same collective); rank 0 regenerates the whole index range on every host core with the oracle
+    (oracle/loghisto_oracle.c: compress = metrics.go:316-322, Histogram = :273-295, Counter = :251-269,
+    processHistograms/percentile = :336-418) and compares every bucket of every histogram, every counter, and the
+    percentile bucket keys -- of the verification step AND of the last timed step."""
+    import numpy as np
+    mixed = a.workload == "c5"
+    keyed = a.workload == "c3"
+    t0 = time.perf_counter()
+    ingest(None)
+    red, sp = sharded.snapshot(PERCENTILES, export=True, counters=mixed)
+    if rank != 0:
+        return None
+    from oracle import oracle as o
+    o.build()
+    got = np.zeros((H, 65536), dtype=np.uint64)
+    ent_h = np.repeat(np.arange(H), np.diff(sp.offsets.astype(np.int64)))
+    got[ent_h, sp.keys.view(np.uint16)] = sp.counts
+    t1 = time.perf_counter()
+    counters_equal = None
+    if mixed:
+        nh, nt = n // 2, n // 4
+        nc = n - nh - nt
+        want = np.zeros((H, 65536), dtype=np.uint64)
+        want_c = np.zeros(1024, dtype=np.uint64)
+        for r in range(world):
+            b = r * n
+            o.stream_ingest_keyed(kind, nh, H, SEED, val_start=b, ids_start=b, counts=want)
+            o.stream_ingest_keyed(o.STREAM_TIMER_NS, nt, H, SEED, val_start=b + nh, ids_start=b + nh, as_i64=True, counts=want)
+            o.stream_counter(nc, 1024, SEED, val_start=b + nh + nt, ids_start=b + nh + nt, counters=want_c)
+        counters_equal = bool((sp.counter_deltas == want_c).all())
+        n_checked = n * world
+    elif keyed:
+        want = o.stream_ingest_keyed(kind, n * world, H, SEED, val_start=0, ids_start=0)
+        n_checked = n * world
+    else:
+        want = o.stream_ingest(kind, n * world, SEED, start=0).reshape(1, 65536)
+        n_checked = n * world
+    t2 = time.perf_counter()
+    buckets_equal = bool((got == want).all())
+    pkeys_equal = True
+    counts_equal = True
+    pvals_equal = True
+    for h in range(H):
+        ref = o.process_histogram(want[h], PERCENTILES)
+        for r_ in (red, timed_red):
+            if int(r_.counts[h]) != ref["total"]:
+                counts_equal = False
+            if ref["total"] and not (r_.pkeys[h] == ref["pkeys"]).all():
+                pkeys_equal = False
+            if ref["total"] and not (r_.pvals[h].view(np.uint64) == ref["pvals"].view(np.uint64)).all():
+                pvals_equal = False
+    out = {"buckets_equal": buckets_equal, "pkeys_equal": pkeys_equal, "counts_equal": counts_equal,
+           "pvals_bit_equal": pvals_equal, "n_checked": n_checked, "histograms_checked": H,
+           "nonempty_buckets": int((want != 0).sum()), "mismatching_buckets": int((got != want).sum()),
+           "oracle": "oracle/loghisto_oracle.c regenerating indices [0, %d) on %d host threads (%.1f s); device side: "
+                     "one more step of the same batch + snapshot export after the all-reduce, and the percentile keys "
+                     "of the last timed step" % (n_checked, os.cpu_count() or 1, t2 - t1),
+           "seconds": time.perf_counter() - t0}
+    if counters_equal is not None:
+        out["counters_equal"] = counters_equal
+    out["ok"] = bool(buckets_equal and pkeys_equal and counts_equal and pvals_equal and counters_equal is not False)
+    return out
 
 
 # ----------------------------------------------------------------- GPU arm
+def default_n(workload, world):
+    if workload == "c5":
+        return 100_000_000
+    if workload == "c4x1":
+        return 10_000_000_000
+    if workload == "c3" or world == 1:
+        return 1_000_000_000
+    return 1_250_000_000
+
+
 def run_b200(a):
     import numpy as np
     import torch
@@ -270,6 +361,8 @@ def run_b200(a):
             raise SystemExit("bench.py --gpus %d must be launched with torch.distributed.run (one rank per GPU)" % a.gpus)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback (use --impl reference)")
+    if a.workload == "c4x1" and world != 1:
+        raise SystemExit("bench.py: c4x1 is the single-GPU 1e10-sample run; use c2 with --gpus N for the sharded form")
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -277,7 +370,7 @@ def run_b200(a):
         # Measured (profiles/r01/scaling_r01.txt): up to 4 ranks the 512 KiB all-reduce is fastest with few channels
         # and no CTA clusters (its CTAs then fit the 2 SMs the ingest kernel leaves free); with 8 ranks those limits
         # turn pathological (3.37 ms/step) and NCCL's own choices plus 8 free SMs are best (1.58 ms/step).
-        if not a.nccl_defaults and world <= 4:
+        if a.collective == "nccl" and not a.nccl_defaults and world <= 4:
             os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
             os.environ.setdefault("NCCL_CGA_CLUSTER_SIZE", "0")
         import torch.distributed as dist
@@ -285,25 +378,34 @@ def run_b200(a):
 
     keyed = a.workload == "c3"
     mixed = a.workload == "c5"
-    n = a.n or (100_000_000 if mixed else 1_000_000_000 if (world == 1 or keyed) else 1_250_000_000)
-    H = 1 if a.workload == "c2" else 1024
+    single = not (keyed or mixed)
+    n = a.n or default_n(a.workload, world)
+    H = 1 if single else 1024
     kind = {"U": 0, "L": 1, "S": 2, "C": 3, "Z": 4}[a.stream]
-    bytes_per_sample = 8 if a.workload == "c2" else 10
+    bytes_per_sample = 8 if single else 10
 
     eng = lh.Engine(device=local, max_histograms=H, max_counters=1024 if mixed else 1)
     if a.k1_grid_mult:
         eng.tune("k1_grid_mult", a.k1_grid_mult)
     if a.k1_variant >= 0:
         eng.tune("k1", a.k1_variant)
+    if a.keyed_mode >= 0:
+        eng.tune("keyed_mode", a.keyed_mode)
     depth = a.pipeline_depth if a.pipeline_depth >= 0 else 2
-    reserve = a.reserve_sms if a.reserve_sms >= 0 else (0 if depth == 0 else 1 if world == 1 else 2 if world <= 4 else 8)
+    peer = world > 1 and a.collective == "peer"
+    reserve = a.reserve_sms if a.reserve_sms >= 0 else (0 if depth == 0 else 1 if (world == 1 or peer) else 2 if world <= 4 else 8)
     if reserve:
         eng.tune("k1_reserve_sms", reserve)
     # launch on the context's own non-blocking ingest stream (torch's legacy default stream serialises against
     # other streams); torch only wraps it so that torch.cuda.Event can time the region on the launching stream
     stream = torch.cuda.ExternalStream(eng.ingest_stream, device=local)
-    d_vals = eng.gen_stream(kind, n, SEED, start=rank * n, stream=stream)
+    d_vals = eng.alloc(n, np.float64)
+    slab = 1_000_000_000
+    for off in range(0, n, slab):        # generated in 1e9-sample slabs (identical bits: the stream is a function of the index)
+        m = min(slab, n - off)
+        eng._check(eng.lib.lh_gen_stream_f64(eng.h, kind, SEED, rank * n + off, m, d_vals.offset(off), stream.cuda_stream))
     d_ids = eng.gen_ids_u16(0, n, H, SEED, start=rank * n, stream=stream) if (keyed or mixed) else None
+    nh = nt = nc = 0
     if mixed:
         # one batch = n ops: [0, n/2) Histogram, [n/2, 3n/4) Timer (int64 ns), [3n/4, n) Counter; ids cover all three
         nh, nt = n // 2, n // 4
@@ -315,9 +417,10 @@ def run_b200(a):
     torch.cuda.synchronize()
 
     from loghisto_b200.distributed import ShardedEngine
-    sharded = ShardedEngine(eng, local)
+    sharded = ShardedEngine(eng, local, collective=a.collective if world > 1 else "none")
     kernel_ms = []
     allreduce_ms = []
+    launches_per_step = 3 if mixed else 1
 
     def ingest(host_src=None):
         if mixed:
@@ -346,33 +449,28 @@ def run_b200(a):
         inside the call."""
         red = None
         pending = []          # (handle, ingest seq) of snapshots whose results are still on their way
-        if depth == 0:
-            # blocking form: ingest, then the whole snapshot, then the next ingest (nothing overlaps)
-            for i in range(k):
-                ingest(host_src)
-                seq = eng.ingest_seq()
-                red, _ = sharded.snapshot(PERCENTILES)
-                if record and host_src is None:
-                    kernel_ms.append(sum(eng.kernel_ms(seq - j) for j in range(3 if mixed else 1)))
-                    if world > 1:
-                        allreduce_ms.append(sharded.last_allreduce_ms())
-            return red
-        ingest(host_src)
 
         def collect(entry):
             h, seq = entry
             r = sharded.result(h)
             if record and host_src is None:
                 # CUDA events around that batch's ingest kernel(s); the mixed batch is three launches
-                kernel_ms.append(sum(eng.kernel_ms(seq - j) for j in range(3 if mixed else 1)))
+                kernel_ms.append(sum(eng.kernel_ms(seq - j) for j in range(launches_per_step)))
                 if world > 1:
-                    allreduce_ms.append(sharded.last_allreduce_ms())
+                    allreduce_ms.append(sharded.allreduce_ms(h))
             return r
 
+        if depth == 0:
+            # blocking form: ingest, then the whole snapshot, then the next ingest (nothing overlaps)
+            for i in range(k):
+                ingest(host_src)
+                red = collect((sharded.snapshot_async(PERCENTILES, counters=mixed), eng.ingest_seq()))
+            return red
+        ingest(host_src)
         for i in range(k):
             seq = eng.ingest_seq()
             nxt = (lambda: ingest(host_src)) if i + 1 < k else None     # batch i+1 goes out right after the swap
-            pending.append((sharded.snapshot_async(PERCENTILES, after_swap=nxt), seq))
+            pending.append((sharded.snapshot_async(PERCENTILES, counters=mixed, after_swap=nxt), seq))
             if len(pending) >= depth:
                 red = collect(pending.pop(0))
         while pending:
@@ -384,6 +482,26 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(k, host_src=None, record=False):
+        """k steps bracketed by barrier + synchronize on both sides; device events on the launching stream and the
+        host clock both cover the region (the snapshot leg ends host-synchronously), the larger one is reported;
+        max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        t0 = time.perf_counter()
+        red = run_steps(k, host_src, record)
+        e1.record(stream)
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        return red, max_over_ranks(max(e0.elapsed_time(e1), wall))
+
     # ---- device-resident leg
     run_steps(max(a.warmup, 3))
     del allreduce_ms[:]
@@ -391,30 +509,32 @@ def run_b200(a):
     launches0 = eng.stats()["kernel_launches"]
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
-    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e_start.record(stream)
-    t_wall = time.perf_counter()
-    red = run_steps(a.steps, record=True)
-    e_stop.record(stream)
-    barrier()
-    wall_ms = (time.perf_counter() - t_wall) * 1e3
-    dev_ms = max(e_start.elapsed_time(e_stop), 0.0)
-    # the snapshot leg runs on the context's own stream and ends host-synchronously, so the step loop's
-    # wall time bounds it; report the larger of the two clocks (they agree within launch latency)
-    total_ms = max(dev_ms, wall_ms)
+    red, total_ms = timed(a.steps, record=True)
     clk = clocks.stop() if clocks else None
     launches = eng.stats()["kernel_launches"] - launches0
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
     kms = sum(kernel_ms) / len(kernel_ms)
     ar_ms = (sum(allreduce_ms) / len(allreduce_ms)) if allreduce_ms else 0.0
     count_ok = int(red.counts.sum()) == (n - nc if mixed else n) * world
 
+    # ---- sustained leg: back-to-back steps for >= S seconds; the rate over the SECOND half is the sustained figure
+    sus = None
+    s_seconds = a.sustain_seconds if a.sustain_seconds >= 0 else (2.0 if (single and world == 1) else 0.0)
+    if s_seconds > 0:
+        ms_step = total_ms / a.steps
+        half = max(4, int(s_seconds * 500.0 / ms_step) + 1)
+        del kernel_ms[:]
+        _, ms_a = timed(half, record=False)
+        clocks2 = ClockSampler(local) if rank == 0 else None
+        _, ms_b = timed(half, record=True)
+        clk2 = clocks2.stop() if clocks2 else None
+        kms_s = sum(kernel_ms) / len(kernel_ms)
+        sus = {"seconds": (ms_a + ms_b) / 1e3, "steps": 2 * half, "ms_per_step_first_half": ms_a / half,
+               "ms_per_step": ms_b / half, "kernel_ms": kms_s, "clocks": clk2}
+        del kernel_ms[:]
+
     # ---- host-fed leg (e2e)
     e2e = None
-    if not a.no_e2e and not mixed:
+    if not a.no_e2e and not mixed and a.workload != "c4x1":
         ksteps = a.e2e_steps or min(a.steps, 5)
         hv = eng.pinned(n, np.float64)
         eng._check(eng.lib.lh_memcpy_d2h(eng.h, hv.ptr, d_vals.ptr, n * 8))
@@ -425,24 +545,23 @@ def run_b200(a):
             eng._check(eng.lib.lh_memcpy_d2h(eng.h, hi.ptr, d_ids.ptr, n * 2))
             hsrc = (hv.array, hi.array)
         run_steps(2, hsrc)
-        barrier()
-        t0 = time.perf_counter()
-        red_h = run_steps(ksteps, hsrc)
-        barrier()
-        e2e_ms = (time.perf_counter() - t0) * 1e3
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+        red_h, e2e_ms = timed(ksteps, hsrc)
         d2h = H * 8 * 3 + H * len(PERCENTILES) * 12
         e2e = {"value": n * world * ksteps / (e2e_ms / 1e3), "unit": "samples/s",
                "h2d_bytes_per_step": n * bytes_per_sample, "d2h_bytes_per_step": d2h, "steps": ksteps,
                "ms_per_step": e2e_ms / ksteps, "api": "lh_ingest_f64_host + lh_snapshot_* (pinned host buffers)",
-               "count_ok": int(red_h.counts.sum()) == n * world}
+               "count_ok": int(red_h.counts.sum()) == n * world,
+               "same_result_as_device_leg": bool((red_h.pkeys == red.pkeys).all() and (red_h.counts == red.counts).all())}
         hv.free()
         if hi is not None:
             hi.free()
 
+    # ---- parity (outside every timed region)
+    parity = None
+    if not a.no_parity:
+        parity = oracle_parity(a, eng, sharded, ingest, world, rank, n, H, kind, red)
+
+    rc = 0
     if rank == 0:
         peak, peak_src = peak_hbm()
         achieved = n * bytes_per_sample / (kms / 1e3) / 1e9
@@ -460,25 +579,46 @@ def run_b200(a):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": n * bytes_per_sample,
                          "peak_source": peak_src,
-                         "kernel": "k_ingest_keyed_vec x2 + k_counter_add_smem" if mixed else "k_ingest_keyed_vec" if keyed else "k_ingest_single (%s)" % eng.k1_variant_name(),
+                         "kernel": ("keyed ingest x2 + k_counter_add_smem (%s)" % eng.keyed_kernel_name()) if mixed else
+                                   eng.keyed_kernel_name() if keyed else "k_ingest_single (%s)" % eng.k1_variant_name(),
                          "kernel_ms": kms, "bytes_per_sample": bytes_per_sample},
-            "allreduce_ms": ar_ms,
         }
+        if world > 1:
+            line["collective"] = {"kind": sharded.collective, "allreduce_ms": ar_ms,
+                                  "timed": "CUDA events around the collective on the snapshot stream, one pair per step, "
+                                           "warm-up pairs discarded",
+                                  "bytes": sharded.allreduce_bytes()}
+            line["allreduce_ms"] = ar_ms
+        if sus:
+            v_s = n * world / (sus["ms_per_step"] / 1e3)
+            a_s = n * bytes_per_sample / (sus["kernel_ms"] / 1e3) / 1e9
+            line["value_sustained"] = v_s
+            line["roofline"]["achieved_sustained"] = a_s
+            line["roofline"]["frac_sustained"] = a_s / peak
+            line["sustained"] = sus
         if e2e:
             line["e2e"] = e2e
+        if parity:
+            line["parity"] = parity
+            if not parity["ok"]:
+                rc = 3
         if world == 1 and not a.no_cpu_baseline and not mixed:
             rate, threads, ns, dense, ladder = cpu_port_rate(H, kind, a.cpu_seconds)
             line["cpu_baseline"] = {
                 "value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
                 "sample": "%d samples of the same stream; C port of metrics.go:273-295 (RWMutex + maps + atomic add, "
-                          "Go-exact compress), all host threads; Go toolchain absent so the reference itself cannot run"
-                          % ns,
+                          "Go-exact compress) at the fastest rung of a thread ladder (= `cores`; more threads are slower, "
+                          "the shared reader count ping-pongs as in the reference); the Go toolchain is absent so the "
+                          "reference itself cannot run" % ns,
                 "host_cpus": os.cpu_count(), "thread_ladder_samples_per_s": ladder,
                 "dense_private_arrays_all_cores_value": dense}
         print(json.dumps(line))
+        sys.stdout.flush()
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
+    if rc:
+        sys.exit(rc)
 
 
 def main():

@@ -44,18 +44,39 @@ class ShardedEngine:
     lh_snapshot_reduce (+ export) -> lh_snapshot_end, so every rank ends with the global percentiles.
     snapshot_async()/result() is the pipelined form: everything is only enqueued (the snapshot stream
     outranks the ingest stream), the caller launches the next interval's ingest, then collects the result.
+
+    collective:
+      "peer"  the library's own peer-memory all-reduce kernel behind the C ABI (lh_comm_* /
+              lh_snapshot_allreduce): every rank sums the live window of all peers' frozen arrays over NVLink
+              in one small kernel; torch.distributed only carries the 512-byte peer handles at start-up;
+      "nccl"  torch.distributed all_reduce (NCCL on GPUs, gloo in the CPU tests) of the dense arrays;
+      "none"  single rank.
     """
 
-    def __init__(self, engine, device_index: int, group=None):
+    def __init__(self, engine, device_index: int, group=None, collective: str = "nccl"):
         import torch.distributed as dist
         self.engine = engine
         self.device_index = device_index
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.last_allreduce_events = None
-        self._ar_events = []
+        self.collective = collective if self.world > 1 else "none"
         self._views = {}     # device pointer -> cached zero-copy tensor
         self._ext = None
+        self._bytes = 0
+        if self.collective == "peer":
+            self._init_peer(dist)
+
+    def _init_peer(self, dist):
+        """Exchange the opaque peer handles (lh_comm_export) with an all_gather and hand them to lh_comm_import."""
+        import torch
+        eng = self.engine
+        mine = eng.comm_export()                                   # bytes
+        rank = dist.get_rank(self.group)
+        t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to("cuda:%d" % self.device_index)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t, group=self.group)
+        eng.comm_import(rank, self.world, b"".join(bytes(o.cpu().numpy().tobytes()) for o in out))
+        dist.barrier(group=self.group)                             # every rank has mapped every peer
 
     def _tensor(self, ptr: int, words: int):
         import torch
@@ -66,12 +87,17 @@ class ShardedEngine:
         return t
 
     def _allreduce_frozen(self, counters: bool):
-        import torch
+        """Enqueue the collective for the open snapshot; returns what allreduce_ms() needs to time it."""
         eng = self.engine
+        if self.collective == "peer":
+            seq = eng.snapshot_allreduce(counters)
+            return ("peer", seq)
+        import torch
         v = eng.snapshot_device()
         if self._ext is None or self._ext.cuda_stream != int(v.stream):
             self._ext = torch.cuda.ExternalStream(int(v.stream), device=self.device_index)
         ext = self._ext
+        self._bytes = int(v.n_bucket_words) * 8 + (int(v.n_counter_words) * 8 if counters else 0)
         with torch.cuda.stream(ext):
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
@@ -80,10 +106,7 @@ class ShardedEngine:
             if counters:
                 allreduce_sum_u64(self._tensor(int(v.d_counters), int(v.n_counter_words)), self.group)
             e1.record(ext)
-        self.last_allreduce_events = (e0, e1)
-        self._ar_events.append((e0, e1))
-        if len(self._ar_events) > 8:
-            self._ar_events.pop(0)
+        return ("nccl", (e0, e1))
 
     def snapshot(self, percentiles, export: bool = False, counters: bool = False):
         eng = self.engine
@@ -98,30 +121,40 @@ class ShardedEngine:
         return red, sp
 
     def snapshot_async(self, percentiles, counters: bool = False, after_swap=None):
-        """begin + all-reduce + reduce + end, all enqueued; returns a handle for result().
+        """begin + all-reduce + reduce + end, all enqueued; returns a handle for result() / allreduce_ms().
 
         `after_swap` (optional callable) runs right after the buffer swap and before the collective is issued:
         pipelined callers launch the next interval's ingest there, so that it is already queued on the device
         should the collective's host call take time."""
         eng = self.engine
         eng.snapshot_begin()
+        ar = None
         try:
             if after_swap is not None:
                 after_swap()
             if self.world > 1:
-                self._allreduce_frozen(counters)
+                ar = self._allreduce_frozen(counters)
             h = eng.snapshot_reduce_async(percentiles)
         finally:
             eng.snapshot_end()
-        return h
+        return (h, ar)
 
     def result(self, handle):
-        return self.engine.snapshot_result(handle)
+        return self.engine.snapshot_result(handle[0])
 
-    def last_allreduce_ms(self) -> float:
-        """Device time of the oldest all-reduce not yet reported (FIFO, matching result() order)."""
-        if not self._ar_events:
+    def allreduce_ms(self, handle) -> float:
+        """Device time of THIS snapshot's collective (CUDA events around it on the snapshot stream)."""
+        ar = handle[1]
+        if ar is None:
             return 0.0
-        e0, e1 = self._ar_events.pop(0)
+        if ar[0] == "peer":
+            return self.engine.comm_allreduce_ms(ar[1])
+        e0, e1 = ar[1]
         e1.synchronize()
         return float(e0.elapsed_time(e1))
+
+    def allreduce_bytes(self) -> int:
+        """Bytes one rank's collective moves per snapshot (dense arrays for nccl; window bytes read from peers)."""
+        if self.collective == "peer":
+            return self.engine.comm_last_bytes()
+        return self._bytes

@@ -200,6 +200,15 @@ class Engine:
     def k1_variant_name(self) -> str:
         return self.lib.lh_k1_variant_name(self.h, self.lib.lh_k1_variant_current(self.h)).decode()
 
+    def keyed_kernel_name(self) -> str:
+        """Name of the kernel lh_ingest_keyed_* dispatches to for this context's histogram count."""
+        fn = getattr(self.lib, "lh_keyed_kernel_name", None)
+        if fn is None:
+            return "k_ingest_keyed_vec" if self.H > 44 else "k_ingest_keyed_small"
+        fn.restype = C.c_char_p
+        fn.argtypes = [C.c_void_p]
+        return fn(self.h).decode()
+
     def last_kernel_ms(self) -> float:
         ms = C.c_float()
         self._check(self.lib.lh_last_kernel_ms(self.h, C.byref(ms)))

@@ -426,6 +426,95 @@ LHO_EXPORT void lho_ingest_mt(const double *v, size_t n, uint64_t *counts65536, 
 }
 
 /* ------------------------------------------------------------------ */
+/* Streaming full-size checkers: regenerate the synthetic stream slab by slab on every host core and bucket it on
+ * the fly (no sample array is ever materialised), so that bench.py and the tests can compare a 1e9 / 1e10-sample
+ * device run bucket for bucket.  Same compress(), same generators as above.
+ *   single:  counts65536[(uint16)compress(stream(val_kind, val_start + i))] += 1          (metrics.go:273-295)
+ *   keyed:   counts[id_i][...] += 1 with id_i = ids(id_kind, ids_start + i) % H; as_i64 != 0 treats the stream bits
+ *            as int64 nanoseconds converted like TimerToken.Stop does (metrics.go:242-246)
+ *   counter: counters[id_i] += amount_i (wrapping)                                         (metrics.go:251-269)
+ * Keyed/counter workers add into the shared arrays with relaxed atomics (integer adds commute). */
+typedef struct {
+    int mode;            /* 0 single, 1 keyed, 2 counter */
+    int val_kind, id_kind, as_i64;
+    uint64_t seed, val_start, ids_start;
+    size_t n;
+    uint32_t H;
+    uint64_t *out;       /* single: private [65536]; keyed: shared [H][65536]; counter: shared [H] */
+} stream_job;
+
+static inline uint32_t stream_id(int kind, uint64_t seed, uint64_t i, uint32_t H) {
+    uint64_t u = splitmix64((seed ^ 0xA5A5A5A5DEADBEEFull) + i);
+    uint32_t a = (uint32_t)((u & 0xFFFFFFFFu) % H), b = (uint32_t)((u >> 32) % H);
+    return kind == 0 ? a : (a < b ? a : b);
+}
+
+static void *stream_worker(void *p) {
+    stream_job *j = (stream_job *)p;
+    for (size_t i = 0; i < j->n; i++) {
+        uint64_t bits = lho_stream_bits(j->val_kind, j->seed, j->val_start + i);
+        if (j->mode == 0) {
+            j->out[(uint16_t)lho_compress(bits_to_f64(bits))]++;
+            continue;
+        }
+        uint32_t id = stream_id(j->id_kind, j->seed, j->ids_start + i, j->H);
+        if (j->mode == 1) {
+            double v = j->as_i64 ? (double)(int64_t)bits : bits_to_f64(bits);
+            __atomic_fetch_add(&j->out[(size_t)id * 65536u + (uint16_t)lho_compress(v)], 1, __ATOMIC_RELAXED);
+        } else {
+            __atomic_fetch_add(&j->out[id], bits, __ATOMIC_RELAXED);
+        }
+    }
+    return NULL;
+}
+
+static void stream_run(stream_job proto, uint64_t *out, int threads) {
+    if (threads < 1) threads = 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+    stream_job *jobs = (stream_job *)malloc(sizeof(stream_job) * (size_t)threads);
+    size_t per = proto.n / (size_t)threads;
+    for (int t = 0; t < threads; t++) {
+        jobs[t] = proto;
+        jobs[t].val_start = proto.val_start + per * (size_t)t;
+        jobs[t].ids_start = proto.ids_start + per * (size_t)t;
+        jobs[t].n = (t == threads - 1) ? proto.n - per * (size_t)t : per;
+        jobs[t].out = proto.mode == 0 ? (uint64_t *)calloc(65536, 8) : out;
+        pthread_create(&th[t], NULL, stream_worker, &jobs[t]);
+    }
+    for (int t = 0; t < threads; t++) {
+        pthread_join(th[t], NULL);
+        if (proto.mode == 0) {
+            for (int k = 0; k < 65536; k++) out[k] += jobs[t].out[k];
+            free(jobs[t].out);
+        }
+    }
+    free(th); free(jobs);
+}
+
+LHO_EXPORT void lho_stream_ingest_mt(int kind, uint64_t seed, uint64_t start, size_t n, uint64_t *counts65536,
+                                     int threads) {
+    stream_job j = {0};
+    j.mode = 0; j.val_kind = kind; j.seed = seed; j.val_start = start; j.n = n; j.H = 1;
+    stream_run(j, counts65536, threads);
+}
+
+LHO_EXPORT void lho_stream_ingest_keyed_mt(int val_kind, int id_kind, int as_i64, uint64_t seed, uint64_t val_start,
+                                           uint64_t ids_start, size_t n, uint32_t H, uint64_t *counts, int threads) {
+    stream_job j = {0};
+    j.mode = 1; j.val_kind = val_kind; j.id_kind = id_kind; j.as_i64 = as_i64; j.seed = seed;
+    j.val_start = val_start; j.ids_start = ids_start; j.n = n; j.H = H;
+    stream_run(j, counts, threads);
+}
+
+LHO_EXPORT void lho_stream_counter_mt(int amount_kind, int id_kind, uint64_t seed, uint64_t val_start,
+                                      uint64_t ids_start, size_t n, uint32_t C, uint64_t *counters, int threads) {
+    stream_job j = {0};
+    j.mode = 2; j.val_kind = amount_kind; j.id_kind = id_kind; j.seed = seed;
+    j.val_start = val_start; j.ids_start = ids_start; j.n = n; j.H = C;
+    stream_run(j, counters, threads);
+}
+
+/* ------------------------------------------------------------------ */
 /*
  * Structure-faithful port of MetricSystem: name-keyed maps
  * guarded by reader/writer locks, read-lock fast path + write-lock creation,

@@ -74,6 +74,11 @@ def lib() -> C.CDLL:
     L.lho_stream_bits.argtypes = [C.c_int, C.c_uint64, C.c_uint64]
     L.lho_gen_stream.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_size_t, dp]
     L.lho_gen_ids.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_size_t, C.c_uint32, u32p]
+    L.lho_stream_ingest_mt.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_size_t, u64p, C.c_int]
+    L.lho_stream_ingest_keyed_mt.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_size_t,
+                                             C.c_uint32, u64p, C.c_int]
+    L.lho_stream_counter_mt.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_size_t, C.c_uint32,
+                                        u64p, C.c_int]
     L.lho_ms_new.restype = C.c_void_p
     L.lho_ms_free.argtypes = [C.c_void_p]
     L.lho_ms_specify_percentiles.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), dp]
@@ -125,6 +130,37 @@ def ingest(vals: np.ndarray, counts: np.ndarray | None = None, threads: int = 1)
     else:
         lib().lho_ingest(_dp(vals), vals.size, _u64p(counts))
     return counts
+
+
+def stream_ingest(kind: int, n: int, seed: int = DEFAULT_SEED, start: int = 0, counts: np.ndarray | None = None,
+                  threads: int | None = None) -> np.ndarray:
+    """Dense histogram of stream `kind` over indices [start, start+n), regenerated and bucketed on the fly on
+    `threads` host threads (default: all) -- the full-size checker for 1e9 / 1e10-sample device runs."""
+    if counts is None:
+        counts = np.zeros(65536, dtype=np.uint64)
+    lib().lho_stream_ingest_mt(kind, seed, start, n, _u64p(counts), threads or os.cpu_count() or 1)
+    return counts
+
+
+def stream_ingest_keyed(val_kind: int, n: int, n_histograms: int, seed: int = DEFAULT_SEED, val_start: int = 0,
+                        ids_start: int = 0, id_kind: int = 0, as_i64: bool = False,
+                        counts: np.ndarray | None = None, threads: int | None = None) -> np.ndarray:
+    """counts[id_i][(uint16)compress(v_i)] += 1 for the (ids, values) streams, regenerated on the fly."""
+    if counts is None:
+        counts = np.zeros((n_histograms, 65536), dtype=np.uint64)
+    lib().lho_stream_ingest_keyed_mt(val_kind, id_kind, 1 if as_i64 else 0, seed, val_start, ids_start, n,
+                                     n_histograms, _u64p(counts), threads or os.cpu_count() or 1)
+    return counts
+
+
+def stream_counter(n: int, n_counters: int, seed: int = DEFAULT_SEED, val_start: int = 0, ids_start: int = 0,
+                   id_kind: int = 0, counters: np.ndarray | None = None, threads: int | None = None) -> np.ndarray:
+    """counters[id_i] += amount_i for the (ids, amounts = stream A) streams, regenerated on the fly."""
+    if counters is None:
+        counters = np.zeros(n_counters, dtype=np.uint64)
+    lib().lho_stream_counter_mt(STREAM_AMOUNTS, id_kind, seed, val_start, ids_start, n, n_counters, _u64p(counters),
+                                threads or os.cpu_count() or 1)
+    return counters
 
 
 def ingest_keyed(ids: np.ndarray, vals: np.ndarray, n_histograms: int,
