@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps for the host-fed leg (default min(steps, 5))")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-api", action="store_true", help="skip the per-call API leg (MetricSystem.Histogram / StartTimer+Stop)")
     ap.add_argument("--no-parity", action="store_true", help="skip the bucket-for-bucket oracle check after the timed legs")
     ap.add_argument("--sustain-seconds", type=float, default=-1.0,
                     help="extra leg of back-to-back steps for at least this long (default 2 s for c2/c4x1 at N=1, else 0)")
@@ -60,6 +61,7 @@ def parse_args():
                     help="N>1: nccl = torch.distributed all-reduce of the frozen arrays; peer = the library's own "
                          "peer-memory all-reduce kernel behind the C ABI (lh_comm_*)")
     ap.add_argument("--keyed-mode", type=int, default=-1)
+    ap.add_argument("--debug-steps", action="store_true", help="print every timed step's kernel time to stderr")
     ap.add_argument("--nccl-defaults", action="store_true", help="do not set NCCL_MAX_NCHANNELS / NCCL_CGA_CLUSTER_SIZE")
     ap.add_argument("--reserve-sms", type=int, default=-1, help="SMs K1 leaves free for the snapshot stream (default: 0 at N=1, 2 at N>1)")
     return ap.parse_args()
@@ -337,6 +339,31 @@ def oracle_parity(a, eng, sharded, ingest, world, rank, n, H, kind, timed_red):
     return out
 
 
+# ----------------------------------------------------------------- per-call API leg
+def api_leg(device, kind):
+    """The reference's one published number (readme.md:34: 2.0171e7 timer samples/s) is a PER-CALL rate: goroutines
+    looping StartTimer/Stop (print_benchmark.go:59-67).  This leg drives the same loop, and a plain
+    Histogram(name, value)-per-sample loop, through the C++ MetricSystem mirror above the C ABI (one OS thread per
+    goroutine; thread-local name cache, one pinned staging shard per thread, batches committed to the GPU)."""
+    from loghisto_b200.metric_system import MetricSystem, timer_loop
+    ncpu = os.cpu_count() or 1
+    out = {"published_reference_samples_per_s": PUBLISHED_SAMPLES_PER_S,
+           "published_reference_source": "readme.md:34 (StartTimer/Stop from 100 goroutines, 2014, unnamed CPU)"}
+    rate, calls, reported = timer_loop("benchmark1234", 100, 2.0, 0.1, device)
+    out["timer_loop"] = {"value": rate, "unit": "calls/s", "threads": 100, "op": "StartTimer + Stop (print_benchmark.go:59-67, empty op)",
+                         "calls": calls, "reported_count": reported, "count_ok": float(calls) == reported, "host_cpus": ncpu}
+    n_api = 500_000_000
+    ms = MetricSystem(3600.0, False, device=device, max_histograms=16, max_counters=16)
+    dt = ms.histogram_stream(["benchmark1234"], kind if kind in (0, 1) else 0, SEED, 0, n_api, ncpu)
+    raw, metrics = ms.collect_and_process()
+    got = sum(raw["Histograms"].get("benchmark1234", {}).values())
+    out["histogram_calls"] = {"value": n_api / dt, "unit": "calls/s", "threads": ncpu, "calls": n_api,
+                              "op": "MetricSystem.Histogram(name, value), one call per sample, 1 name", "count_ok": got == n_api,
+                              "dropped": ms.dropped()}
+    ms.close()
+    return out
+
+
 # ----------------------------------------------------------------- GPU arm
 def default_n(workload, world):
     if workload == "c5":
@@ -513,6 +540,8 @@ def run_b200(a):
     clk = clocks.stop() if clocks else None
     launches = eng.stats()["kernel_launches"] - launches0
     kms = sum(kernel_ms) / len(kernel_ms)
+    if a.debug_steps and rank == 0:
+        sys.stderr.write("kernel_ms per step: %s\ntotal_ms %.3f\n" % (" ".join("%.3f" % x for x in kernel_ms), total_ms))
     ar_ms = (sum(allreduce_ms) / len(allreduce_ms)) if allreduce_ms else 0.0
     count_ok = int(red.counts.sum()) == (n - nc if mixed else n) * world
 
@@ -556,6 +585,11 @@ def run_b200(a):
         if hi is not None:
             hi.free()
 
+    # ---- per-call API leg: the path an instrumented service uses (one Histogram / StartTimer+Stop call per sample)
+    api = None
+    if a.workload == "c2" and world == 1 and not a.no_api:
+        api = api_leg(local, kind)
+
     # ---- parity (outside every timed region)
     parity = None
     if not a.no_parity:
@@ -598,6 +632,8 @@ def run_b200(a):
             line["sustained"] = sus
         if e2e:
             line["e2e"] = e2e
+        if api:
+            line["api_e2e"] = api
         if parity:
             line["parity"] = parity
             if not parity["ok"]:

@@ -43,9 +43,12 @@ extern "C" {
 #define LH_API
 #endif
 
-#define LH_ABI_VERSION 1
+#define LH_ABI_VERSION 2
 #define LH_KEYS_PER_HISTOGRAM 65536
 #define LH_MAX_PERCENTILES 32
+#define LH_MAX_PRECISION 250     /* buckets per unit of ln(1+|v|); the reference's constant is 100 (metrics.go:40-43) */
+#define LH_MAX_RANKS 16          /* GPUs one lh_comm group may span (one node) */
+#define LH_PEER_HANDLE_BYTES 1024
 
 typedef int32_t lh_status;
 enum {
@@ -68,6 +71,9 @@ typedef struct lh_config {
     uint64_t staging_bytes;   /* bytes per pinned staging slot (0 = 32 MiB) */
     uint32_t staging_slots;   /* slots in the ring (0 = 3) */
     uint32_t flags;           /* reserved, 0 */
+    uint32_t precision;       /* `precision` of compress/decompress (metrics.go:40-43, 316-332): key =
+                               * int16(precision*ln(1+|v|)+0.5).  0 = the reference's 100; 1..LH_MAX_PRECISION */
+    uint32_t reserved[3];     /* 0 */
 } lh_config;
 
 /* ---- lifecycle ------------------------------------------------------- */
@@ -160,6 +166,11 @@ typedef struct lh_device_view {
     uint64_t n_bucket_words;
     uint64_t n_counter_words;
     void *stream;          /* cudaStream_t the snapshot work is ordered on */
+    uint32_t *d_flags;     /* [max_histograms] 0 = untouched this interval, 1 = counts inside the fast window only,
+                            * 3 = also outside it.  A caller that reduces d_buckets in place across GPUs must reduce
+                            * these with MAX (= bitwise OR) too: the reduction / export kernels scan only what the
+                            * flags cover */
+    uint64_t n_flag_words;
 } lh_device_view;
 
 LH_API lh_status lh_snapshot_begin(lh_ctx *ctx);
@@ -197,6 +208,39 @@ LH_API lh_status lh_snapshot_export(lh_ctx *ctx, lh_sparse *out);
 LH_API lh_status lh_snapshot_copy_histogram(lh_ctx *ctx, uint32_t histogram_id, uint64_t *h_out65536);
 LH_API lh_status lh_snapshot_end(lh_ctx *ctx);
 
+/* ---- multi-GPU: sharded sample stream, bucket arrays summed at snapshot time -------------
+ * One context per GPU (one process per GPU, or one thread per GPU in one process).  Each rank ingests its shard
+ * into its own arrays; between lh_snapshot_begin and the reduction, lh_snapshot_allreduce sums the live window of
+ * every rank's frozen arrays into this rank's view of the snapshot with ONE small kernel that reads the peers'
+ * memory directly over NVLink (peer mappings: CUDA IPC between processes, peer access inside one process) -- no
+ * library collective, nothing to link.  uint64 sums are associative, so every rank ends with exactly the bucket
+ * counts a single GPU would have produced (metrics.go:273-295 over the whole stream).
+ *
+ *   lh_comm_export   opaque handle describing this context's arrays; the host exchanges the handles of all ranks
+ *                    by any means it has (a file, a pipe, MPI, torch.distributed, Go channels in one process)
+ *   lh_comm_import   maps every peer; handles[rank] must be this context's own.  Collective: every rank calls it
+ *                    before any rank calls lh_snapshot_allreduce
+ *   lh_snapshot_allreduce  collective, between lh_snapshot_begin and lh_snapshot_reduce/_export: ranks must take
+ *                    their snapshots in lock-step (same number, same order).  Enqueued on the snapshot stream; the
+ *                    kernel waits on the device for the peers' frozen arrays (no host synchronisation) and returns
+ *                    LH_OK immediately.  A peer that never arrives makes the kernel give up after 10 s; that is
+ *                    reported by lh_comm_info.status != 0 (the snapshot's counts are then this rank's own only)
+ *   lh_comm_allreduce_ms   device time of all-reduce `seq` (CUDA events around the kernel on the snapshot stream)
+ */
+typedef struct lh_peer_handle { uint8_t bytes[LH_PEER_HANDLE_BYTES]; } lh_peer_handle;
+typedef struct lh_comm_stats {
+    uint32_t rank, world;
+    uint32_t status;                 /* 0 ok, 1 a peer did not arrive in time, 2 peers froze different buffers */
+    uint32_t reserved;
+    uint64_t allreduces;
+    uint64_t last_bytes_from_peers;  /* bytes read over NVLink by the most recent all-reduce */
+} lh_comm_stats;
+LH_API lh_status lh_comm_export(lh_ctx *ctx, lh_peer_handle *out);
+LH_API lh_status lh_comm_import(lh_ctx *ctx, uint32_t rank, uint32_t world, const lh_peer_handle *handles);
+LH_API lh_status lh_snapshot_allreduce(lh_ctx *ctx, uint32_t include_counters, uint64_t *seq);
+LH_API lh_status lh_comm_allreduce_ms(lh_ctx *ctx, uint64_t seq, float *ms);
+LH_API lh_status lh_comm_info(lh_ctx *ctx, lh_comm_stats *out);
+
 /* ---- scalar helpers, evaluated ON THE DEVICE (parity probes for tests) --- */
 /* out[i] = compress(values[i]) exactly as the ingest kernels compute it
  * (mode 0: production fast path + exact fallback; mode 1: exact path only) */
@@ -213,7 +257,8 @@ LH_API lh_status lh_fastpath_margin(lh_ctx *ctx, const double *d_values, size_t 
 LH_API lh_status lh_fastpath_margin_detail(lh_ctx *ctx, double *h_err_estimator1, double *h_err_estimator2);
 
 /* ---- synthetic streams (bench / tests) ------------- */
-/* kind: 0=U log-uniform, 1=L latency-like, 2=S signed/edge mix, 3=C constant, 4=Z heavy hitter */
+/* kind: 0=U log-uniform, 1=L latency-like, 2=S signed/edge mix, 3=C constant, 4=Z heavy hitter,
+ *       6=timer durations (int64 ns bit patterns), 7=counter amounts 1..16, 8=N (stream U with a random sign) */
 LH_API lh_status lh_gen_stream_f64(lh_ctx *ctx, int kind, uint64_t seed, uint64_t start, size_t n,
                             double *d_out, void *stream);
 LH_API lh_status lh_gen_ids_u16(lh_ctx *ctx, int kind, uint64_t seed, uint64_t start, size_t n,
@@ -242,13 +287,16 @@ LH_API lh_status lh_host_free_pinned(lh_ctx *ctx, void *h_ptr);
 LH_API lh_status lh_memcpy_h2d(lh_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 LH_API lh_status lh_memcpy_d2h(lh_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
 /* kernel-variant selection for profiling: key "k1" -> variant number,
- * "k1_grid_mult", "k1_reserve_sms" (SMs the single-histogram kernel leaves free so that a concurrent
- * snapshot / all-reduce kernel can run beside it), "keyed_blocks_per_sm", "keyed_mode" (0 auto, 1 L2-atomic
- * kernel, 2 owner-partitioned kernel), "kp_chunk" (samples per chunk of the owner-partitioned kernel) */
+ * "k1_grid_mult", "k1_reserve_sms" (SMs the ingest kernels leave free so that a concurrent
+ * snapshot / all-reduce kernel can run beside them), "keyed_blocks_per_sm", "keyed_mode" (0 auto, 1 L2-atomic
+ * kernel, 2 owner-partitioned write-combining kernel whatever the batch size), "kp_chunk" (samples per chunk of the
+ * owner-partitioned kernel) */
 LH_API lh_status lh_tune(lh_ctx *ctx, const char *key, int64_t value);
 LH_API int32_t lh_k1_variant_count(void);
 LH_API int32_t lh_k1_variant_current(lh_ctx *ctx);
 LH_API const char *lh_k1_variant_name(lh_ctx *ctx, int32_t i);
+/* name of the kernel the most recent keyed ingest dispatched to */
+LH_API const char *lh_keyed_kernel_name(lh_ctx *ctx);
 /* time the last `lh_ingest_*` launch range on its stream: CUDA events bracket
  * every ingest kernel; returns the device time of the most recent one in ms */
 LH_API lh_status lh_last_kernel_ms(lh_ctx *ctx, float *ms);

@@ -8,4 +8,5 @@ from .engine import DeviceArray, Engine, LhError, PinnedArray, Reduced, Sparse  
 
 STREAM_U, STREAM_L, STREAM_S, STREAM_C, STREAM_Z = 0, 1, 2, 3, 4
 STREAM_RAW, STREAM_TIMER_NS, STREAM_AMOUNTS = 5, 6, 7   # raw u64 bits / int64 ns / counter amounts 1..16
+STREAM_N = 8                                            # stream U with a random sign
 DEFAULT_SEED = 0x10C415C0

@@ -28,6 +28,7 @@ class lh_config(C.Structure):
         ("struct_size", C.c_uint32), ("device", C.c_int32),
         ("max_histograms", C.c_uint32), ("max_counters", C.c_uint32),
         ("staging_bytes", C.c_uint64), ("staging_slots", C.c_uint32), ("flags", C.c_uint32),
+        ("precision", C.c_uint32), ("reserved", C.c_uint32 * 3),
     ]
 
 
@@ -39,6 +40,17 @@ class lh_device_view(C.Structure):
     _fields_ = [
         ("d_buckets", C.c_void_p), ("d_counters", C.c_void_p),
         ("n_bucket_words", C.c_uint64), ("n_counter_words", C.c_uint64), ("stream", C.c_void_p),
+        ("d_flags", C.c_void_p), ("n_flag_words", C.c_uint64),
+    ]
+
+
+LH_PEER_HANDLE_BYTES = 1024
+
+
+class lh_comm_stats(C.Structure):
+    _fields_ = [
+        ("rank", C.c_uint32), ("world", C.c_uint32), ("status", C.c_uint32), ("reserved", C.c_uint32),
+        ("allreduces", C.c_uint64), ("last_bytes_from_peers", C.c_uint64),
     ]
 
 
@@ -90,6 +102,12 @@ SIGNATURES = {
     "lh_snapshot_export": (_i32, [_vp, C.POINTER(lh_sparse)]),
     "lh_snapshot_copy_histogram": (_i32, [_vp, _u32, _vp]),
     "lh_snapshot_end": (_i32, [_vp]),
+    "lh_comm_export": (_i32, [_vp, _vp]),
+    "lh_comm_import": (_i32, [_vp, _u32, _u32, _vp]),
+    "lh_snapshot_allreduce": (_i32, [_vp, _u32, C.POINTER(_u64)]),
+    "lh_comm_allreduce_ms": (_i32, [_vp, _u64, C.POINTER(C.c_float)]),
+    "lh_comm_info": (_i32, [_vp, C.POINTER(lh_comm_stats)]),
+    "lh_keyed_kernel_name": (C.c_char_p, [_vp]),
     "lh_compress_f64": (_i32, [_vp, _vp, _sz, _vp, C.c_int, _vp]),
     "lh_decompress_table": (_i32, [_vp, _vp]),
     "lh_fastpath_margin": (_i32, [_vp, _vp, _sz, C.POINTER(C.c_double), C.POINTER(_u64), _vp]),

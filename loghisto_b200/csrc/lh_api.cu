@@ -7,12 +7,14 @@
 #include "lh_kernels.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <new>
 #include <string>
 #include <vector>
+#include <unistd.h>
 
 using namespace lh;
 
@@ -23,7 +25,8 @@ struct WriterEvent { cudaStream_t stream; cudaEvent_t ev; };
 struct Buffer {
     unsigned long long *d_buckets = nullptr;   // [H][65536]
     unsigned long long *d_counters = nullptr;  // [C]
-    unsigned int *d_hot = nullptr;             // [hot_replicas][H][LH_SUBHIST] uint32 window of the keyed path
+    uint32_t *d_flags = nullptr;               // [H] 0 untouched / 1 window only / 3 also outside the window
+    unsigned int *d_hot = nullptr;             // [hot_replicas][H][2*win] uint32 window of the keyed path
     unsigned long long hot_pending = 0;        // samples added to d_hot since it was last drained
     cudaEvent_t cleared = nullptr;             // zeroing finished
     std::vector<WriterEvent> writers;          // last ingest per stream
@@ -41,81 +44,92 @@ struct Slot {
 struct K1Variant {
     const char *name;
     void (*launch)(int grid, size_t smem, cudaStream_t s, const double *v32, size_t nvec,
-                   const double *head, int nhead, const double *tail, int ntail, unsigned long long *counts);
+                   const double *head, int nhead, const double *tail, int ntail, unsigned long long *counts,
+                   uint32_t *flag, const Prec &pc);
     const void *func;
     int threads;
-    size_t smem;
+    size_t smem_fixed;   // bytes besides the sub-histogram (ring + barriers)
     int blocks_per_sm;   // filled at create
+    size_t smem;         // filled at create: smem_fixed + sub-histogram for the context's precision
 };
 
-template <int THREADS, int UNROLL, int COPIES, int MINB, bool WIDE>
+template <int THREADS, int UNROLL, int MINB>
 void launch_ldg(int grid, size_t smem, cudaStream_t s, const double *v32, size_t nvec, const double *head, int nhead,
-                const double *tail, int ntail, unsigned long long *counts) {
-    k_ingest_single_ldg<THREADS, UNROLL, COPIES, MINB, WIDE><<<grid, THREADS, smem, s>>>(v32, nvec, head, nhead, tail, ntail, counts);
+                const double *tail, int ntail, unsigned long long *counts, uint32_t *flag, const Prec &pc) {
+    k_ingest_single_ldg<THREADS, UNROLL, MINB><<<grid, THREADS, smem, s>>>(v32, nvec, head, nhead, tail, ntail, counts, flag, pc);
 }
-template <int CW, int STAGES, int STAGE_BYTES, int COPIES, int MINB>
+template <int CW, int STAGES, int STAGE_BYTES, int MINB, bool FOLD>
 void launch_bulk(int grid, size_t smem, cudaStream_t s, const double *v32, size_t nvec, const double *head, int nhead,
-                 const double *tail, int ntail, unsigned long long *counts) {
-    k_ingest_single_bulk<CW, STAGES, STAGE_BYTES, COPIES, MINB><<<grid, (CW + 1) * 32, smem, s>>>(v32, nvec, head, nhead, tail, ntail, counts);
+                 const double *tail, int ntail, unsigned long long *counts, uint32_t *flag, const Prec &pc) {
+    k_ingest_single_bulk<CW, STAGES, STAGE_BYTES, MINB, FOLD><<<grid, (CW + 1) * 32, smem, s>>>(v32, nvec, head, nhead, tail, ntail, counts, flag, pc);
+}
+void launch_probe(int grid, size_t, cudaStream_t s, const double *v32, size_t nvec, const double *head, int nhead,
+                  const double *tail, int ntail, unsigned long long *counts, uint32_t *flag, const Prec &pc) {
+    k_stream_probe<512, 4><<<grid, 512, 0, s>>>(v32, nvec, head, nhead, tail, ntail, counts, flag, pc);
 }
 
-constexpr size_t hist_bytes(int copies) { return (size_t)copies * LH_SUBHIST_ALLOC * 4; }
-constexpr size_t bulk_smem(int stages, int stage_bytes, int copies) {
-    return (size_t)stages * stage_bytes + (size_t)stages * 16 + hist_bytes(copies);
-}
+#define LDG_VARIANT(T, U, M) \
+    { "ldg256_t" #T "_u" #U "_b" #M, launch_ldg<T, U, M>, (const void *)k_ingest_single_ldg<T, U, M>, T, 0, 0, 0 }
+#define BULK_VARIANT(W, S, B, M, F) \
+    { "bulk2_w" #W "_s" #S "_" #B "_b" #M "_sign" #F, launch_bulk<W, S, B, M, F != 0>, (const void *)k_ingest_single_bulk<W, S, B, M, F != 0>, (W + 1) * 32, \
+      (size_t)S * B + (size_t)S * 16, 0, 0 }
 
-#define LDG_VARIANT(T, U, C, M, W) \
-    { "ldg" #W "_t" #T "_u" #U "_c" #C "_b" #M, launch_ldg<T, U, C, M, W == 256>, (const void *)k_ingest_single_ldg<T, U, C, M, W == 256>, T, hist_bytes(C), 0 }
-#define BULK_VARIANT(W, S, B, C, M) \
-    { "bulk_w" #W "_s" #S "_" #B "_c" #C "_b" #M, launch_bulk<W, S, B, C, M>, (const void *)k_ingest_single_bulk<W, S, B, C, M>, (W + 1) * 32, bulk_smem(S, B, C), 0 }
-
+// The shipped kernel plus what the parity tests and profiles/ compare it with (the round-1 sweep of 27 shapes is
+// archived in profiles/r01/k1_variants_sustained.txt; only the winners and the independent first version remain).
 K1Variant g_k1_variants[] = {
-    LDG_VARIANT(512, 2, 1, 2, 256),     // 0
-    LDG_VARIANT(512, 2, 2, 2, 256),     // 1
-    LDG_VARIANT(256, 2, 1, 4, 256),     // 2
-    LDG_VARIANT(512, 2, 1, 2, 128),     // 3
-    LDG_VARIANT(512, 1, 1, 2, 256),     // 4
-    BULK_VARIANT(16, 4, 32768, 1, 1),   // 5
-    BULK_VARIANT(16, 4, 32768, 2, 1),   // 6
-    BULK_VARIANT(8, 4, 16384, 1, 2),    // 7
-    BULK_VARIANT(8, 3, 32768, 1, 2),    // 8
-    BULK_VARIANT(16, 3, 65536, 1, 1),   // 9
-    BULK_VARIANT(4, 4, 8192, 1, 4),     // 10
-#define V2_VARIANT(T, U, M) \
-    { "v2_t" #T "_u" #U "_b" #M, [](int grid, size_t smem, cudaStream_t s, const double *v32, size_t nvec, const double *h, int nh, \
-                                     const double *t, int nt, unsigned long long *c) { k_ingest_single_v2<T, U, M><<<grid, T, smem, s>>>(v32, nvec, h, nh, t, nt, c); }, \
-      (const void *)k_ingest_single_v2<T, U, M>, T, hist_bytes(1), 0 }
-    // 11: read-only diagnostic, produces no counts (never selected by default)
-    { "probe_read_only_t512_u4", [](int grid, size_t, cudaStream_t s, const double *v32, size_t nvec, const double *h, int nh,
-                                    const double *t, int nt, unsigned long long *c) { k_stream_probe<512, 4><<<grid, 512, 0, s>>>(v32, nvec, h, nh, t, nt, c); },
-      (const void *)k_stream_probe<512, 4>, 512, 0, 0 },
-    V2_VARIANT(512, 2, 2),    // 12
-    V2_VARIANT(512, 1, 2),    // 13
-    V2_VARIANT(256, 2, 4),    // 14
-    V2_VARIANT(1024, 1, 1),   // 15
-    V2_VARIANT(512, 2, 1),    // 16
-#define V3_VARIANT(T, M, D) \
-    { "v3_t" #T "_b" #M "_d" #D, [](int grid, size_t smem, cudaStream_t s, const double *v32, size_t nvec, const double *h, int nh, \
-                                      const double *t, int nt, unsigned long long *c) { k_ingest_single_v3<T, M, D><<<grid, T, smem, s>>>(v32, nvec, h, nh, t, nt, c); }, \
-      (const void *)k_ingest_single_v3<T, M, D>, T, hist_bytes(1), 0 }
-    V3_VARIANT(512, 2, 3),    // 17
-    V3_VARIANT(512, 2, 4),    // 18
-    V3_VARIANT(1024, 1, 3),   // 19
-    V3_VARIANT(256, 4, 3),    // 20
-    V3_VARIANT(384, 2, 4),    // 21
-    V3_VARIANT(512, 2, 2),    // 22
-#define BULK2_VARIANT(W, S, B, M) \
-    { "bulk2_w" #W "_s" #S "_" #B "_b" #M, [](int grid, size_t smem, cudaStream_t s, const double *v32, size_t nvec, const double *h, int nh, \
-          const double *t, int nt, unsigned long long *c) { k_ingest_single_bulk<W, S, B, 1, M, true><<<grid, (W + 1) * 32, smem, s>>>(v32, nvec, h, nh, t, nt, c); }, \
-      (const void *)k_ingest_single_bulk<W, S, B, 1, M, true>, (W + 1) * 32, bulk_smem(S, B, 1), 0 }
-    BULK2_VARIANT(16, 3, 65536, 1),   // 23
-    BULK2_VARIANT(16, 4, 32768, 1),   // 24
-    BULK2_VARIANT(8, 4, 16384, 2),    // 25
-    BULK2_VARIANT(8, 5, 16384, 2),    // 26
-    BULK2_VARIANT(16, 5, 32768, 1),   // 27
+    BULK_VARIANT(16, 4, 32768, 1, 1),   // 0: default (sign folded into the slot)
+    BULK_VARIANT(16, 3, 65536, 1, 1),   // 1
+    BULK_VARIANT(8, 4, 16384, 2, 1),    // 2
+    LDG_VARIANT(512, 2, 2),             // 3: first version (scalar fast_candidate, register double-buffering)
+    // 4: read-only diagnostic, produces no counts (never selected by default)
+    { "probe_read_only_t512_u4", launch_probe, (const void *)k_stream_probe<512, 4>, 512, 0, 0, 0 },
+    BULK_VARIANT(16, 4, 32768, 1, 0),   // 5: negatives flagged to the fix-up instead of folded (2 instructions less per sample)
+    BULK_VARIANT(16, 3, 65536, 1, 0),   // 6
 };
 constexpr int kNumK1Variants = (int)(sizeof(g_k1_variants) / sizeof(g_k1_variants[0]));
-constexpr int kDefaultK1Variant = 24;   // bulk2_w16_s4_32768_b1: best burst and sustained time (profiles/r01/k1_variants_sustained.txt)
+constexpr int kDefaultK1Variant = 0;   // bulk2_w16_s4_32768_b1: best burst and sustained time (profiles/r01/k1_variants_sustained.txt)
+
+// Everything the kernels derive from `precision` (metrics.go:40-43), see lh_device.cuh.
+Prec make_prec(uint32_t precision) {
+    Prec pc{};
+    const double P = (double)precision;
+    const double c1 = P * 0.6931471805599453094172321;
+    pc.precision = P;
+    pc.a_int = (uint32_t)std::floor(c1);
+    pc.c1 = (float)c1;
+    pc.c2 = (float)(c1 - (double)pc.a_int);
+    pc.kb = (float)(-1023.0 * (double)pc.c2);
+    const float eps = 0.000244140625f * (precision > 100 ? (float)P / 100.0f : 1.0f);
+    pc.thresh = 0.5f - eps;
+    pc.win = (uint32_t)std::floor(P * 63.0 * 0.6931471805599453094172321 + 0.5) + 1u;
+    pc.a4 = pc.a_int * 4u;
+    pc.coff = 0u - 1023u * pc.a4 - (0x4B400000u << 2);
+    pc.coff0 = 0u - 1023u * pc.a_int - 0x4B400000u;
+    return pc;
+}
+
+constexpr int kMaxRanks = LH_MAX_RANKS;
+constexpr int kCommWords = 2 * LH_MAX_RANKS;       // arrive[16], depart[16]
+constexpr uint32_t kPeerMagic = 0x4C485052u;       // "LHPR"
+
+// what lh_comm_export hands to the peers (fits lh_peer_handle)
+struct PeerWire {
+    uint32_t magic, abi, H, C;
+    uint32_t precision, device;
+    int64_t pid;
+    uint64_t ctx_id;                               // distinguishes contexts of one process
+    uint64_t ptr_buckets[2], ptr_flags[2], ptr_counters[2], ptr_comm;
+    cudaIpcMemHandle_t ipc_buckets[2], ipc_flags[2], ipc_counters[2], ipc_comm;
+};
+static_assert(sizeof(PeerWire) <= LH_PEER_HANDLE_BYTES, "lh_peer_handle too small");
+
+struct PeerMap {                                   // one remote rank as mapped into this process
+    unsigned long long *buckets[2] = {nullptr, nullptr};
+    uint32_t *flags[2] = {nullptr, nullptr};
+    unsigned long long *counters[2] = {nullptr, nullptr};
+    unsigned long long *comm = nullptr;
+    bool ipc = false;                              // pointers came from cudaIpcOpenMemHandle (must be closed)
+};
 
 }  // namespace
 
@@ -124,6 +138,7 @@ struct lh_ctx {
     int device = 0;
     int sm_count = 0;
     uint32_t H = 0, C = 0;
+    Prec pc{};
     Buffer buf[2];
     int active = 0;
     bool frozen = false;
@@ -132,12 +147,13 @@ struct lh_ctx {
     double *d_decomp = nullptr;
     unsigned long long *d_dropped = nullptr;
     // reduce / export scratch
-    // two result slots (ticket & 1): packed [count H][sum H][avg H][pvals H*np][pkeys H*np]
-    double *d_ps[2] = {nullptr, nullptr};
-    char *d_res[2] = {nullptr, nullptr};
-    char *h_res[2] = {nullptr, nullptr};
-    cudaEvent_t res_done[2] = {nullptr, nullptr};
-    uint32_t res_np[2] = {0, 0};
+    // two result slots (ticket & 1): packed [count H][sum H][avg H][pvals H*np][pkeys H*np]; slot 2 is scratch for
+    // lh_snapshot_export when no reduction has produced the non-empty-bucket counts yet (never holds a ticket)
+    double *d_ps[3] = {nullptr, nullptr, nullptr};
+    char *d_res[3] = {nullptr, nullptr, nullptr};
+    char *h_res[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t res_done[3] = {nullptr, nullptr, nullptr};
+    uint32_t res_np[3] = {0, 0, 0};
     uint64_t res_ticket[2] = {0, 0};
     uint64_t next_ticket = 1;
     uint32_t *d_nnz = nullptr, *d_offsets = nullptr;
@@ -157,14 +173,29 @@ struct lh_ctx {
     int k1_reserve_sms = 0;   // SMs left free for concurrent snapshot / collective kernels
     int keyed_blocks_per_sm = 8;
     uint32_t hot_replicas = 1;          // copies of the hot window (all L2-resident); only the vector RED kernel spreads over them
-    int keyed_mode = 0;                 // 0 auto, 1 force L2-atomic kernel, 2 force owner-partitioned kernel
-    int kp_shape = 1;                   // owner-partitioned kernel: 0 = 1x1024 threads per SM, 1 = 2x512
-    int64_t kp_chunk = 16 << 20;        // samples per chunk of the partitioned kernel
+    int keyed_mode = 0;                 // 0 auto, 1 force L2-atomic kernel, 2 force the write-combining owner kernel
+    int64_t kp_chunk = 16 << 20;        // samples per chunk of the owner-partitioned kernel
+    int wc_spt = 16;                    // samples per thread per tile of that kernel (8 or 16)
     // owner-partitioned keyed kernel scratch (allocated on first use)
     unsigned short *d_kp_queues = nullptr;
-    unsigned int *d_kp_tail = nullptr;    // [2][P] tails, then the barrier word
+    unsigned int *d_kp_cnt = nullptr;     // per-(owner, writer) record counts, then the grid-barrier word
     size_t kp_cap = 0;
     int kp_parts = 0;
+    const char *keyed_kernel = "";       // kernel the last keyed launch used
+    // multi-GPU (lh_comm_*): peer mappings of every rank's arrays + this rank's reduced output arrays
+    uint32_t comm_rank = 0, comm_world = 0;
+    unsigned long long *d_comm = nullptr;         // this rank's comm block (uint64[kCommWords])
+    unsigned int *d_comm_aux = nullptr;           // [0] block counter, [1] status
+    PeerMap peers[kMaxRanks];
+    unsigned long long *d_red_buckets = nullptr;  // [H][65536] sums over ranks (valid for the open snapshot after lh_snapshot_allreduce)
+    uint32_t *d_red_flags = nullptr;
+    unsigned long long *d_red_counters = nullptr;
+    bool view_reduced = false;                    // the open snapshot's reduce/export read the reduced arrays
+    bool view_counters_reduced = false;
+    uint64_t comm_seq = 0;
+    static constexpr int kCommRing = 8;
+    cudaEvent_t comm_t0[kCommRing] = {}, comm_t1[kCommRing] = {};
+    uint64_t ctx_id = 0;
     K1Variant k1[kNumK1Variants];
     // timing of the most recent ingest kernel
     // CUDA events bracket every ingest launch; a ring keeps the last kTimingRing of them
@@ -235,6 +266,7 @@ lh_status launch_single(lh_ctx *ctx, uint32_t hid, const double *d_values, size_
     lh_status st = before_write(ctx, b, s);
     if (st != LH_OK) return st;
     unsigned long long *counts = ctx->buf[b].d_buckets + (size_t)hid * 65536u;
+    uint32_t *flag = ctx->buf[b].d_flags + hid;
     const K1Variant &kv = ctx->k1[ctx->k1_variant];
     // a CTA's uint32 sub-histogram must not overflow: tiles are dealt round-robin, so bounding a launch to
     // 2^31 samples per CTA keeps every cell below 2^32 whatever the grid size (reserved SMs shrink it)
@@ -254,11 +286,10 @@ lh_status launch_single(lh_ctx *ctx, uint32_t hid, const double *d_values, size_
         size_t nvec = (m - nhead) >> 2;
         const double *tail = body + nvec * 4;
         int ntail = (int)(m - nhead - nvec * 4);
-        size_t consumed = m;
-        kv.launch(grid, kv.smem, s, body, nvec, head, nhead, tail, ntail, counts);
+        kv.launch(grid, kv.smem, s, body, nvec, head, nhead, tail, ntail, counts, flag, ctx->pc);
         LH_CUDA(ctx, cudaGetLastError());
         ctx->stats.kernel_launches++;
-        done += consumed;
+        done += m;
     }
     LH_CUDA(ctx, cudaEventRecord(ctx->ev_t1, s));
     ctx->timing_valid = true;
@@ -267,57 +298,77 @@ lh_status launch_single(lh_ctx *ctx, uint32_t hid, const double *d_values, size_
 }
 
 lh_status fold_hot(lh_ctx *ctx, int b, cudaStream_t s) {
-    const size_t cells = (size_t)ctx->H * LH_SUBHIST;
+    const size_t cells = (size_t)ctx->H * 2u * ctx->pc.win;
     int grid = (int)std::min<size_t>((cells + 255) / 256, (size_t)ctx->sm_count * 16);
-    k_fold_hot<<<grid, 256, 0, s>>>(ctx->buf[b].d_hot, ctx->buf[b].d_buckets, cells, ctx->hot_replicas);
+    k_fold_hot<<<grid, 256, 0, s>>>(ctx->buf[b].d_hot, ctx->buf[b].d_buckets, ctx->buf[b].d_flags, cells, ctx->hot_replicas, ctx->pc.win);
     LH_CUDA(ctx, cudaGetLastError());
     ctx->stats.kernel_launches++;
     ctx->buf[b].hot_pending = 0;
     return LH_OK;
 }
 
-// Owner-partitioned keyed kernel: worth it (and possible) when there are enough histograms that they cannot
-// be privatised per CTA, few enough that P owners can hold them (ids_per <= 10), and enough samples.
-template <typename IdT, typename ValT>
-lh_status launch_keyed_part(lh_ctx *ctx, int b, const IdT *ids, const ValT *vals, size_t n4x4, cudaStream_t s, bool *used) {
+KeyedOut keyed_out(lh_ctx *ctx, int b) {
+    KeyedOut o{};
+    o.hot = ctx->buf[b].d_hot; o.buckets = ctx->buf[b].d_buckets; o.flags = ctx->buf[b].d_flags;
+    o.dropped = ctx->d_dropped; o.H = ctx->H;
+    return o;
+}
+
+// How many histograms' positive windows one pass of k_ingest_keyed_small can privatise.
+uint32_t ks_ids_per_pass(const lh_ctx *ctx) { return std::max<uint32_t>(1, (uint32_t)(KS_SMEM_BYTES / ((size_t)ctx->pc.win * 4))); }
+
+// Owner-partitioned write-combining kernel: used when the histograms cannot be privatised per CTA in a few
+// passes but P owner CTAs (one per SM) can hold them all, and the batch is big enough to amortise the
+// cooperative launch.
+constexpr size_t kSmemBudget = 227 * 1024;
+// Processes the first *taken samples (whole tiles only); the caller sends the rest to the scalar kernel.
+template <typename IdT, typename ValT, int SPT>
+lh_status launch_keyed_wc_spt(lh_ctx *ctx, int b, const IdT *ids, const ValT *vals, size_t n4x4, cudaStream_t s, bool *used, size_t *taken) {
     *used = false;
-    // kp_shape 0: one 1024-thread CTA per SM; 1: two 512-thread CTAs per SM (stalls of one overlap the other)
-    const bool two = ctx->kp_shape == 1;
-    const int threads = two ? 512 : 1024, tile = threads * 8;
-    const int P = std::min((ctx->sm_count - ctx->k1_reserve_sms) * (two ? 2 : 1), KP_MAX_PARTS);
-    if (P < 8) return LH_OK;
+    *taken = 0;
+    const int P = std::min(ctx->sm_count - ctx->k1_reserve_sms, (int)WC_MAX_PARTS);
+    if (P < 8 || n4x4 == 0) return LH_OK;
     const uint32_t ids_per = (ctx->H + P - 1) / P;
-    // Opt-in only (lh_tune "keyed_mode" = 2): measured 141 G samples/s against 167 G/s for the L2-atomic kernel
-    // (profiles/r01/keyed_modes.txt) -- phase A is latency-bound without a prefetch stage -- so "auto" keeps the
-    // L2-atomic kernel until that is fixed.
-    if (ctx->keyed_mode != 2 || ids_per > 10 || n4x4 == 0) return LH_OK;
-    const size_t slice_tiles = std::max<size_t>(1, ((size_t)ctx->kp_chunk + (size_t)P * tile - 1) / ((size_t)P * tile));
-    // every (owner, writer) pair has its own sub-queue: 2x the expected records per pair per chunk, plus slack
-    const size_t expect = slice_tiles * tile / P;
-    const size_t cap = ((expect * 2 + 256 + 7) / 8) * 8;
+    using S = WcShape<SPT>;
+    const size_t hist_bytes = (((size_t)ids_per * ctx->pc.win + 3) & ~(size_t)3) * 4;
+    const size_t smem = hist_bytes + 2 * WC_MAX_PARTS * 4 + (size_t)(P + 1) * S::STRIDE * 2;
+    if (smem > kSmemBudget || (size_t)ids_per * ctx->pc.win > 65535) return LH_OK;     // records are 16-bit (lid*win + slot)
+    if (ctx->keyed_mode != 2 && n4x4 < ((size_t)1 << 22)) return LH_OK;                // small batches: the L2-atomic kernel
+    n4x4 = n4x4 / S::TILE * S::TILE;
+    if (n4x4 == 0) return LH_OK;
+    const size_t slice_tiles = std::max<size_t>(1, ((size_t)ctx->kp_chunk + (size_t)P * S::TILE - 1) / ((size_t)P * S::TILE));
+    // every (owner, writer) pair has its own sub-queue: 1.5x the expected records per pair per chunk, plus slack
+    const size_t expect = slice_tiles * S::TILE / P;
+    const size_t cap = ((expect * 3 / 2 + 4 * WC_LINE + WC_LINE - 1) / WC_LINE) * WC_LINE;
     if (!ctx->d_kp_queues || ctx->kp_cap != cap || ctx->kp_parts != P) {
-        cudaFree(ctx->d_kp_queues); cudaFree(ctx->d_kp_tail);
-        ctx->d_kp_queues = nullptr; ctx->d_kp_tail = nullptr;
+        cudaFree(ctx->d_kp_queues); cudaFree(ctx->d_kp_cnt);
+        ctx->d_kp_queues = nullptr; ctx->d_kp_cnt = nullptr;
         LH_CUDA(ctx, cudaMalloc(&ctx->d_kp_queues, (size_t)2 * P * P * cap * sizeof(unsigned short)));
-        LH_CUDA(ctx, cudaMalloc(&ctx->d_kp_tail, ((size_t)2 * P * P + 1) * sizeof(unsigned int)));
+        LH_CUDA(ctx, cudaMalloc(&ctx->d_kp_cnt, ((size_t)2 * P * P + 1) * sizeof(unsigned int)));
         ctx->kp_cap = cap; ctx->kp_parts = P;
     }
-    const size_t smem = (size_t)ids_per * LH_WIN * 4 + 3 * KP_MAX_PARTS * 4 + (size_t)tile * 6;
-    const void *fn = two ? (const void *)k_ingest_keyed_part<IdT, ValT, 512, 2> : (const void *)k_ingest_keyed_part<IdT, ValT, 1024, 1>;
+    const void *fn = (const void *)k_ingest_keyed_wc<IdT, ValT, SPT>;
     LH_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    unsigned int *d_barrier = ctx->d_kp_tail + (size_t)2 * P * P;
+    unsigned int *d_barrier = ctx->d_kp_cnt + (size_t)2 * P * P;
     LH_CUDA(ctx, cudaMemsetAsync(d_barrier, 0, sizeof(unsigned int), s));
-    KpParams prm{};
-    prm.ids = ids; prm.vals = vals; prm.n = n4x4; prm.H = ctx->H; prm.ids_per = ids_per; prm.cap = (uint32_t)cap;
+    WcParams prm{};
+    prm.ids = ids; prm.vals = vals; prm.n = n4x4; prm.ids_per = ids_per; prm.cap = (uint32_t)cap;
     prm.inv_p = (uint32_t)(((uint64_t)1 << 32) / (uint64_t)P) + 1u;
-    prm.slice_tiles = (uint32_t)slice_tiles; prm.queues = ctx->d_kp_queues; prm.q_cnt = ctx->d_kp_tail;
-    prm.barrier = d_barrier; prm.hot = ctx->buf[b].d_hot; prm.buckets = ctx->buf[b].d_buckets;
-    prm.dropped = ctx->d_dropped;
-    void *args[] = {&prm};
-    LH_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(P), dim3(threads), args, smem, s));
+    prm.inv_vq = (uint32_t)(((uint64_t)1 << 32) / (uint64_t)(cap / 8)) + 1u;
+    prm.slice_tiles = (uint32_t)slice_tiles; prm.queues = ctx->d_kp_queues; prm.q_cnt = ctx->d_kp_cnt;
+    prm.barrier = d_barrier; prm.o = keyed_out(ctx, b);
+    Prec pc = ctx->pc;
+    void *args[] = {&prm, &pc};
+    LH_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(P), dim3(WC_THREADS), args, smem, s));
     ctx->stats.kernel_launches++;
     *used = true;
+    *taken = n4x4;
     return LH_OK;
+}
+template <typename IdT, typename ValT>
+lh_status launch_keyed_wc(lh_ctx *ctx, int b, const IdT *ids, const ValT *vals, size_t n4x4, cudaStream_t s, bool *used, size_t *taken) {
+    return ctx->wc_spt == 8 ? launch_keyed_wc_spt<IdT, ValT, 8>(ctx, b, ids, vals, n4x4, s, used, taken)
+                            : launch_keyed_wc_spt<IdT, ValT, 16>(ctx, b, ids, vals, n4x4, s, used, taken);
 }
 
 template <typename IdT, typename ValT>
@@ -328,6 +379,7 @@ lh_status launch_keyed(lh_ctx *ctx, const IdT *d_ids, const ValT *d_vals, size_t
     lh_status st = before_write(ctx, b, s);
     if (st != LH_OK) return st;
     constexpr int T = 256;
+    const KeyedOut ko = keyed_out(ctx, b);
     next_timing_slot(ctx);
     LH_CUDA(ctx, cudaEventRecord(ctx->ev_t0, s));
     size_t done = 0;
@@ -345,7 +397,7 @@ lh_status launch_keyed(lh_ctx *ctx, const IdT *d_ids, const ValT *d_vals, size_t
         size_t tail_off = head + n4 * 4;
         if (!vec_ok) { head = 0; tail_off = 0; }
         if (head) {
-            k_ingest_keyed<IdT, ValT, T><<<1, T, 0, s>>>(ids, vals, head, ctx->H, ctx->buf[b].d_hot, ctx->buf[b].d_buckets, ctx->d_dropped);
+            k_ingest_keyed<IdT, ValT, T><<<1, T, 0, s>>>(ids, vals, head, ko, ctx->pc);
             ctx->stats.kernel_launches++;
         }
         if (n4) {
@@ -354,10 +406,11 @@ lh_status launch_keyed(lh_ctx *ctx, const IdT *d_ids, const ValT *d_vals, size_t
             // passes over id sub-ranges match or beat the L2-atomic kernel (each pass is HBM-bound at 10 B/sample) and,
             // unlike it, do not depend on how clustered the values are.
             constexpr uint32_t KS_MAX_PASSES = 4;
-            const uint32_t passes = (ctx->H + KS_MAX_H - 1) / KS_MAX_H;
+            const uint32_t per_max = ks_ids_per_pass(ctx);
+            const uint32_t passes = (ctx->H + per_max - 1) / per_max;
             if (passes <= KS_MAX_PASSES && ctx->keyed_mode == 0 && n4 >= 4096) {
                 const uint32_t per = (ctx->H + passes - 1) / passes;
-                const size_t smem = ((size_t)per * LH_WIN + 4) * 4;
+                const size_t smem = ((size_t)per * ctx->pc.win + 4) * 4;
                 const void *fn = (const void *)k_ingest_keyed_small<IdT, ValT>;
                 LH_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 // one CTA per SM; fewer when the batch is small, so that the per-CTA flush stays negligible
@@ -365,26 +418,32 @@ lh_status launch_keyed(lh_ctx *ctx, const IdT *d_ids, const ValT *d_vals, size_t
                                                                       n4 / (KS_THREADS * 16)));
                 for (uint32_t lo = 0; lo < ctx->H; lo += per) {
                     const uint32_t cnt = std::min(per, ctx->H - lo);
-                    k_ingest_keyed_small<IdT, ValT><<<grid, KS_THREADS, smem, s>>>(ids + head, vals + head, n4, ctx->H, lo, cnt,
-                                                                                  ctx->buf[b].d_hot, ctx->buf[b].d_buckets, ctx->d_dropped);
+                    k_ingest_keyed_small<IdT, ValT><<<grid, KS_THREADS, smem, s>>>(ids + head, vals + head, n4, lo, cnt, ko, ctx->pc);
                     ctx->stats.kernel_launches++;
                 }
                 used = true;
+                ctx->keyed_kernel = "k_ingest_keyed_small";
             }
-            if (!used) st = launch_keyed_part<IdT, ValT>(ctx, b, ids + head, vals + head, n4 * 4, s, &used);
-            if (st != LH_OK) return st;
+            if (!used && ctx->keyed_mode != 1) {
+                size_t taken = 0;
+                st = launch_keyed_wc<IdT, ValT>(ctx, b, ids + head, vals + head, n4 * 4, s, &used, &taken);
+                if (st != LH_OK) return st;
+                if (used) {
+                    ctx->keyed_kernel = "k_ingest_keyed_wc";
+                    tail_off = head + taken;          // whole tiles only: the ragged remainder goes through the scalar kernel below
+                }
+            }
             if (!used) {
                 int grid = grid_1d(ctx, n4, T, 1, ctx->keyed_blocks_per_sm);
-                k_ingest_keyed_vec<IdT, ValT, T><<<grid, T, 0, s>>>(ids + head, vals + head, n4, ctx->H, ctx->buf[b].d_hot,
-                                                                    ctx->hot_replicas, ctx->buf[b].d_buckets, ctx->d_dropped);
+                k_ingest_keyed_vec<IdT, ValT, T><<<grid, T, 0, s>>>(ids + head, vals + head, n4, ctx->hot_replicas, ko, ctx->pc);
                 ctx->stats.kernel_launches++;
+                ctx->keyed_kernel = "k_ingest_keyed_vec";
             }
         }
         if (tail_off < m) {
             size_t r = m - tail_off;
             int grid = grid_1d(ctx, r, T, 1, ctx->keyed_blocks_per_sm);
-            k_ingest_keyed<IdT, ValT, T><<<grid, T, 0, s>>>(ids + tail_off, vals + tail_off, r, ctx->H, ctx->buf[b].d_hot,
-                                                            ctx->buf[b].d_buckets, ctx->d_dropped);
+            k_ingest_keyed<IdT, ValT, T><<<grid, T, 0, s>>>(ids + tail_off, vals + tail_off, r, ko, ctx->pc);
             ctx->stats.kernel_launches++;
         }
         LH_CUDA(ctx, cudaGetLastError());
@@ -425,18 +484,65 @@ lh_status launch_counter(lh_ctx *ctx, const IdT *d_ids, const uint64_t *d_amount
 }
 
 // ---- staging ring (locked) ----
-lh_status slot_wait_free(lh_ctx *ctx, int *out) {
-    // prefer a free slot; otherwise wait for the oldest in-flight one
-    int best = -1;
+// Called with ctx->mu held through `lk`.  The host-side wait for an in-flight slot happens with the mutex RELEASED
+// (the slot is parked as SLOT_ACQUIRED meanwhile so nobody else takes it): other ingest threads are never held up.
+lh_status slot_wait_free(lh_ctx *ctx, std::unique_lock<std::mutex> &lk, int *out) {
+    // prefer a free slot that already has memory, then an in-flight one that has already finished, then a fresh
+    // slot (allocating its pinned + device memory), and only then wait for the oldest in-flight one
+    int best = -1, fresh = -1;
+    for (size_t i = 0; i < ctx->slots.size(); i++) {
+        if (ctx->slots[i].state != SLOT_FREE) continue;
+        if (ctx->slots[i].h) { *out = (int)i; return LH_OK; }
+        if (fresh < 0) fresh = (int)i;
+    }
     for (size_t i = 0; i < ctx->slots.size(); i++)
-        if (ctx->slots[i].state == SLOT_FREE) { *out = (int)i; return LH_OK; }
+        if (ctx->slots[i].state == SLOT_INFLIGHT && cudaEventQuery(ctx->slots[i].done) == cudaSuccess) {
+            ctx->slots[i].state = SLOT_FREE;
+            *out = (int)i;
+            return LH_OK;
+        }
+    cudaGetLastError();   // cudaErrorNotReady from the queries above is not an error
+    if (fresh >= 0) {
+        Slot &sl = ctx->slots[fresh];
+        cudaError_t e = cudaMallocHost(&sl.h, ctx->staging_bytes);
+        if (e == cudaSuccess) e = cudaMalloc(&sl.d, ctx->staging_bytes);
+        if (e != cudaSuccess) {
+            if (sl.h) cudaFreeHost(sl.h);
+            sl.h = nullptr; sl.d = nullptr;
+            return fail(ctx, e == cudaErrorMemoryAllocation ? LH_ERR_NOMEM : LH_ERR_CUDA, "allocating a staging slot", e);
+        }
+        *out = fresh;
+        return LH_OK;
+    }
     for (size_t i = 0; i < ctx->slots.size(); i++)
         if (ctx->slots[i].state == SLOT_INFLIGHT && (best < 0 || ctx->slots[i].seq < ctx->slots[best].seq)) best = (int)i;
     if (best < 0) return fail(ctx, LH_ERR_STATE, "every staging slot is acquired and none is in flight");
-    LH_CUDA(ctx, cudaEventSynchronize(ctx->slots[best].done));
+    ctx->slots[best].state = SLOT_ACQUIRED;
+    cudaEvent_t ev = ctx->slots[best].done;
+    lk.unlock();
+    cudaError_t e = cudaEventSynchronize(ev);
+    lk.lock();
     ctx->slots[best].state = SLOT_FREE;
+    if (e != cudaSuccess) return fail(ctx, LH_ERR_CUDA, "cudaEventSynchronize(slot)", e);
     *out = best;
     return LH_OK;
+}
+
+// close the IPC mappings of the peers (lh_comm_import), if any
+void comm_unmap(lh_ctx *ctx) {
+    for (int r = 0; r < kMaxRanks; r++) {
+        PeerMap &pm = ctx->peers[r];
+        if (pm.ipc) {
+            for (int b = 0; b < 2; b++) {
+                if (pm.buckets[b]) cudaIpcCloseMemHandle(pm.buckets[b]);
+                if (pm.flags[b]) cudaIpcCloseMemHandle(pm.flags[b]);
+                if (pm.counters[b]) cudaIpcCloseMemHandle(pm.counters[b]);
+            }
+            if (pm.comm) cudaIpcCloseMemHandle(pm.comm);
+        }
+        pm = PeerMap{};
+    }
+    ctx->comm_world = 0;
 }
 
 bool is_pinned_or_managed(const void *p) {
@@ -468,6 +574,7 @@ extern "C" const char *lh_last_error(const lh_ctx *ctx) { return ctx ? ctx->last
 extern "C" lh_status lh_create(const lh_config *cfg, lh_ctx **out) {
     if (!cfg || !out || cfg->struct_size != sizeof(lh_config) || cfg->max_histograms == 0 || cfg->max_counters == 0)
         return LH_ERR_INVALID;
+    if (cfg->precision > LH_MAX_PRECISION) return LH_ERR_RANGE;
     *out = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return LH_ERR_NO_DEVICE; }
@@ -478,8 +585,15 @@ extern "C" lh_status lh_create(const lh_config *cfg, lh_ctx **out) {
     ctx->device = cfg->device;
     ctx->H = cfg->max_histograms;
     ctx->C = cfg->max_counters;
+    ctx->pc = make_prec(cfg->precision ? cfg->precision : 100);
+    {
+        static std::mutex id_mu;
+        static uint64_t next_id = 1;
+        std::lock_guard<std::mutex> lk(id_mu);
+        ctx->ctx_id = next_id++;
+    }
     {   // replicas of the keyed hot window: as many as keep all copies within ~48 MB (L2-resident), at most 32
-        const size_t one = (size_t)ctx->H * LH_SUBHIST * 4u;
+        const size_t one = (size_t)ctx->H * 2u * ctx->pc.win * 4u;
         ctx->hot_replicas = (uint32_t)std::max<size_t>(1, std::min<size_t>(32, ((size_t)48 << 20) / one));
     }
     ctx->staging_bytes = cfg->staging_bytes ? (size_t)cfg->staging_bytes : ((size_t)32 << 20);
@@ -516,24 +630,35 @@ extern "C" lh_status lh_create(const lh_config *cfg, lh_ctx **out) {
         LH_CREATE_CUDA(cudaEventCreate(&ctx->ev_t0s[i]));
         LH_CREATE_CUDA(cudaEventCreate(&ctx->ev_t1s[i]));
     }
+    for (int i = 0; i < lh_ctx::kCommRing; i++) {
+        LH_CREATE_CUDA(cudaEventCreate(&ctx->comm_t0[i]));
+        LH_CREATE_CUDA(cudaEventCreate(&ctx->comm_t1[i]));
+    }
 
     const size_t bucket_bytes = (size_t)ctx->H * 65536u * 8u, counter_bytes = (size_t)ctx->C * 8u;
+    const size_t hot_bytes = (size_t)ctx->hot_replicas * ctx->H * 2u * ctx->pc.win * 4u;
     for (int b = 0; b < 2; b++) {
         LH_CREATE_CUDA(cudaMalloc(&ctx->buf[b].d_buckets, bucket_bytes));
         LH_CREATE_CUDA(cudaMalloc(&ctx->buf[b].d_counters, counter_bytes));
+        LH_CREATE_CUDA(cudaMalloc(&ctx->buf[b].d_flags, (size_t)ctx->H * 4u));
         LH_CREATE_CUDA(cudaMemsetAsync(ctx->buf[b].d_buckets, 0, bucket_bytes, ctx->snap_stream));
         LH_CREATE_CUDA(cudaMemsetAsync(ctx->buf[b].d_counters, 0, counter_bytes, ctx->snap_stream));
-        LH_CREATE_CUDA(cudaMalloc(&ctx->buf[b].d_hot, (size_t)ctx->hot_replicas * ctx->H * LH_SUBHIST * 4u));
-        LH_CREATE_CUDA(cudaMemsetAsync(ctx->buf[b].d_hot, 0, (size_t)ctx->hot_replicas * ctx->H * LH_SUBHIST * 4u, ctx->snap_stream));
+        LH_CREATE_CUDA(cudaMemsetAsync(ctx->buf[b].d_flags, 0, (size_t)ctx->H * 4u, ctx->snap_stream));
+        LH_CREATE_CUDA(cudaMalloc(&ctx->buf[b].d_hot, hot_bytes));
+        LH_CREATE_CUDA(cudaMemsetAsync(ctx->buf[b].d_hot, 0, hot_bytes, ctx->snap_stream));
         LH_CREATE_CUDA(cudaEventCreateWithFlags(&ctx->buf[b].cleared, cudaEventDisableTiming));
         LH_CREATE_CUDA(cudaEventRecord(ctx->buf[b].cleared, ctx->snap_stream));
     }
     LH_CREATE_CUDA(cudaMalloc(&ctx->d_decomp, 65536 * sizeof(double)));
-    k_fill_decompress<<<65536 / 256, 256, 0, ctx->snap_stream>>>(ctx->d_decomp);
+    k_fill_decompress<<<65536 / 256, 256, 0, ctx->snap_stream>>>(ctx->d_decomp, ctx->pc.precision);
     LH_CREATE_CUDA(cudaGetLastError());
+    LH_CREATE_CUDA(cudaMalloc(&ctx->d_comm, kCommWords * 8));
+    LH_CREATE_CUDA(cudaMemsetAsync(ctx->d_comm, 0, kCommWords * 8, ctx->snap_stream));
+    LH_CREATE_CUDA(cudaMalloc(&ctx->d_comm_aux, 16));
+    LH_CREATE_CUDA(cudaMemsetAsync(ctx->d_comm_aux, 0, 16, ctx->snap_stream));
     LH_CREATE_CUDA(cudaMalloc(&ctx->d_dropped, 8));
     LH_CREATE_CUDA(cudaMemsetAsync(ctx->d_dropped, 0, 8, ctx->snap_stream));
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 3; i++) {
         const size_t res_bytes = (size_t)ctx->H * (24 + LH_MAX_PERCENTILES * 12);
         LH_CREATE_CUDA(cudaMalloc(&ctx->d_ps[i], LH_MAX_PERCENTILES * sizeof(double)));
         LH_CREATE_CUDA(cudaMalloc(&ctx->d_res[i], res_bytes));
@@ -545,10 +670,8 @@ extern "C" lh_status lh_create(const lh_config *cfg, lh_ctx **out) {
     LH_CREATE_CUDA(cudaMallocHost(&ctx->h_offsets, ((size_t)ctx->H + 1) * 4));
     LH_CREATE_CUDA(cudaMallocHost(&ctx->h_counter_deltas, counter_bytes));
 
-    ctx->slots.resize(nslots);
+    ctx->slots.resize(nslots);   // pinned + device memory of a slot is allocated the first time it is handed out
     for (auto &sl : ctx->slots) {
-        LH_CREATE_CUDA(cudaMallocHost(&sl.h, ctx->staging_bytes));
-        LH_CREATE_CUDA(cudaMalloc(&sl.d, ctx->staging_bytes));
         LH_CREATE_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
         LH_CREATE_CUDA(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
     }
@@ -557,6 +680,13 @@ extern "C" lh_status lh_create(const lh_config *cfg, lh_ctx **out) {
     LH_CREATE_CUDA(cudaFuncSetAttribute((const void *)k_counter_add_smem<unsigned int, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_COUNTERS * 8));
     for (int i = 0; i < kNumK1Variants; i++) {
         ctx->k1[i] = g_k1_variants[i];
+        const bool probe = ctx->k1[i].launch == launch_probe;
+        ctx->k1[i].smem = probe ? 0 : ctx->k1[i].smem_fixed + ((size_t)2 * ctx->pc.win + 8) * 4;
+        if (ctx->k1[i].smem > kSmemBudget) {   // this shape does not fit at this precision: fall back to the register-pipelined kernel
+            ctx->k1[i] = g_k1_variants[3];
+            ctx->k1[i].name = g_k1_variants[i].name;
+            ctx->k1[i].smem = ((size_t)2 * ctx->pc.win + 8) * 4;
+        }
         LH_CREATE_CUDA(cudaFuncSetAttribute(ctx->k1[i].func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->k1[i].smem));
         int nb = 0;
         LH_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ctx->k1[i].func, ctx->k1[i].threads, ctx->k1[i].smem));
@@ -572,14 +702,21 @@ extern "C" lh_status lh_destroy(lh_ctx *ctx) {
     if (!ctx) return LH_OK;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    comm_unmap(ctx);
+    cudaFree(ctx->d_comm); cudaFree(ctx->d_comm_aux);
+    cudaFree(ctx->d_red_buckets); cudaFree(ctx->d_red_flags); cudaFree(ctx->d_red_counters);
+    for (int i = 0; i < lh_ctx::kCommRing; i++) {
+        if (ctx->comm_t0[i]) cudaEventDestroy(ctx->comm_t0[i]);
+        if (ctx->comm_t1[i]) cudaEventDestroy(ctx->comm_t1[i]);
+    }
     for (int b = 0; b < 2; b++) {
-        cudaFree(ctx->buf[b].d_buckets); cudaFree(ctx->buf[b].d_counters); cudaFree(ctx->buf[b].d_hot);
+        cudaFree(ctx->buf[b].d_buckets); cudaFree(ctx->buf[b].d_counters); cudaFree(ctx->buf[b].d_hot); cudaFree(ctx->buf[b].d_flags);
         if (ctx->buf[b].cleared) cudaEventDestroy(ctx->buf[b].cleared);
         for (auto &w : ctx->buf[b].writers) cudaEventDestroy(w.ev);
     }
     cudaFree(ctx->d_decomp); cudaFree(ctx->d_dropped);
-    cudaFree(ctx->d_kp_queues); cudaFree(ctx->d_kp_tail);
-    for (int i = 0; i < 2; i++) {
+    cudaFree(ctx->d_kp_queues); cudaFree(ctx->d_kp_cnt);
+    for (int i = 0; i < 3; i++) {
         cudaFree(ctx->d_ps[i]); cudaFree(ctx->d_res[i]);
         if (ctx->h_res[i]) cudaFreeHost(ctx->h_res[i]);
         if (ctx->res_done[i]) cudaEventDestroy(ctx->res_done[i]);
@@ -611,7 +748,7 @@ extern "C" lh_status lh_destroy(lh_ctx *ctx) {
 // =========================================================== ingest (device)
 #define LH_ENTER(ctx)                                   \
     if (!(ctx)) return LH_ERR_INVALID;                  \
-    std::lock_guard<std::mutex> _lk((ctx)->mu);         \
+    std::unique_lock<std::mutex> _lk((ctx)->mu);        \
     LH_CUDA((ctx), cudaSetDevice((ctx)->device))
 
 extern "C" lh_status lh_ingest_f64(lh_ctx *ctx, uint32_t hid, const double *d_values, size_t n, void *stream) {
@@ -652,8 +789,8 @@ extern "C" lh_status lh_counter_add_u32(lh_ctx *ctx, const uint32_t *d_ids, cons
 namespace {
 enum HostKind { HK_SINGLE, HK_KEYED_U16, HK_COUNTER_U16 };
 
-lh_status ingest_host(lh_ctx *ctx, HostKind kind, uint32_t hid, const void *h_a /* 8-byte items */,
-                      const uint16_t *h_ids, size_t n) {
+lh_status ingest_host(lh_ctx *ctx, std::unique_lock<std::mutex> &lk, HostKind kind, uint32_t hid,
+                      const void *h_a /* 8-byte items */, const uint16_t *h_ids, size_t n) {
     const bool pinned = is_pinned_or_managed(h_a) && (!h_ids || is_pinned_or_managed(h_ids));
     const size_t item = (kind == HK_SINGLE) ? 8 : 10;
     size_t per = ctx->staging_bytes / item;
@@ -661,47 +798,56 @@ lh_status ingest_host(lh_ctx *ctx, HostKind kind, uint32_t hid, const void *h_a 
     if (per == 0) return fail(ctx, LH_ERR_INVALID, "staging_bytes too small");
     cudaStream_t s = ctx->ingest_stream;
     size_t done = 0;
+    cudaEvent_t last_copied = nullptr;
     while (done < n) {
         size_t m = std::min(per, n - done);
         int si;
-        lh_status st = slot_wait_free(ctx, &si);
+        lh_status st = slot_wait_free(ctx, lk, &si);
         if (st != LH_OK) return st;
         Slot &sl = ctx->slots[si];
         const char *src_a = (const char *)h_a + done * 8;
         char *d_a = (char *)sl.d;
         char *d_i = (char *)sl.d + per * 8;
+        const void *cp_a = src_a;
+        const void *cp_i = h_ids ? (const void *)(h_ids + done) : nullptr;
+        if (!pinned) {
+            // pageable source: stage through the slot's pinned buffer.  The memcpy (milliseconds per 32 MiB) runs with
+            // the context mutex RELEASED -- the slot is parked as ACQUIRED so no other thread can take it.
+            sl.state = SLOT_ACQUIRED;
+            lk.unlock();
+            memcpy(sl.h, src_a, m * 8);
+            if (h_ids) memcpy((char *)sl.h + per * 8, h_ids + done, m * 2);
+            lk.lock();
+            cp_a = sl.h;
+            cp_i = (char *)sl.h + per * 8;
+        }
         // copies run on their own stream so that chunk k+1's DMA overlaps chunk k's kernel; the slot's device
         // buffer is free again once the kernel that read it last is done (slot_wait_free already waited on the host
         // for a recycled slot, the event wait covers the rest)
         cudaStream_t cs = ctx->copy_stream;
         if (sl.seq) LH_CUDA(ctx, cudaStreamWaitEvent(cs, sl.done, 0));
-        if (pinned) {
-            LH_CUDA(ctx, cudaMemcpyAsync(d_a, src_a, m * 8, cudaMemcpyHostToDevice, cs));
-            if (h_ids) LH_CUDA(ctx, cudaMemcpyAsync(d_i, h_ids + done, m * 2, cudaMemcpyHostToDevice, cs));
-        } else {
-            memcpy(sl.h, src_a, m * 8);
-            LH_CUDA(ctx, cudaMemcpyAsync(d_a, sl.h, m * 8, cudaMemcpyHostToDevice, cs));
-            if (h_ids) {
-                memcpy((char *)sl.h + per * 8, h_ids + done, m * 2);
-                LH_CUDA(ctx, cudaMemcpyAsync(d_i, (char *)sl.h + per * 8, m * 2, cudaMemcpyHostToDevice, cs));
-            }
-        }
+        LH_CUDA(ctx, cudaMemcpyAsync(d_a, cp_a, m * 8, cudaMemcpyHostToDevice, cs));
+        if (h_ids) LH_CUDA(ctx, cudaMemcpyAsync(d_i, cp_i, m * 2, cudaMemcpyHostToDevice, cs));
         LH_CUDA(ctx, cudaEventRecord(sl.copied, cs));
         LH_CUDA(ctx, cudaStreamWaitEvent(s, sl.copied, 0));
+        last_copied = sl.copied;
         ctx->stats.h2d_bytes += m * item;
         if (kind == HK_SINGLE) st = launch_single(ctx, hid, (const double *)d_a, m, s);
         else if (kind == HK_KEYED_U16) st = launch_keyed<unsigned short, double>(ctx, (const unsigned short *)d_i, (const double *)d_a, m, s);
         else st = launch_counter<unsigned short>(ctx, (const unsigned short *)d_i, (const uint64_t *)d_a, m, s);
-        if (st != LH_OK) return st;
+        if (st != LH_OK) { sl.state = SLOT_FREE; return st; }
         LH_CUDA(ctx, cudaEventRecord(sl.done, s));
         sl.state = SLOT_INFLIGHT;
         sl.seq = ++ctx->slot_seq;
         done += m;
     }
-    if (pinned) {
-        // the caller may reuse its buffers on return: the async copies must have read them
-        LH_CUDA(ctx, cudaStreamSynchronize(s));
-        for (auto &sl : ctx->slots) if (sl.state == SLOT_INFLIGHT) sl.state = SLOT_FREE;
+    if (pinned && last_copied) {
+        // the caller may reuse its buffers on return: the async copies must have READ them (the kernels may still run);
+        // waited for with the mutex released
+        lk.unlock();
+        cudaError_t e = cudaEventSynchronize(last_copied);
+        lk.lock();
+        if (e != cudaSuccess) return fail(ctx, LH_ERR_CUDA, "cudaEventSynchronize(copied)", e);
     }
     return LH_OK;
 }
@@ -711,17 +857,17 @@ extern "C" lh_status lh_ingest_f64_host(lh_ctx *ctx, uint32_t hid, const double 
     LH_ENTER(ctx);
     if (n && !h_values) return fail(ctx, LH_ERR_INVALID, "h_values is NULL");
     if (hid >= ctx->H) return fail(ctx, LH_ERR_RANGE, "histogram_id >= max_histograms");
-    return ingest_host(ctx, HK_SINGLE, hid, h_values, nullptr, n);
+    return ingest_host(ctx, _lk, HK_SINGLE, hid, h_values, nullptr, n);
 }
 extern "C" lh_status lh_ingest_keyed_f64_u16_host(lh_ctx *ctx, const uint16_t *h_ids, const double *h_values, size_t n) {
     LH_ENTER(ctx);
     if (n && (!h_ids || !h_values)) return fail(ctx, LH_ERR_INVALID, "NULL input");
-    return ingest_host(ctx, HK_KEYED_U16, 0, h_values, h_ids, n);
+    return ingest_host(ctx, _lk, HK_KEYED_U16, 0, h_values, h_ids, n);
 }
 extern "C" lh_status lh_counter_add_u16_host(lh_ctx *ctx, const uint16_t *h_ids, const uint64_t *h_amounts, size_t n) {
     LH_ENTER(ctx);
     if (n && (!h_ids || !h_amounts)) return fail(ctx, LH_ERR_INVALID, "NULL input");
-    return ingest_host(ctx, HK_COUNTER_U16, 0, h_amounts, h_ids, n);
+    return ingest_host(ctx, _lk, HK_COUNTER_U16, 0, h_amounts, h_ids, n);
 }
 
 // Merge sparse bucket counts held in host memory (e.g. another process's lh_snapshot_export) into the ACTIVE arrays.
@@ -742,7 +888,7 @@ extern "C" lh_status lh_merge_counts_host(lh_ctx *ctx, const uint32_t *h_ids, co
     if (e == cudaSuccess) {
         int grid = grid_1d(ctx, n, 256, 1, 8);
         k_merge_sparse<<<grid, 256, 0, s>>>((const uint32_t *)d, (const short *)(d + off_keys), (const unsigned long long *)(d + off_counts),
-                                            n, ctx->H, ctx->buf[b].d_buckets, ctx->d_dropped);
+                                            n, ctx->H, ctx->buf[b].d_buckets, ctx->buf[b].d_flags, ctx->d_dropped, ctx->pc.win);
         e = cudaGetLastError();
     }
     cudaFreeAsync(d, s);
@@ -758,7 +904,7 @@ extern "C" lh_status lh_staging_acquire(lh_ctx *ctx, lh_staging *out) {
     LH_ENTER(ctx);
     if (!out) return fail(ctx, LH_ERR_INVALID, "out is NULL");
     int si;
-    lh_status st = slot_wait_free(ctx, &si);
+    lh_status st = slot_wait_free(ctx, _lk, &si);
     if (st != LH_OK) return st;
     ctx->slots[si].state = SLOT_ACQUIRED;
     out->host = ctx->slots[si].h;
@@ -839,6 +985,8 @@ extern "C" lh_status lh_snapshot_begin(lh_ctx *ctx) {
     ctx->active ^= 1;
     ctx->frozen = true;
     ctx->nnz_valid = false;
+    ctx->view_reduced = false;
+    ctx->view_counters_reduced = false;
     ctx->stats.snapshots++;
     return LH_OK;
 }
@@ -853,6 +1001,8 @@ extern "C" lh_status lh_snapshot_device(lh_ctx *ctx, lh_device_view *out) {
     out->n_bucket_words = (uint64_t)ctx->H * 65536u;
     out->n_counter_words = ctx->C;
     out->stream = ctx->snap_stream;
+    out->d_flags = ctx->buf[f].d_flags;
+    out->n_flag_words = ctx->H;
     return LH_OK;
 }
 
@@ -865,16 +1015,28 @@ ResLayout res_layout(size_t H, uint32_t np) {
     return l;
 }
 
+// the arrays the open snapshot's reduction / export read: this rank's frozen buffer, or the sums over all ranks
+// once lh_snapshot_allreduce has run
+struct View { const unsigned long long *buckets; const uint32_t *flags; const unsigned long long *counters; };
+View snapshot_view(lh_ctx *ctx) {
+    const int f = ctx->active ^ 1;
+    View v;
+    v.buckets = ctx->view_reduced ? ctx->d_red_buckets : ctx->buf[f].d_buckets;
+    v.flags = ctx->view_reduced ? ctx->d_red_flags : ctx->buf[f].d_flags;
+    v.counters = ctx->view_counters_reduced ? ctx->d_red_counters : ctx->buf[f].d_counters;
+    return v;
+}
+
 // enqueue K3 + one packed D2H for the open snapshot into result slot `slot`
 lh_status enqueue_reduce(lh_ctx *ctx, const double *ps, uint32_t np, int slot) {
-    const int f = ctx->active ^ 1;
     cudaStream_t s = ctx->snap_stream;
     const ResLayout l = res_layout(ctx->H, np);
+    const View v = snapshot_view(ctx);
     if (np) {
         LH_CUDA(ctx, cudaMemcpyAsync(ctx->d_ps[slot], ps, np * sizeof(double), cudaMemcpyHostToDevice, s));
     }
     char *d = ctx->d_res[slot];
-    k_reduce<<<ctx->H, K3_THREADS, 0, s>>>(ctx->buf[f].d_buckets, ctx->d_decomp, ctx->d_ps[slot], (int)np,
+    k_reduce<<<ctx->H, K3_THREADS, 0, s>>>(v.buckets, v.flags, ctx->pc.win, ctx->d_decomp, ctx->d_ps[slot], (int)np,
                                            (unsigned long long *)(d + l.count), (double *)(d + l.sum), (double *)(d + l.avg),
                                            (int *)(d + l.pkeys), (double *)(d + l.pvals), ctx->d_nnz);
     LH_CUDA(ctx, cudaGetLastError());
@@ -896,7 +1058,15 @@ extern "C" lh_status lh_snapshot_reduce_async(lh_ctx *ctx, const double *percent
     const uint64_t t = ctx->next_ticket++;
     const int slot = (int)(t & 1);
     // the slot's previous results (ticket t-2) are overwritten: make sure its copy is not still in flight
-    if (ctx->res_ticket[slot]) LH_CUDA(ctx, cudaEventSynchronize(ctx->res_done[slot]));
+    // (waited for with the mutex released: ingest threads are not held up)
+    if (ctx->res_ticket[slot]) {
+        cudaEvent_t ev = ctx->res_done[slot];
+        _lk.unlock();
+        cudaError_t e = cudaEventSynchronize(ev);
+        _lk.lock();
+        if (e != cudaSuccess) return fail(ctx, LH_ERR_CUDA, "cudaEventSynchronize(result slot)", e);
+        if (!ctx->frozen) return fail(ctx, LH_ERR_STATE, "snapshot ended while waiting");
+    }
     lh_status st = enqueue_reduce(ctx, percentiles, np, slot);
     if (st != LH_OK) return st;
     ctx->res_ticket[slot] = t;
@@ -943,20 +1113,18 @@ extern "C" lh_status lh_snapshot_export(lh_ctx *ctx, lh_sparse *out) {
     LH_ENTER(ctx);
     if (!out) return fail(ctx, LH_ERR_INVALID, "out is NULL");
     if (!ctx->frozen) return fail(ctx, LH_ERR_STATE, "no snapshot in progress");
-    const int f = ctx->active ^ 1;
     cudaStream_t s = ctx->snap_stream;
-    if (!ctx->nnz_valid) {   // non-empty bucket counts come out of K3; run it with no percentiles if nobody has yet
-        const uint64_t t = ctx->next_ticket++;
-        const int slot = (int)(t & 1);
-        if (ctx->res_ticket[slot]) LH_CUDA(ctx, cudaEventSynchronize(ctx->res_done[slot]));
-        lh_status st = enqueue_reduce(ctx, nullptr, 0, slot);
+    const View v = snapshot_view(ctx);
+    if (!ctx->nnz_valid) {
+        // non-empty bucket counts come out of K3: run it with no percentiles into the scratch result slot, which never
+        // carries a ticket (outstanding lh_snapshot_reduce_async tickets keep their documented lifetime)
+        lh_status st = enqueue_reduce(ctx, nullptr, 0, 2);
         if (st != LH_OK) return st;
-        ctx->res_ticket[slot] = t;
     }
     k_scan_nnz<<<1, 1024, 0, s>>>(ctx->d_nnz, ctx->H, ctx->d_offsets);
     LH_CUDA(ctx, cudaGetLastError());
     LH_CUDA(ctx, cudaMemcpyAsync(ctx->h_offsets, ctx->d_offsets, ((size_t)ctx->H + 1) * 4, cudaMemcpyDeviceToHost, s));
-    LH_CUDA(ctx, cudaMemcpyAsync(ctx->h_counter_deltas, ctx->buf[f].d_counters, (size_t)ctx->C * 8, cudaMemcpyDeviceToHost, s));
+    LH_CUDA(ctx, cudaMemcpyAsync(ctx->h_counter_deltas, v.counters, (size_t)ctx->C * 8, cudaMemcpyDeviceToHost, s));
     LH_CUDA(ctx, cudaStreamSynchronize(s));
     const size_t total = ctx->h_offsets[ctx->H];
     if (total > ctx->x_cap) {
@@ -972,7 +1140,7 @@ extern "C" lh_status lh_snapshot_export(lh_ctx *ctx, lh_sparse *out) {
         ctx->x_cap = cap;
     }
     if (total) {
-        k_export<<<ctx->H, K3_THREADS, 0, s>>>(ctx->buf[f].d_buckets, ctx->d_offsets, ctx->d_x_keys, ctx->d_x_counts);
+        k_export<<<ctx->H, K3_THREADS, 0, s>>>(v.buckets, v.flags, ctx->pc.win, ctx->d_offsets, ctx->d_x_keys, ctx->d_x_counts);
         LH_CUDA(ctx, cudaGetLastError());
         ctx->stats.kernel_launches += 2;
         LH_CUDA(ctx, cudaMemcpyAsync(ctx->h_x_keys, ctx->d_x_keys, total * 2, cudaMemcpyDeviceToHost, s));
@@ -993,8 +1161,8 @@ extern "C" lh_status lh_snapshot_copy_histogram(lh_ctx *ctx, uint32_t hid, uint6
     if (!ctx->frozen) return fail(ctx, LH_ERR_STATE, "no snapshot in progress");
     if (hid >= ctx->H) return fail(ctx, LH_ERR_RANGE, "histogram_id >= max_histograms");
     if (!h_out) return fail(ctx, LH_ERR_INVALID, "h_out is NULL");
-    const int f = ctx->active ^ 1;
-    LH_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->buf[f].d_buckets + (size_t)hid * 65536u, 65536 * 8, cudaMemcpyDeviceToHost, ctx->snap_stream));
+    const View v = snapshot_view(ctx);
+    LH_CUDA(ctx, cudaMemcpyAsync(h_out, v.buckets + (size_t)hid * 65536u, 65536 * 8, cudaMemcpyDeviceToHost, ctx->snap_stream));
     LH_CUDA(ctx, cudaStreamSynchronize(ctx->snap_stream));
     ctx->stats.d2h_bytes += 65536 * 8;
     return LH_OK;
@@ -1004,12 +1172,181 @@ extern "C" lh_status lh_snapshot_end(lh_ctx *ctx) {
     LH_ENTER(ctx);
     if (!ctx->frozen) return fail(ctx, LH_ERR_STATE, "no snapshot in progress");
     const int f = ctx->active ^ 1;
-    LH_CUDA(ctx, cudaMemsetAsync(ctx->buf[f].d_buckets, 0, (size_t)ctx->H * 65536u * 8u, ctx->snap_stream));
-    LH_CUDA(ctx, cudaMemsetAsync(ctx->buf[f].d_counters, 0, (size_t)ctx->C * 8u, ctx->snap_stream));
-    LH_CUDA(ctx, cudaEventRecord(ctx->buf[f].cleared, ctx->snap_stream));
+    cudaStream_t s = ctx->snap_stream;
+    // zero only what the interval touched (flags), not the whole uint64[H][65536] array
+    k_clear_touched<<<ctx->H, 256, 0, s>>>(ctx->buf[f].d_buckets, ctx->buf[f].d_flags, ctx->pc.win);
+    LH_CUDA(ctx, cudaGetLastError());
+    if (ctx->view_reduced) {
+        k_clear_touched<<<ctx->H, 256, 0, s>>>(ctx->d_red_buckets, ctx->d_red_flags, ctx->pc.win);
+        LH_CUDA(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches++;
+    }
+    ctx->stats.kernel_launches++;
+    LH_CUDA(ctx, cudaMemsetAsync(ctx->buf[f].d_counters, 0, (size_t)ctx->C * 8u, s));
+    LH_CUDA(ctx, cudaEventRecord(ctx->buf[f].cleared, s));
     ctx->frozen = false;
+    ctx->view_reduced = false;
+    ctx->view_counters_reduced = false;
     return LH_OK;
 }
+
+// =========================================================== multi-GPU (peer memory)
+extern "C" lh_status lh_comm_export(lh_ctx *ctx, lh_peer_handle *out) {
+    LH_ENTER(ctx);
+    if (!out) return fail(ctx, LH_ERR_INVALID, "out is NULL");
+    PeerWire w{};
+    w.magic = kPeerMagic; w.abi = LH_ABI_VERSION; w.H = ctx->H; w.C = ctx->C;
+    w.precision = (uint32_t)ctx->pc.precision; w.device = (uint32_t)ctx->device;
+    w.pid = (int64_t)getpid(); w.ctx_id = ctx->ctx_id;
+    for (int b = 0; b < 2; b++) {
+        w.ptr_buckets[b] = (uint64_t)(uintptr_t)ctx->buf[b].d_buckets;
+        w.ptr_flags[b] = (uint64_t)(uintptr_t)ctx->buf[b].d_flags;
+        w.ptr_counters[b] = (uint64_t)(uintptr_t)ctx->buf[b].d_counters;
+        LH_CUDA(ctx, cudaIpcGetMemHandle(&w.ipc_buckets[b], ctx->buf[b].d_buckets));
+        LH_CUDA(ctx, cudaIpcGetMemHandle(&w.ipc_flags[b], ctx->buf[b].d_flags));
+        LH_CUDA(ctx, cudaIpcGetMemHandle(&w.ipc_counters[b], ctx->buf[b].d_counters));
+    }
+    w.ptr_comm = (uint64_t)(uintptr_t)ctx->d_comm;
+    LH_CUDA(ctx, cudaIpcGetMemHandle(&w.ipc_comm, ctx->d_comm));
+    memset(out, 0, sizeof *out);
+    memcpy(out->bytes, &w, sizeof w);
+    return LH_OK;
+}
+
+extern "C" lh_status lh_comm_import(lh_ctx *ctx, uint32_t rank, uint32_t world, const lh_peer_handle *all) {
+    LH_ENTER(ctx);
+    if (!all || world < 1 || world > (uint32_t)kMaxRanks || rank >= world) return fail(ctx, LH_ERR_INVALID, "bad rank / world / handles");
+    if (ctx->frozen) return fail(ctx, LH_ERR_STATE, "lh_comm_import during a snapshot");
+    comm_unmap(ctx);
+    const int64_t my_pid = (int64_t)getpid();
+    for (uint32_t r = 0; r < world; r++) {
+        PeerWire w;
+        memcpy(&w, all[r].bytes, sizeof w);
+        if (w.magic != kPeerMagic || w.abi != LH_ABI_VERSION) return fail(ctx, LH_ERR_INVALID, "peer handle is not from this library version");
+        if (w.H != ctx->H || w.C != ctx->C || w.precision != (uint32_t)ctx->pc.precision)
+            return fail(ctx, LH_ERR_INVALID, "peer context has a different shape (max_histograms / max_counters / precision)");
+        PeerMap &pm = ctx->peers[r];
+        if (r == rank) {
+            if (w.ctx_id != ctx->ctx_id || w.pid != my_pid) return fail(ctx, LH_ERR_INVALID, "handles[rank] is not this context's own handle");
+            for (int b = 0; b < 2; b++) { pm.buckets[b] = ctx->buf[b].d_buckets; pm.flags[b] = ctx->buf[b].d_flags; pm.counters[b] = ctx->buf[b].d_counters; }
+            pm.comm = ctx->d_comm;
+            continue;
+        }
+        if (w.pid == my_pid) {
+            // same process (one thread per GPU): plain peer access on the raw pointers
+            if ((int)w.device != ctx->device) {
+                int can = 0;
+                LH_CUDA(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, (int)w.device));
+                if (!can) return fail(ctx, LH_ERR_NO_DEVICE, "no peer access between the two devices");
+                cudaError_t e = cudaDeviceEnablePeerAccess((int)w.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, LH_ERR_CUDA, "cudaDeviceEnablePeerAccess", e);
+                cudaGetLastError();
+            }
+            for (int b = 0; b < 2; b++) {
+                pm.buckets[b] = (unsigned long long *)(uintptr_t)w.ptr_buckets[b];
+                pm.flags[b] = (uint32_t *)(uintptr_t)w.ptr_flags[b];
+                pm.counters[b] = (unsigned long long *)(uintptr_t)w.ptr_counters[b];
+            }
+            pm.comm = (unsigned long long *)(uintptr_t)w.ptr_comm;
+        } else {
+            // another process on this node: CUDA IPC mappings (NVLink peer-to-peer underneath)
+            pm.ipc = true;
+            for (int b = 0; b < 2; b++) {
+                LH_CUDA(ctx, cudaIpcOpenMemHandle((void **)&pm.buckets[b], w.ipc_buckets[b], cudaIpcMemLazyEnablePeerAccess));
+                LH_CUDA(ctx, cudaIpcOpenMemHandle((void **)&pm.flags[b], w.ipc_flags[b], cudaIpcMemLazyEnablePeerAccess));
+                LH_CUDA(ctx, cudaIpcOpenMemHandle((void **)&pm.counters[b], w.ipc_counters[b], cudaIpcMemLazyEnablePeerAccess));
+            }
+            LH_CUDA(ctx, cudaIpcOpenMemHandle((void **)&pm.comm, w.ipc_comm, cudaIpcMemLazyEnablePeerAccess));
+        }
+    }
+    if (!ctx->d_red_buckets) {
+        const size_t bucket_bytes = (size_t)ctx->H * 65536u * 8u;
+        LH_CUDA(ctx, cudaMalloc(&ctx->d_red_buckets, bucket_bytes));
+        LH_CUDA(ctx, cudaMalloc(&ctx->d_red_flags, (size_t)ctx->H * 4));
+        LH_CUDA(ctx, cudaMalloc(&ctx->d_red_counters, (size_t)ctx->C * 8));
+        LH_CUDA(ctx, cudaMemsetAsync(ctx->d_red_buckets, 0, bucket_bytes, ctx->snap_stream));
+        LH_CUDA(ctx, cudaMemsetAsync(ctx->d_red_flags, 0, (size_t)ctx->H * 4, ctx->snap_stream));
+        LH_CUDA(ctx, cudaMemsetAsync(ctx->d_red_counters, 0, (size_t)ctx->C * 8, ctx->snap_stream));
+        LH_CUDA(ctx, cudaStreamSynchronize(ctx->snap_stream));
+    }
+    ctx->comm_rank = rank;
+    ctx->comm_world = world;
+    return LH_OK;
+}
+
+extern "C" lh_status lh_snapshot_allreduce(lh_ctx *ctx, uint32_t include_counters, uint64_t *seq_out) {
+    LH_ENTER(ctx);
+    if (!ctx->frozen) return fail(ctx, LH_ERR_STATE, "no snapshot in progress");
+    if (ctx->comm_world < 2) return fail(ctx, LH_ERR_STATE, "lh_comm_import has not been called with world >= 2");
+    if (ctx->view_reduced) return fail(ctx, LH_ERR_STATE, "this snapshot has already been all-reduced");
+    const int f = ctx->active ^ 1;
+    cudaStream_t s = ctx->snap_stream;
+    PeerParams p{};
+    p.rank = ctx->comm_rank; p.world = ctx->comm_world; p.H = ctx->H; p.C = ctx->C; p.win = ctx->pc.win;
+    p.do_counters = include_counters ? 1u : 0u; p.frozen = (uint32_t)f;
+    p.seq = ++ctx->comm_seq;
+    p.timeout_ns = 10ull * 1000ull * 1000ull * 1000ull;
+    for (uint32_t r = 0; r < ctx->comm_world; r++) {
+        p.buckets[r] = ctx->peers[r].buckets[f];
+        p.flags[r] = ctx->peers[r].flags[f];
+        p.counters[r] = ctx->peers[r].counters[f];
+        p.comm[r] = ctx->peers[r].comm;
+    }
+    p.out_buckets = ctx->d_red_buckets; p.out_flags = ctx->d_red_flags; p.out_counters = ctx->d_red_counters;
+    p.block_counter = ctx->d_comm_aux; p.status = ctx->d_comm_aux + 1;
+    p.cells = reinterpret_cast<unsigned long long *>(ctx->d_comm_aux + 2);
+    LH_CUDA(ctx, cudaMemsetAsync(ctx->d_comm_aux + 2, 0, 8, s));
+    const int ring = (int)(p.seq % lh_ctx::kCommRing);
+    // a few CTAs: the kernel shares the GPU with the next interval's ingest (which leaves k1_reserve_sms SMs free)
+    const size_t items = (size_t)ctx->H * (65536u / K5_CHUNK);
+    const int grid = (int)std::min<size_t>(items, ctx->H == 1 ? 5 : 32);
+    LH_CUDA(ctx, cudaEventRecord(ctx->comm_t0[ring], s));
+    k_peer_allreduce<<<grid, K5_THREADS, 0, s>>>(p);
+    LH_CUDA(ctx, cudaGetLastError());
+    LH_CUDA(ctx, cudaEventRecord(ctx->comm_t1[ring], s));
+    ctx->stats.kernel_launches++;
+    ctx->view_reduced = true;
+    ctx->view_counters_reduced = include_counters != 0;
+    ctx->nnz_valid = false;
+    if (seq_out) *seq_out = p.seq;
+    return LH_OK;
+}
+
+extern "C" lh_status lh_comm_allreduce_ms(lh_ctx *ctx, uint64_t seq, float *ms) {
+    if (!ctx || !ms) return LH_ERR_INVALID;
+    cudaEvent_t e0, e1;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (seq == 0 || seq > ctx->comm_seq || ctx->comm_seq - seq >= (uint64_t)lh_ctx::kCommRing)
+            return fail(ctx, LH_ERR_STATE, "that all-reduce is unknown or its events were recycled");
+        const int ring = (int)(seq % lh_ctx::kCommRing);
+        e0 = ctx->comm_t0[ring]; e1 = ctx->comm_t1[ring];
+    }
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(ms, e0, e1);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (e != cudaSuccess) return fail(ctx, LH_ERR_CUDA, "lh_comm_allreduce_ms", e);
+    return LH_OK;
+}
+
+extern "C" lh_status lh_comm_info(lh_ctx *ctx, lh_comm_stats *out) {
+    LH_ENTER(ctx);
+    if (!out) return fail(ctx, LH_ERR_INVALID, "out is NULL");
+    memset(out, 0, sizeof *out);
+    out->rank = ctx->comm_rank; out->world = ctx->comm_world; out->allreduces = ctx->comm_seq;
+    if (ctx->comm_world >= 2) {
+        unsigned int aux[2] = {0, 0};
+        LH_CUDA(ctx, cudaMemcpy(aux, ctx->d_comm_aux, 8, cudaMemcpyDeviceToHost));
+        out->status = aux[1];
+        // bytes this rank read from its peers in the last all-reduce: window (or dense) cells of every touched histogram
+        unsigned long long cells = 0;
+        LH_CUDA(ctx, cudaMemcpy(&cells, ctx->d_comm_aux + 2, 8, cudaMemcpyDeviceToHost));
+        out->last_bytes_from_peers = cells * 8u * (ctx->comm_world - 1);
+    }
+    return LH_OK;
+}
+
+extern "C" const char *lh_keyed_kernel_name(lh_ctx *ctx) { return ctx ? ctx->keyed_kernel : ""; }
 
 // =========================================================== probes
 extern "C" lh_status lh_compress_f64(lh_ctx *ctx, const double *d_values, size_t n, int16_t *d_out, int mode, void *stream) {
@@ -1017,7 +1354,7 @@ extern "C" lh_status lh_compress_f64(lh_ctx *ctx, const double *d_values, size_t
     if (n && (!d_values || !d_out)) return fail(ctx, LH_ERR_INVALID, "NULL input");
     if (!n) return LH_OK;
     cudaStream_t s = pick_stream(ctx, stream);
-    k_compress_probe<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_values, n, d_out, mode);
+    k_compress_probe<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_values, n, d_out, mode, ctx->pc);
     LH_CUDA(ctx, cudaGetLastError());
     return LH_OK;
 }
@@ -1036,7 +1373,7 @@ extern "C" lh_status lh_fastpath_margin(lh_ctx *ctx, const double *d_values, siz
     unsigned long long *d = nullptr;
     LH_CUDA(ctx, cudaMalloc(&d, 24));
     LH_CUDA(ctx, cudaMemsetAsync(d, 0, 24, s));
-    if (n) k_fastpath_margin<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_values, n, d);
+    if (n) k_fastpath_margin<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_values, n, d, ctx->pc);
     unsigned long long h[3];
     cudaError_t e = cudaMemcpyAsync(h, d, 24, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
@@ -1089,8 +1426,20 @@ extern "C" lh_status lh_get_stats(lh_ctx *ctx, lh_stats *out) {
 }
 extern "C" lh_status lh_sync(lh_ctx *ctx) {
     LH_ENTER(ctx);
-    LH_CUDA(ctx, cudaDeviceSynchronize());
-    for (auto &sl : ctx->slots) if (sl.state == SLOT_INFLIGHT) sl.state = SLOT_FREE;
+    // this context's work only (its three streams and every caller stream that carried an ingest), not the whole
+    // device: another context on the same GPU may be inside a collective that waits for THIS caller's next step
+    std::vector<cudaStream_t> streams = {ctx->ingest_stream, ctx->copy_stream, ctx->snap_stream};
+    for (int b = 0; b < 2; b++)
+        for (auto &w : ctx->buf[b].writers)
+            if (std::find(streams.begin(), streams.end(), w.stream) == streams.end()) streams.push_back(w.stream);
+    _lk.unlock();
+    cudaError_t e = cudaSuccess;
+    for (cudaStream_t st : streams) { cudaError_t x = cudaStreamSynchronize(st); if (e == cudaSuccess) e = x; }
+    _lk.lock();
+    if (e != cudaSuccess) return fail(ctx, LH_ERR_CUDA, "lh_sync", e);
+    for (auto &sl : ctx->slots)
+        if (sl.state == SLOT_INFLIGHT && cudaEventQuery(sl.done) == cudaSuccess) sl.state = SLOT_FREE;
+    cudaGetLastError();
     return LH_OK;
 }
 extern "C" void *lh_ingest_stream(lh_ctx *ctx) { return ctx ? (void *)ctx->ingest_stream : nullptr; }
@@ -1149,13 +1498,13 @@ extern "C" lh_status lh_tune(lh_ctx *ctx, const char *key, int64_t value) {
         return LH_OK;
     }
     if (!strcmp(key, "keyed_mode")) {
-        if (value < 0 || value > 2) return fail(ctx, LH_ERR_RANGE, "keyed_mode is 0 (auto), 1 (L2 atomics) or 2 (owner-partitioned)");
+        if (value < 0 || value > 2) return fail(ctx, LH_ERR_RANGE, "keyed_mode is 0 (auto), 1 (L2 atomics) or 2 (owner-partitioned, write-combining)");
         ctx->keyed_mode = (int)value;
         return LH_OK;
     }
-    if (!strcmp(key, "kp_shape")) {
-        if (value < 0 || value > 1) return fail(ctx, LH_ERR_RANGE, "kp_shape is 0 or 1");
-        ctx->kp_shape = (int)value;
+    if (!strcmp(key, "wc_spt")) {
+        if (value != 8 && value != 16) return fail(ctx, LH_ERR_RANGE, "wc_spt is 8 or 16");
+        ctx->wc_spt = (int)value;
         return LH_OK;
     }
     if (!strcmp(key, "kp_chunk")) {

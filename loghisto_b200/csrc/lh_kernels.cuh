@@ -3,21 +3,29 @@
 //   K1   k_ingest_single_*  one histogram, float64 stream -> bucket counts
 //                           (compress + Histogram increment, metrics.go:273-295, 316-322)
 //          _bulk  : cp.async.bulk (TMA 1-D, UBLKCP) into a shared-memory ring guarded by mbarriers, one producer
-//                   warp + N consumer warps; with V2 = packed-FP32 bucket arithmetic this is the shipped default
-//          _ldg   : 256-bit ld.global.nc loads, software-pipelined in registers (first version)
-//          _v2/_v3: register-only variants of the lean arithmetic (kept for the comparison in profiles/)
-//        all privatise the histogram in shared memory (uint32 sub-histograms, ATOMS.POPC.INC) and flush once per
+//                   warp + N consumer warps, packed-FP32 bucket arithmetic: the shipped default
+//          _ldg   : 256-bit ld.global.nc loads, software-pipelined in registers, scalar fast_candidate() (first version;
+//                   kept as the second, independently written evaluator the parity tests run against the oracle)
+//        both privatise the histogram in shared memory (uint32 sub-histograms, ATOMS.POPC.INC) and flush once per
 //        CTA with one global 64-bit atomic per non-empty bucket.
-//   K1k  k_ingest_keyed_small   (id,value) pairs, <= 11 ids per pass privatised in shared memory (HBM-bound)
+//   K1k  k_ingest_keyed_small   (id,value) pairs, as many ids per pass as fit privatised in shared memory (HBM-bound)
 //        k_ingest_keyed_vec     any number of ids: one L2 RED per sample into a compact, replicated uint32 window
-//        k_ingest_keyed_part    owner-partitioned cooperative kernel (opt-in experiment)
+//        k_ingest_keyed_wc      owner-partitioned, write-combining cooperative kernel (many histograms)
 //        k_ingest_keyed         scalar fallback for ragged / misaligned pieces;  k_fold_hot drains the window
 //   K2   k_counter_add{_smem}   (id,amount) pairs -> counters[id]        (metrics.go:251-269)
 //   K3   k_reduce               per histogram: count, sum, avg, percentiles (processHistograms + percentile,
 //                               metrics.go:336-418)
 //   K4   k_scan_nnz, k_export   sparse (key,count) lists (RawMetricSet.Histograms);  k_merge_sparse is the inverse
-//   misc k_fill_decompress, k_compress_probe, k_fastpath_margin, k_stream_probe, k_gen_stream, k_gen_ids_u16
+//   K5   k_peer_allreduce       multi-GPU: sums the live window of every peer's frozen arrays over NVLink peer
+//                               mappings -- no library collective
+//   misc k_clear_touched, k_fill_decompress, k_compress_probe, k_fastpath_margin, k_stream_probe, k_gen_stream,
+//        k_gen_ids_u16
+//
+// Per-histogram flags (uint32[H], one array per bucket buffer): 0 = untouched since the buffer was cleared,
+// 1 = counts inside the fast window only, 3 = some count outside it.  Every kernel that adds into the uint64
+// arrays raises them; the snapshot kernels (reduce, export, clear, all-reduce) scan only what they cover.
 #pragma once
+#include "../../include/loghisto_b200.h"
 #include "lh_device.cuh"
 
 namespace lh {
@@ -77,27 +85,78 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
     return p;
 }
 
-// One sample -> shared sub-histogram slot.  Samples outside the window are
-// counted straight into the global array and redirected to a trash slot so
-// the shared atomic below stays unconditional.
-constexpr uint32_t LH_TRASH = LH_SUBHIST;          // slot never flushed
-constexpr uint32_t LH_SUBHIST_ALLOC = LH_SUBHIST + 8;
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void red_add_u32_keep(unsigned int *addr, unsigned int v, uint64_t policy) {
+    asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(addr), "r"(v), "l"(policy) : "memory");
+}
 
+// ---------------------------------------------------------------- flags
+// level 1 = the histogram has counts inside the fast window, 3 = also outside it.  Plain read first: the flag is
+// almost always already set, and same-address atomics from every thread would serialise in L2.
+__device__ __forceinline__ void mark(uint32_t *flag, uint32_t level) {
+    if ((*reinterpret_cast<volatile uint32_t *>(flag) & level) != level) atomicOr(flag, level);
+}
+// One count (or c of them) straight into the uint64 row of a histogram, raising its flag.
+__device__ __forceinline__ void add_bucket_global(unsigned long long *__restrict__ row, uint32_t *flag, uint32_t key16,
+                                                  unsigned long long c, uint32_t win) {
+    atomicAdd(&row[key16], c);
+    mark(flag, key16_in_window(key16, win) ? 1u : 3u);
+}
+
+// Shared sub-histogram of one histogram: [0, 2*win) slots + one trash slot that is never flushed (samples
+// outside the window are counted straight into the global array and redirected there so that the shared atomic
+// stays unconditional).
+__device__ __forceinline__ uint32_t subhist_words(uint32_t win) { return 2u * win + 8u; }
+
+// Flush: one 64-bit global atomic per non-empty slot, then one flag update per CTA.
+__device__ __forceinline__ void flush_subhist(const uint32_t *hist, int tid, int nthreads,
+                                              unsigned long long *__restrict__ counts, uint32_t *flag, uint32_t win) {
+    int any = 0;
+    for (uint32_t slot = tid; slot < 2u * win; slot += nthreads) {
+        const uint32_t c = hist[slot];
+        if (c) { atomicAdd(&counts[slot_to_key16(slot, win)], (unsigned long long)c); any = 1; }
+    }
+    any = __syncthreads_or(any);
+    if (any && tid == 0) mark(flag, 1u);
+}
+
+// Exact slot of one sample for the fix-up paths; out-of-window keys are counted globally and sent to the trash slot.
+__device__ __forceinline__ uint32_t fixup_slot(double v, const Prec &pc, unsigned long long *__restrict__ counts,
+                                               uint32_t *flag) {
+    const uint32_t key = key16_of(v, pc);
+    uint32_t slot = key16_to_slot(key, pc.win);
+    if (slot == 0xFFFFFFFFu) { add_bucket_global(counts, flag, key, 1ull, pc.win); slot = 2u * pc.win; }
+    return slot;
+}
+
+// Up to three scalar stragglers on either side of the vector body (misaligned head, ragged tail).
+__device__ __forceinline__ void bucket_stragglers(const double *p, int n, const Prec &pc,
+                                                  unsigned long long *__restrict__ counts, uint32_t *flag) {
+    for (int i = 0; i < n; i++) add_bucket_global(counts, flag, key16_of(p[i], pc), 1ull, pc.win);
+}
+
+// ------------------------------------------------------------------- K1/ldg
+// First version, kept as a second evaluator: scalar fast_candidate() per sample, 256-bit loads double-buffered in
+// registers.  vals32: 32-byte aligned, nvec 32-byte vectors (4 samples each).
 template <int NS>
-__device__ __forceinline__ void bucket_samples(const double (&v)[NS], uint32_t *hist,
-                                               unsigned long long *__restrict__ counts) {
+__device__ __forceinline__ void bucket_samples(const double (&v)[NS], uint32_t *hist, const Prec &pc,
+                                               unsigned long long *__restrict__ counts, uint32_t *flag) {
     uint32_t idx[NS];
     bool slow[NS];
     bool any = false;
 #pragma unroll
-    for (int i = 0; i < NS; i++) { fast_candidate(v[i], idx[i], slow[i]); any |= slow[i]; }
+    for (int i = 0; i < NS; i++) { fast_candidate(v[i], pc, idx[i], slow[i]); any |= slow[i]; }
     if (__any_sync(0xFFFFFFFFu, any)) {
 #pragma unroll
         for (int i = 0; i < NS; i++) {
             if (slow[i]) {
-                uint32_t key = exact_key16(v[i]);
-                uint32_t slot = key16_to_slot(key);
-                if (slot == 0xFFFFFFFFu) { atomicAdd(&counts[key], 1ull); slot = LH_TRASH; }
+                const uint32_t key = exact_key16(v[i], pc.precision);
+                uint32_t slot = key16_to_slot(key, pc.win);
+                if (slot == 0xFFFFFFFFu) { add_bucket_global(counts, flag, key, 1ull, pc.win); slot = 2u * pc.win; }
                 idx[i] = slot;
             }
         }
@@ -106,30 +165,13 @@ __device__ __forceinline__ void bucket_samples(const double (&v)[NS], uint32_t *
     for (int i = 0; i < NS; i++) atomicAdd(&hist[idx[i]], 1u);
 }
 
-__device__ __forceinline__ void flush_subhist(const uint32_t *hist, int copies, int tid, int nthreads,
-                                              unsigned long long *__restrict__ counts) {
-    for (int slot = tid; slot < LH_SUBHIST; slot += nthreads) {
-        uint32_t c = 0;
-        for (int k = 0; k < copies; k++) c += hist[k * LH_SUBHIST_ALLOC + slot];
-        if (c) atomicAdd(&counts[slot_to_key16((uint32_t)slot)], (unsigned long long)c);
-    }
-}
-
-// ------------------------------------------------------------------- K1/ldg
-// vals32: 32-byte aligned, nvec 32-byte vectors (4 samples each).  Up to three
-// scalar stragglers on either side (misaligned head, ragged tail) come separately.
-__device__ __forceinline__ void bucket_stragglers(const double *p, int n, unsigned long long *__restrict__ counts) {
-    for (int i = 0; i < n; i++) atomicAdd(&counts[key16_of(p[i])], 1ull);
-}
-
-template <int THREADS, int UNROLL, int COPIES, int MINB, bool WIDE>
+template <int THREADS, int UNROLL, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_ingest_single_ldg(const double *__restrict__ vals32, size_t nvec, const double *head, int nhead,
-                    const double *tail, int ntail, unsigned long long *__restrict__ counts) {
+                    const double *tail, int ntail, unsigned long long *__restrict__ counts, uint32_t *flag, Prec pc) {
     extern __shared__ __align__(16) uint32_t s_hist[];
-    for (int i = threadIdx.x; i < COPIES * (int)LH_SUBHIST_ALLOC; i += THREADS) s_hist[i] = 0;
+    for (uint32_t i = threadIdx.x; i < subhist_words(pc.win); i += THREADS) s_hist[i] = 0;
     __syncthreads();
-    uint32_t *my = s_hist + ((threadIdx.x >> 5) % COPIES) * LH_SUBHIST_ALLOC;
     const char *base = reinterpret_cast<const char *>(vals32);
 
     constexpr size_t TILE = (size_t)THREADS * UNROLL;   // 32-byte vectors per tile
@@ -138,72 +180,53 @@ k_ingest_single_ldg(const double *__restrict__ vals32, size_t nvec, const double
     size_t tile = blockIdx.x;
     if (tile < ntiles) {
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            const char *p = base + (tile * TILE + (size_t)u * THREADS + threadIdx.x) * 32;
-            cur[u] = WIDE ? ldg_stream_f64x4(p) : ldg_stream_f64x2x2(p);
-        }
+        for (int u = 0; u < UNROLL; u++) cur[u] = ldg_stream_f64x4(base + (tile * TILE + (size_t)u * THREADS + threadIdx.x) * 32);
     }
     while (tile < ntiles) {
-        size_t nt = tile + gridDim.x;
+        const size_t nt = tile + gridDim.x;
         if (nt < ntiles) {
 #pragma unroll
-            for (int u = 0; u < UNROLL; u++) {
-                const char *p = base + (nt * TILE + (size_t)u * THREADS + threadIdx.x) * 32;
-                nxt[u] = WIDE ? ldg_stream_f64x4(p) : ldg_stream_f64x2x2(p);
-            }
+            for (int u = 0; u < UNROLL; u++) nxt[u] = ldg_stream_f64x4(base + (nt * TILE + (size_t)u * THREADS + threadIdx.x) * 32);
         }
         double v[4 * UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) { v[4 * u] = cur[u].a; v[4 * u + 1] = cur[u].b; v[4 * u + 2] = cur[u].c; v[4 * u + 3] = cur[u].d; }
-        bucket_samples<4 * UNROLL>(v, my, counts);
+        bucket_samples<4 * UNROLL>(v, s_hist, pc, counts, flag);
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) cur[u] = nxt[u];
         tile = nt;
     }
     // partial last tile + stragglers: one CTA, bounds-checked (rare, < TILE vectors)
     if (blockIdx.x == ntiles % gridDim.x) {
-        for (size_t j = ntiles * TILE * 4 + threadIdx.x; j < nvec * 4; j += THREADS) {
-            uint32_t k0 = key16_of(vals32[j]);
-            uint32_t s0 = key16_to_slot(k0);
-            if (s0 == 0xFFFFFFFFu) atomicAdd(&counts[k0], 1ull); else atomicAdd(&my[s0], 1u);
-        }
-        if (threadIdx.x == 0) { bucket_stragglers(head, nhead, counts); bucket_stragglers(tail, ntail, counts); }
+        for (size_t j = ntiles * TILE * 4 + threadIdx.x; j < nvec * 4; j += THREADS)
+            atomicAdd(&s_hist[fixup_slot(vals32[j], pc, counts, flag)], 1u);
+        if (threadIdx.x == 0) { bucket_stragglers(head, nhead, pc, counts, flag); bucket_stragglers(tail, ntail, pc, counts, flag); }
     }
     __syncthreads();
-    flush_subhist(s_hist, COPIES, threadIdx.x, THREADS, counts);
+    flush_subhist(s_hist, threadIdx.x, THREADS, counts, flag, pc.win);
 }
 
-// ---------------------------------------------------------------- K1/ldg v2
-// Same algorithm as k_ingest_single_ldg with the per-sample instruction count cut from ~30 to ~20 so that the
+// ------------------------------------------------------- packed-FP32 bucket arithmetic
+// Same algorithm as fast_candidate() with the per-sample instruction count cut from ~30 to ~20 so that the
 // kernel stays HBM-bound under sustained load (profiles/r01/sustained_probe.txt):
 //   * samples are processed in pairs with Blackwell's packed FP32 ops (fma.rn.f32x2 / add.f32x2);
-//   * (float)e comes from one I2FP and the -1023 bias rides in the FMA addend;
-//   * ONE flag per sample -- estimate too close to a bucket boundary, OR v's high word >= 0x43E00000 unsigned
-//     (|v| >= 2^63, Inf, NaN, and every negative value) -- sends it to a fix-up that re-derives the slot
-//     (negative values cost a second fast evaluation there, not the FP64 path);
-//   * the shared-memory byte offset is built as e*276 + (rounded bits << 2) + const: one IMAD and one LEA;
-//   * two register buffers alternate, so no copies.
-// Extra estimate error vs fast_candidate(): the float constant -1023*c2 (|err| <= 1.6e-5 bucket units), still
-// well inside LH_FAST_EPS.
-__device__ __forceinline__ uint32_t fixup_slot(double v, unsigned long long *__restrict__ counts) {
-    uint32_t key = key16_of(v);
-    uint32_t slot = key16_to_slot(key);
-    if (slot == 0xFFFFFFFFu) { atomicAdd(&counts[key], 1ull); slot = LH_TRASH; }
-    return slot;
-}
-
-template <int NS>
-__device__ __forceinline__ void bucket_samples_v2(const double (&v)[NS], uint32_t *hist, uint32_t one_bits,
-                                                  unsigned long long *__restrict__ counts) {
+//   * (float)e comes from one I2FP and the -1023 bias rides in the FMA addend (Prec::kb);
+//   * ONE flag per sample: estimate too close to a bucket boundary, OR x = 1+|v| outside the window
+//     (x's high word >= 0x43E00000: |v| >= 2^63, Inf, NaN);
+//   * the sign of v is folded into the slot (negative values land in [win, 2*win)) instead of being flagged, so a
+//     stream with many negative durations (readme.md:43) stays on the fast path;
+//   * the shared-memory byte offset is built as eb*a4 + (rounded bits << 2) + const: one IMAD and one LEA.
+// Extra estimate error vs fast_candidate(): the float constant -1023*c2 (|err| <= 1.6e-5 bucket units at
+// precision 100), still well inside eps.
+// FOLD_SIGN = false: positive-only layout (rows of `win` slots); negative samples are flagged instead.
+// SHIFT = 2: byte offsets into a uint32 sub-histogram; SHIFT = 0: slot indices.
+template <int NS, bool FOLD_SIGN, int SHIFT = 2>
+__device__ __forceinline__ void bucket_offsets_v2(const double (&v)[NS], const Prec &pc, uint32_t one_bits,
+                                                  uint32_t (&off)[NS], bool (&flag)[NS]) {
     static_assert(NS % 2 == 0, "pairs");
-    constexpr float C1 = 69.31471805599453f, C2 = 0.31471805599453f;
-    constexpr float KB = (float)(-1023.0 * (double)C2);
     constexpr float MAGIC = 12582912.0f;
-    // byte offset = 4*(69*(eb-1023) + (bits(r) - 0x4B400000))  (mod 2^32)
-    constexpr uint32_t COFF = 0u - (1023u * 69u * 4u) - (0x4B400000u << 2);
-    uint32_t off[NS];
-    bool flag[NS];
-    bool any = false;
+    const uint32_t negoff = pc.win << SHIFT;
+    const uint32_t am = SHIFT ? pc.a4 : pc.a_int, cm = SHIFT ? pc.coff : pc.coff0;
 #pragma unroll
     for (int i = 0; i < NS; i += 2) {
         const double x0 = __dadd_rn(1.0, fabs(v[i])), x1 = __dadd_rn(1.0, fabs(v[i + 1]));
@@ -218,127 +241,55 @@ __device__ __forceinline__ void bucket_samples_v2(const double (&v)[NS], uint32_
         asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg.y) : "f"(__uint_as_float(m1)));
         const uint32_t e0 = h0 >> 20, e1 = h1 >> 20;                    // 1023 + e
         const float2 ef = make_float2(__uint2float_rn(e0), __uint2float_rn(e1));
-        const float2 a = __ffma2_rn(ef, make_float2(C2, C2), make_float2(KB, KB));
-        const float2 w = __ffma2_rn(lg, make_float2(C1, C1), a);
+        const float2 a = __ffma2_rn(ef, make_float2(pc.c2, pc.c2), make_float2(pc.kb, pc.kb));
+        const float2 w = __ffma2_rn(lg, make_float2(pc.c1, pc.c1), a);
         const float2 r = __fadd2_rn(w, make_float2(MAGIC, MAGIC));
         const float2 s = __fadd2_rn(r, make_float2(-MAGIC, -MAGIC));
         const float2 d = __ffma2_rn(s, make_float2(-1.0f, -1.0f), w);   // w - s, one rounding
-        flag[i] = (fabsf(d.x) > 0.5f - LH_FAST_EPS) | ((uint32_t)__double2hiint(v[i]) >= 0x43E00000u);
-        flag[i + 1] = (fabsf(d.y) > 0.5f - LH_FAST_EPS) | ((uint32_t)__double2hiint(v[i + 1]) >= 0x43E00000u);
-        off[i] = e0 * 276u + (__float_as_uint(r.x) << 2) + COFF;
-        off[i + 1] = e1 * 276u + (__float_as_uint(r.y) << 2) + COFF;
-        any |= flag[i] | flag[i + 1];
+        if (FOLD_SIGN) {
+            flag[i] = (fabsf(d.x) > pc.thresh) | (h0 >= 0x43E00000u);
+            flag[i + 1] = (fabsf(d.y) > pc.thresh) | (h1 >= 0x43E00000u);
+            const uint32_t n0 = (uint32_t)__double2hiint(v[i]) >> 31, n1 = (uint32_t)__double2hiint(v[i + 1]) >> 31;
+            off[i] = e0 * am + (__float_as_uint(r.x) << SHIFT) + (n0 * negoff + cm);
+            off[i + 1] = e1 * am + (__float_as_uint(r.y) << SHIFT) + (n1 * negoff + cm);
+        } else {
+            // v's high word >= 0x43E00000 unsigned: |v| >= 2^63, Inf, NaN and every negative value
+            flag[i] = (fabsf(d.x) > pc.thresh) | ((uint32_t)__double2hiint(v[i]) >= 0x43E00000u);
+            flag[i + 1] = (fabsf(d.y) > pc.thresh) | ((uint32_t)__double2hiint(v[i + 1]) >= 0x43E00000u);
+            off[i] = e0 * am + (__float_as_uint(r.x) << SHIFT) + cm;
+            off[i + 1] = e1 * am + (__float_as_uint(r.y) << SHIFT) + cm;
+        }
     }
+}
+
+template <int NS, bool FOLD_SIGN>
+__device__ __forceinline__ void bucket_samples_v2(const double (&v)[NS], uint32_t *hist, const Prec &pc, uint32_t one_bits,
+                                                  unsigned long long *__restrict__ counts, uint32_t *gflag) {
+    uint32_t off[NS];
+    bool flag[NS];
+    bucket_offsets_v2<NS, FOLD_SIGN>(v, pc, one_bits, off, flag);
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < NS; i++) any |= flag[i];
     if (__any_sync(0xFFFFFFFFu, any)) {
+        // only the sample positions some lane flagged are re-derived (a warp-uniform branch per position)
 #pragma unroll
         for (int i = 0; i < NS; i++)
-            if (flag[i]) off[i] = fixup_slot(v[i], counts) * 4u;
+            if (__any_sync(0xFFFFFFFFu, flag[i])) {
+                if (flag[i]) off[i] = fixup_slot(v[i], pc, counts, gflag) * 4u;
+            }
     }
 #pragma unroll
     for (int i = 0; i < NS; i++) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(hist) + off[i]), 1u);
 }
 
-template <int THREADS, int UNROLL, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB)
-k_ingest_single_v2(const double *__restrict__ vals32, size_t nvec, const double *head, int nhead,
-                   const double *tail, int ntail, unsigned long long *__restrict__ counts) {
-    extern __shared__ __align__(16) uint32_t s_hist[];
-    for (int i = threadIdx.x; i < (int)LH_SUBHIST_ALLOC; i += THREADS) s_hist[i] = 0;
-    __syncthreads();
-    uint32_t one_bits;
-    asm volatile("mov.b32 %0, 0x3F800000;" : "=r"(one_bits));   // opaque to constant folding: keeps LOP3 at one instruction
-    const char *base = reinterpret_cast<const char *>(vals32);
-    constexpr size_t TILE = (size_t)THREADS * UNROLL;           // 32-byte vectors per tile
-    const size_t ntiles = nvec / TILE;
-    const size_t step = gridDim.x;
-
-    f64x4 A[UNROLL], B[UNROLL];
-    auto load = [&](f64x4(&buf)[UNROLL], size_t tile) {
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) buf[u] = ldg_stream_f64x4(base + (tile * TILE + (size_t)u * THREADS + threadIdx.x) * 32);
-    };
-    auto process = [&](const f64x4(&buf)[UNROLL]) {
-        double v[4 * UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) { v[4 * u] = buf[u].a; v[4 * u + 1] = buf[u].b; v[4 * u + 2] = buf[u].c; v[4 * u + 3] = buf[u].d; }
-        bucket_samples_v2<4 * UNROLL>(v, s_hist, one_bits, counts);
-    };
-    size_t tile = blockIdx.x;
-    if (tile < ntiles) load(A, tile);
-    while (tile < ntiles) {
-        const size_t t1 = tile + step;
-        if (t1 < ntiles) load(B, t1);
-        process(A);
-        if (t1 >= ntiles) break;
-        const size_t t2 = t1 + step;
-        if (t2 < ntiles) load(A, t2);
-        process(B);
-        tile = t2;
-    }
-    if (blockIdx.x == ntiles % gridDim.x) {   // partial last tile + stragglers
-        for (size_t j = ntiles * TILE * 4 + threadIdx.x; j < nvec * 4; j += THREADS) {
-            uint32_t slot = fixup_slot(vals32[j], counts);
-            atomicAdd(&s_hist[slot], 1u);
-        }
-        if (threadIdx.x == 0) { bucket_stragglers(head, nhead, counts); bucket_stragglers(tail, ntail, counts); }
-    }
-    __syncthreads();
-    flush_subhist(s_hist, 1, threadIdx.x, THREADS, counts);
-}
-
-// ---------------------------------------------------------------- K1/ldg v3
-// v2's arithmetic with a three-deep register rotation: every thread always has DEPTH-1 256-bit loads in flight
-// (64 KB per SM at 1024 threads) while it buckets the 4 samples of the oldest one, inside 64 registers.
-template <int THREADS, int MINB, int DEPTH>
-__global__ void __launch_bounds__(THREADS, MINB)
-k_ingest_single_v3(const double *__restrict__ vals32, size_t nvec, const double *head, int nhead,
-                   const double *tail, int ntail, unsigned long long *__restrict__ counts) {
-    extern __shared__ __align__(16) uint32_t s_hist[];
-    for (int i = threadIdx.x; i < (int)LH_SUBHIST_ALLOC; i += THREADS) s_hist[i] = 0;
-    __syncthreads();
-    uint32_t one_bits;
-    asm volatile("mov.b32 %0, 0x3F800000;" : "=r"(one_bits));
-    const char *base = reinterpret_cast<const char *>(vals32) + (size_t)threadIdx.x * 32;
-    constexpr size_t TILE_BYTES = (size_t)THREADS * 32;
-    const size_t ntiles = nvec / THREADS;
-    const size_t step = gridDim.x;
-
-    f64x4 buf[DEPTH];
-    size_t tile = blockIdx.x;          // tile whose data sits in buf[0]
-#pragma unroll
-    for (int d = 0; d < DEPTH - 1; d++)
-        if (tile + d * step < ntiles) buf[d] = ldg_stream_f64x4(base + (tile + d * step) * TILE_BYTES);
-    while (tile < ntiles) {
-#pragma unroll
-        for (int d = 0; d < DEPTH; d++) {          // rotation unrolled: buffer indices are compile-time
-            const size_t cur = tile + (size_t)d * step;
-            if (cur >= ntiles) break;
-            const size_t pre = cur + (size_t)(DEPTH - 1) * step;
-            if (pre < ntiles) buf[(d + DEPTH - 1) % DEPTH] = ldg_stream_f64x4(base + pre * TILE_BYTES);
-            const double v[4] = {buf[d].a, buf[d].b, buf[d].c, buf[d].d};
-            bucket_samples_v2<4>(v, s_hist, one_bits, counts);
-        }
-        tile += (size_t)DEPTH * step;
-    }
-    if (blockIdx.x == ntiles % gridDim.x) {   // partial last tile + stragglers
-        for (size_t j = ntiles * THREADS * 4 + threadIdx.x; j < nvec * 4; j += THREADS) {
-            uint32_t slot = fixup_slot(vals32[j], counts);
-            atomicAdd(&s_hist[slot], 1u);
-        }
-        if (threadIdx.x == 0) { bucket_stragglers(head, nhead, counts); bucket_stragglers(tail, ntail, counts); }
-    }
-    __syncthreads();
-    flush_subhist(s_hist, 1, threadIdx.x, THREADS, counts);
-}
-
 // --------------------------------------------------------------- read probe
-// Diagnostic only (lh_tune "k1" = last variant): the same 256-bit streaming loads as K1/ldg with the
-// bucket arithmetic replaced by an XOR fold, to separate memory-side from SM-side limits.  Counts are NOT
-// produced; one word per CTA is written so the loads cannot be elided.
+// Diagnostic only (a K1 "variant" that produces NO counts): the same 256-bit streaming loads as K1/ldg with the
+// bucket arithmetic replaced by an XOR fold, to separate memory-side from SM-side limits.
 template <int THREADS, int UNROLL>
 __global__ void __launch_bounds__(THREADS, 2)
 k_stream_probe(const double *__restrict__ vals32, size_t nvec, const double *, int, const double *, int,
-               unsigned long long *__restrict__ counts) {
+               unsigned long long *__restrict__ counts, uint32_t *, Prec) {
     const char *base = reinterpret_cast<const char *>(vals32);
     constexpr size_t TILE = (size_t)THREADS * UNROLL;
     const size_t ntiles = nvec / TILE;
@@ -357,14 +308,12 @@ k_stream_probe(const double *__restrict__ vals32, size_t nvec, const double *, i
 // ------------------------------------------------------------------ K1/bulk
 // Producer warp streams STAGE_BYTES tiles into a STAGES-deep shared ring with
 // cp.async.bulk; CW consumer warps bucket them.  Tiles are dealt round-robin.
-template <int NS>
-__device__ __forceinline__ void bucket_samples_v2(const double (&v)[NS], uint32_t *hist, uint32_t one_bits,
-                                                  unsigned long long *__restrict__ counts);
-
-template <int CW, int STAGES, int STAGE_BYTES, int COPIES, int MINB, bool V2 = false>
+// FOLD_SIGN: negative samples stay on the fast path (their slot is offset by `win`) at the price of two more integer
+// instructions per sample; without it they are flagged and re-derived in the fix-up.
+template <int CW, int STAGES, int STAGE_BYTES, int MINB, bool FOLD_SIGN>
 __global__ void __launch_bounds__((CW + 1) * 32, MINB)
 k_ingest_single_bulk(const double *__restrict__ vals32, size_t nvec32, const double *head, int nhead,
-                     const double *tail, int ntail, unsigned long long *__restrict__ counts) {
+                     const double *tail, int ntail, unsigned long long *__restrict__ counts, uint32_t *flag, Prec pc) {
     const double2 *vals16 = reinterpret_cast<const double2 *>(vals32);
     const size_t nvec = nvec32 * 2;   // 16-byte vectors
     constexpr int CT = CW * 32;                       // consumer threads
@@ -379,7 +328,7 @@ k_ingest_single_bulk(const double *__restrict__ vals32, size_t nvec32, const dou
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
-    for (int i = tid; i < COPIES * (int)LH_SUBHIST_ALLOC; i += (CW + 1) * 32) s_hist[i] = 0;
+    for (uint32_t i = tid; i < subhist_words(pc.win); i += (CW + 1) * 32) s_hist[i] = 0;
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -404,7 +353,8 @@ k_ingest_single_bulk(const double *__restrict__ vals32, size_t nvec32, const dou
         }
     } else {
         // ===== consumers =====
-        uint32_t *my = s_hist + (warp % COPIES) * LH_SUBHIST_ALLOC;
+        uint32_t one_bits;
+        asm volatile("mov.b32 %0, 0x3F800000;" : "=r"(one_bits));   // opaque to constant folding: keeps LOP3 at one instruction
         uint32_t it = 0;
         for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
             const int s = it % STAGES;
@@ -421,39 +371,31 @@ k_ingest_single_bulk(const double *__restrict__ vals32, size_t nvec32, const dou
                 }
                 __syncwarp();
                 if ((tid & 31) == 0) mbar_arrive(&empty[s]);   // registers hold the data: release early
-                if constexpr (V2) {
-                    uint32_t one_bits;
-                    asm volatile("mov.b32 %0, 0x3F800000;" : "=r"(one_bits));
 #pragma unroll
-                    for (int q = 0; q < 2 * PER_THREAD; q += 4) {
-                        const double v4[4] = {v[q], v[q + 1], v[q + 2], v[q + 3]};
-                        bucket_samples_v2<4>(v4, my, one_bits, counts);
-                    }
-                } else {
-                    bucket_samples<2 * PER_THREAD>(v, my, counts);
+                for (int q = 0; q < 2 * PER_THREAD; q += 4) {
+                    const double v4[4] = {v[q], v[q + 1], v[q + 2], v[q + 3]};
+                    bucket_samples_v2<4, FOLD_SIGN>(v4, s_hist, pc, one_bits, counts, flag);
                 }
             } else {
                 for (int j = tid; j < (int)rem; j += CT) {
                     double2 d = st[j];
-                    uint32_t k0 = key16_of(d.x), k1 = key16_of(d.y);
-                    uint32_t s0 = key16_to_slot(k0), s1 = key16_to_slot(k1);
-                    if (s0 == 0xFFFFFFFFu) atomicAdd(&counts[k0], 1ull); else atomicAdd(&my[s0], 1u);
-                    if (s1 == 0xFFFFFFFFu) atomicAdd(&counts[k1], 1ull); else atomicAdd(&my[s1], 1u);
+                    atomicAdd(&s_hist[fixup_slot(d.x, pc, counts, flag)], 1u);
+                    atomicAdd(&s_hist[fixup_slot(d.y, pc, counts, flag)], 1u);
                 }
                 __syncwarp();
                 if ((tid & 31) == 0) mbar_arrive(&empty[s]);
             }
         }
-        if (blockIdx.x == 0 && tid == 0) { bucket_stragglers(head, nhead, counts); bucket_stragglers(tail, ntail, counts); }
+        if (blockIdx.x == 0 && tid == 0) { bucket_stragglers(head, nhead, pc, counts, flag); bucket_stragglers(tail, ntail, pc, counts, flag); }
     }
     __syncthreads();
-    flush_subhist(s_hist, COPIES, tid, (CW + 1) * 32, counts);
+    flush_subhist(s_hist, tid, (CW + 1) * 32, counts, flag, pc.win);
 }
 
 // --------------------------------------------------------------------- K1k
 // (id,value) pairs.  1024 histograms x ~4.4K live buckets cannot be privatised
-// in shared memory, so the cells live in L2: a compact uint32 "hot window"
-// [H][LH_SUBHIST] (36 MB at H = 1024, vs 512 MB for the dense uint64 arrays)
+// in one CTA's shared memory.  The general fallback keeps the cells in L2: a compact uint32 "hot window"
+// [H][2*win] (36 MB at H = 1024, vs 512 MB for the dense uint64 arrays)
 // updated with no-return atomics that carry an L2 evict_last policy, while the
 // sample stream is read once with 256-bit evict_first loads so it does not push
 // the cells out of the 126 MB L2.  Keys outside the window go straight to the
@@ -464,107 +406,115 @@ template <> __device__ __forceinline__ double sample_to_f64<double>(double v) { 
 // float64(duration.Nanoseconds()): CVTSQ2SD, round-to-nearest-even
 template <> __device__ __forceinline__ double sample_to_f64<long long>(long long v) { return __ll2double_rn(v); }
 
-__device__ __forceinline__ uint64_t policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void red_add_u32_keep(unsigned int *addr, unsigned int v, uint64_t policy) {
-    asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(addr), "r"(v), "l"(policy) : "memory");
-}
+struct KeyedOut {
+    unsigned int *hot;                 // [replicas][H][2*win] uint32
+    unsigned long long *buckets;       // [H][65536]
+    uint32_t *flags;                   // [H]
+    unsigned long long *dropped;
+    uint32_t H;
+};
 
 template <typename ValT>
-__device__ __forceinline__ void keyed_one(uint32_t id, ValT raw, uint32_t H, unsigned int *__restrict__ hot,
-                                          unsigned long long *__restrict__ buckets,
-                                          unsigned long long *__restrict__ dropped, uint64_t pol) {
-    if (id >= H) { atomicAdd(dropped, 1ull); return; }
+__device__ __forceinline__ void keyed_one(uint32_t id, ValT raw, const Prec &pc, const KeyedOut &o, unsigned int *hot, uint64_t pol) {
+    if (id >= o.H) { atomicAdd(o.dropped, 1ull); return; }
     double v = sample_to_f64<ValT>(raw);
     uint32_t idx; bool slow;
-    fast_candidate(v, idx, slow);
+    fast_candidate(v, pc, idx, slow);
     if (slow) {
-        uint32_t key = exact_key16(v);
-        idx = key16_to_slot(key);
-        if (idx == 0xFFFFFFFFu) { atomicAdd(&buckets[(size_t)id * 65536u + key], 1ull); return; }
+        uint32_t key = exact_key16(v, pc.precision);
+        idx = key16_to_slot(key, pc.win);
+        if (idx == 0xFFFFFFFFu) { add_bucket_global(o.buckets + (size_t)id * 65536u, o.flags + id, key, 1ull, pc.win); return; }
     }
-    red_add_u32_keep(&hot[(size_t)id * LH_SUBHIST + idx], 1u, pol);
+    red_add_u32_keep(&hot[(size_t)id * (2u * pc.win) + idx], 1u, pol);
+}
+
+// Out-of-line form for kernels whose common path must stay small (the write-combining kernel calls it for the
+// ~0.05 % of samples its fast path does not cover).
+template <typename ValT>
+__device__ __noinline__ void keyed_one_slow(uint32_t id, unsigned long long raw, Prec pc, KeyedOut o, uint64_t pol) {
+    if (id == 0xFFFFFFFFu) return;            // padding lane past the end of the batch
+    ValT r;
+    memcpy(&r, &raw, 8);
+    keyed_one<ValT>(id, r, pc, o, o.hot, pol);
+}
+
+template <typename IdT>
+__device__ __forceinline__ void load_ids4(const IdT *ids, size_t g, uint32_t (&id4)[4]) {
+    if (sizeof(IdT) == 2) {
+        unsigned int lo, hi;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi)
+                     : "l"(reinterpret_cast<const char *>(ids) + g * 8));
+        id4[0] = lo & 0xFFFFu; id4[1] = lo >> 16; id4[2] = hi & 0xFFFFu; id4[3] = hi >> 16;
+    } else {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(id4[0]), "=r"(id4[1]), "=r"(id4[2]), "=r"(id4[3])
+                     : "l"(reinterpret_cast<const char *>(ids) + g * 16));
+    }
+}
+__device__ __forceinline__ void load_vals4(const void *vals, size_t g, unsigned long long (&raw)[4]) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
+                 : "=l"(raw[0]), "=l"(raw[1]), "=l"(raw[2]), "=l"(raw[3]) : "l"(reinterpret_cast<const char *>(vals) + g * 32));
 }
 
 // Vector body: every thread takes 4 consecutive pairs (one 256-bit value load, one 64/128-bit id load).
 // vals must be 32-byte aligned and ids 4*sizeof(IdT)-aligned; n4 = number of 4-sample groups.
-// `hot` holds `replicas` copies of the window ([replicas][H][LH_SUBHIST]); CTA b updates copy b % replicas, which
+// `hot` holds `replicas` copies of the window ([replicas][H][2*win]); CTA b updates copy b % replicas, which
 // divides the same-address pressure on hot cells (clustered, latency-like data) by the replica count while every
 // copy stays L2-resident.  k_fold_hot sums the copies.
 template <typename IdT, typename ValT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-k_ingest_keyed_vec(const IdT *__restrict__ ids, const ValT *__restrict__ vals, size_t n4, uint32_t H,
-                   unsigned int *__restrict__ hot, uint32_t replicas, unsigned long long *__restrict__ buckets,
-                   unsigned long long *__restrict__ dropped) {
-    hot += (size_t)(blockIdx.x % replicas) * H * LH_SUBHIST;
+k_ingest_keyed_vec(const IdT *__restrict__ ids, const ValT *__restrict__ vals, size_t n4, uint32_t replicas, KeyedOut o, Prec pc) {
+    unsigned int *hot = o.hot + (size_t)(blockIdx.x % replicas) * o.H * (2u * pc.win);
     const uint64_t pol = policy_evict_last();
     const size_t stride = (size_t)gridDim.x * THREADS;
     for (size_t g = (size_t)blockIdx.x * THREADS + threadIdx.x; g < n4; g += stride) {
-        unsigned long long a, b, c, d;
-        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
-                     : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(reinterpret_cast<const char *>(vals) + g * 32));
-        uint32_t i0, i1, i2, i3;
-        if (sizeof(IdT) == 2) {
-            unsigned int lo, hi;
-            asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi)
-                         : "l"(reinterpret_cast<const char *>(ids) + g * 8));
-            i0 = lo & 0xFFFFu; i1 = lo >> 16; i2 = hi & 0xFFFFu; i3 = hi >> 16;
-        } else {
-            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(i0), "=r"(i1), "=r"(i2), "=r"(i3)
-                         : "l"(reinterpret_cast<const char *>(ids) + g * 16));
+        unsigned long long raw[4];
+        uint32_t id4[4];
+        load_vals4(vals, g, raw);
+        load_ids4<IdT>(ids, g, id4);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            ValT r;
+            memcpy(&r, &raw[j], 8);
+            keyed_one<ValT>(id4[j], r, pc, o, hot, pol);
         }
-        ValT r0, r1, r2, r3;
-        memcpy(&r0, &a, 8); memcpy(&r1, &b, 8); memcpy(&r2, &c, 8); memcpy(&r3, &d, 8);
-        keyed_one<ValT>(i0, r0, H, hot, buckets, dropped, pol);
-        keyed_one<ValT>(i1, r1, H, hot, buckets, dropped, pol);
-        keyed_one<ValT>(i2, r2, H, hot, buckets, dropped, pol);
-        keyed_one<ValT>(i3, r3, H, hot, buckets, dropped, pol);
     }
 }
 
 // Scalar version for ragged heads/tails and misaligned inputs.
 template <typename IdT, typename ValT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-k_ingest_keyed(const IdT *__restrict__ ids, const ValT *__restrict__ vals, size_t n, uint32_t H,
-               unsigned int *__restrict__ hot, unsigned long long *__restrict__ buckets,
-               unsigned long long *__restrict__ dropped) {
+k_ingest_keyed(const IdT *__restrict__ ids, const ValT *__restrict__ vals, size_t n, KeyedOut o, Prec pc) {
     const uint64_t pol = policy_evict_last();
     const size_t stride = (size_t)gridDim.x * THREADS;
     for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += stride)
-        keyed_one<ValT>((uint32_t)ids[i], vals[i], H, hot, buckets, dropped, pol);
+        keyed_one<ValT>((uint32_t)ids[i], vals[i], pc, o, o.hot, pol);
 }
 
 // ------------------------------------------------------------------ K1k/small
-// Keyed ingest when only a few histograms are configured (H <= KS_MAX_H): all their positive windows
-// (uint32[H][4368]) are privatised per CTA in shared memory, exactly like K1, so the kernel is HBM-bound
-// (10 B/sample) instead of L2-atomic-bound.  Same packed-FP32 bucket arithmetic as bucket_samples_v2; the ONE
-// flag per sample also covers id >= H, and flagged samples (boundary-close estimates, negatives, |v| >= 2^63,
-// NaN/Inf, bad ids) take the L2 route of keyed_one().  Windows are added into the uint32 hot window at the end.
-constexpr int KS_MAX_H = 11;                 // 11 * 4368 * 4 B = 192 KB of shared memory
+// Keyed ingest when only a few histograms are configured: all their windows (uint32[ids][2*win]) are privatised
+// per CTA in shared memory, exactly like K1, so the kernel is HBM-bound (10 B/sample) instead of L2-atomic-bound.
+// Same packed-FP32 bucket arithmetic as K1 but with positive-only rows (uint32[ids][win]) so that twice as many
+// histograms fit; the ONE flag per sample also covers id >= H, and flagged samples (boundary-close estimates,
+// negatives, |v| >= 2^63, NaN/Inf, bad ids) take the L2 route of keyed_one().  Windows are added into the uint32
+// hot window at the end.
 constexpr int KS_THREADS = 1024;
+constexpr int KS_SMEM_BYTES = 196608;        // shared memory the windows of one pass may take (11 ids at precision 100)
 
 template <typename IdT, typename ValT>
 __global__ void __launch_bounds__(KS_THREADS, 1)
-k_ingest_keyed_small(const IdT *__restrict__ ids, const ValT *__restrict__ vals, size_t n4, uint32_t H,
-                     uint32_t id_lo, uint32_t id_cnt, unsigned int *__restrict__ hot,
-                     unsigned long long *__restrict__ buckets, unsigned long long *__restrict__ dropped) {
-    // This launch owns ids [id_lo, id_lo + id_cnt) (id_cnt <= KS_MAX_H); with more histograms than fit, the host
+k_ingest_keyed_small(const IdT *__restrict__ ids, const ValT *__restrict__ vals, size_t n4,
+                     uint32_t id_lo, uint32_t id_cnt, KeyedOut o, Prec pc) {
+    // This launch owns ids [id_lo, id_lo + id_cnt); with more histograms than fit, the host
     // runs one pass per id sub-range over the same batch.  Samples of other valid ids are skipped; ids >= H are
     // dropped (and counted) by the pass that starts at id 0.
-    extern __shared__ __align__(16) uint32_t ks_hist[];          // [id_cnt][LH_WIN] + trash word
-    const uint32_t words = id_cnt * (uint32_t)LH_WIN;
+    extern __shared__ __align__(16) uint32_t ks_hist[];          // [id_cnt][win] + trash word
+    const uint32_t row = pc.win;
+    const uint32_t words = id_cnt * row;
     for (uint32_t i = threadIdx.x; i <= words; i += KS_THREADS) ks_hist[i] = 0;
     __syncthreads();
     const uint64_t pol = policy_evict_last();
     uint32_t one_bits;
     asm volatile("mov.b32 %0, 0x3F800000;" : "=r"(one_bits));
-    constexpr float C1 = 69.31471805599453f, C2 = 0.31471805599453f;
-    constexpr float KB = (float)(-1023.0 * (double)C2);
-    constexpr float MAGIC = 12582912.0f;
-    constexpr uint32_t COFF = 0u - (1023u * 69u * 4u) - (0x4B400000u << 2);
     const uint32_t trash_off = words * 4u;
 
     // The loop bound is warp-uniform (base index of the CTA's row of groups); lanes past the end are predicated
@@ -573,58 +523,26 @@ k_ingest_keyed_small(const IdT *__restrict__ ids, const ValT *__restrict__ vals,
     size_t base = (size_t)blockIdx.x * KS_THREADS;
     unsigned long long cur[4] = {0, 0, 0, 0}, nxt[4] = {0, 0, 0, 0};
     uint32_t cur_id[4] = {0, 0, 0, 0}, nxt_id[4] = {0, 0, 0, 0};
-    auto load = [&](unsigned long long(&raw)[4], uint32_t(&id4)[4], size_t gi) {
-        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
-                     : "=l"(raw[0]), "=l"(raw[1]), "=l"(raw[2]), "=l"(raw[3]) : "l"(reinterpret_cast<const char *>(vals) + gi * 32));
-        if (sizeof(IdT) == 2) {
-            unsigned int lo, hi;
-            asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi)
-                         : "l"(reinterpret_cast<const char *>(ids) + gi * 8));
-            id4[0] = lo & 0xFFFFu; id4[1] = lo >> 16; id4[2] = hi & 0xFFFFu; id4[3] = hi >> 16;
-        } else {
-            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(id4[0]), "=r"(id4[1]), "=r"(id4[2]), "=r"(id4[3])
-                         : "l"(reinterpret_cast<const char *>(ids) + gi * 16));
-        }
-    };
-    if (base + threadIdx.x < n4) load(cur, cur_id, base + threadIdx.x);
+    if (base + threadIdx.x < n4) { load_vals4(vals, base + threadIdx.x, cur); load_ids4<IdT>(ids, base + threadIdx.x, cur_id); }
     for (; base < n4; base += stride) {
         const bool valid = base + threadIdx.x < n4;
         const size_t gn = base + stride + threadIdx.x;
-        if (gn < n4) load(nxt, nxt_id, gn);
+        if (gn < n4) { load_vals4(vals, gn, nxt); load_ids4<IdT>(ids, gn, nxt_id); }
+        double v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { ValT r; memcpy(&r, &cur[i], 8); v[i] = sample_to_f64<ValT>(r); }
         uint32_t off[4];
         bool flag[4];
+        bucket_offsets_v2<4, false>(v, pc, one_bits, off, flag);
         bool any = false;
 #pragma unroll
-        for (int i = 0; i < 4; i += 2) {
-            ValT r0, r1;
-            memcpy(&r0, &cur[i], 8); memcpy(&r1, &cur[i + 1], 8);
-            const double v0 = sample_to_f64<ValT>(r0), v1 = sample_to_f64<ValT>(r1);
-            const double x0 = __dadd_rn(1.0, fabs(v0)), x1 = __dadd_rn(1.0, fabs(v1));
-            const uint32_t h0 = (uint32_t)__double2hiint(x0), h1 = (uint32_t)__double2hiint(x1);
-            const uint32_t t0 = __funnelshift_l((uint32_t)__double2loint(x0), h0, 3);
-            const uint32_t t1 = __funnelshift_l((uint32_t)__double2loint(x1), h1, 3);
-            uint32_t m0, m1;
-            asm("lop3.b32 %0, %1, 0x007FFFFF, %2, 0xEA;" : "=r"(m0) : "r"(t0), "r"(one_bits));
-            asm("lop3.b32 %0, %1, 0x007FFFFF, %2, 0xEA;" : "=r"(m1) : "r"(t1), "r"(one_bits));
-            float2 lg;
-            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg.x) : "f"(__uint_as_float(m0)));
-            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg.y) : "f"(__uint_as_float(m1)));
-            const uint32_t e0 = h0 >> 20, e1 = h1 >> 20;
-            const float2 ef = make_float2(__uint2float_rn(e0), __uint2float_rn(e1));
-            const float2 a = __ffma2_rn(ef, make_float2(C2, C2), make_float2(KB, KB));
-            const float2 w = __ffma2_rn(lg, make_float2(C1, C1), a);
-            const float2 r = __fadd2_rn(w, make_float2(MAGIC, MAGIC));
-            const float2 sv = __fadd2_rn(r, make_float2(-MAGIC, -MAGIC));
-            const float2 d = __ffma2_rn(sv, make_float2(-1.0f, -1.0f), w);
-            // v's high word >= 0x43E00000 unsigned: |v| >= 2^63, Inf, NaN and every negative value
-            const uint32_t l0 = cur_id[i] - id_lo, l1 = cur_id[i + 1] - id_lo;          // local ids (wrap when below id_lo)
-            const bool mine0 = valid & (l0 < id_cnt), mine1 = valid & (l1 < id_cnt);
-            const bool bad0 = valid & (cur_id[i] >= H) & (id_lo == 0), bad1 = valid & (cur_id[i + 1] >= H) & (id_lo == 0);
-            flag[i] = (mine0 & ((fabsf(d.x) > 0.5f - LH_FAST_EPS) | ((uint32_t)__double2hiint(v0) >= 0x43E00000u))) | bad0;
-            flag[i + 1] = (mine1 & ((fabsf(d.y) > 0.5f - LH_FAST_EPS) | ((uint32_t)__double2hiint(v1) >= 0x43E00000u))) | bad1;
-            off[i] = mine0 ? e0 * 276u + (__float_as_uint(r.x) << 2) + COFF + l0 * (uint32_t)(LH_WIN * 4) : trash_off;
-            off[i + 1] = mine1 ? e1 * 276u + (__float_as_uint(r.y) << 2) + COFF + l1 * (uint32_t)(LH_WIN * 4) : trash_off;
-            any |= flag[i] | flag[i + 1];
+        for (int i = 0; i < 4; i++) {
+            const uint32_t l = cur_id[i] - id_lo;                                  // local id (wraps when below id_lo)
+            const bool mine = valid & (l < id_cnt);
+            const bool bad = valid & (cur_id[i] >= o.H) & (id_lo == 0);
+            flag[i] = (mine & flag[i]) | bad;
+            off[i] = mine ? off[i] + l * (row * 4u) : trash_off;
+            any |= flag[i];
         }
         if (__any_sync(0xFFFFFFFFu, any)) {
 #pragma unroll
@@ -632,9 +550,9 @@ k_ingest_keyed_small(const IdT *__restrict__ ids, const ValT *__restrict__ vals,
                 if (!flag[i]) continue;
                 ValT rv;
                 memcpy(&rv, &cur[i], 8);
-                // uncertain-but-positive samples of a valid id could stay in shared memory; the L2 route is exact too
+                // uncertain samples of a valid id could stay in shared memory; the L2 route is exact too
                 // and keeps this path trivial (it handles ~0.05 % of the samples)
-                keyed_one<ValT>(cur_id[i], rv, H, hot, buckets, dropped, pol);
+                keyed_one<ValT>(cur_id[i], rv, pc, o, o.hot, pol);
                 off[i] = trash_off;
             }
         }
@@ -647,45 +565,59 @@ k_ingest_keyed_small(const IdT *__restrict__ ids, const ValT *__restrict__ vals,
     for (uint32_t i = threadIdx.x; i < words; i += KS_THREADS) {
         const uint32_t c = ks_hist[i];
         if (!c) continue;
-        const uint32_t lid = i / (uint32_t)LH_WIN, slot = i - lid * (uint32_t)LH_WIN;
-        atomicAdd(&hot[(size_t)(id_lo + lid) * LH_SUBHIST + slot], c);
+        const uint32_t lid = i / row, slot = i - lid * row;
+        atomicAdd(&o.hot[(size_t)(id_lo + lid) * (2u * pc.win) + slot], c);
     }
 }
 
-// ------------------------------------------------------------- K1k/partitioned
-// Gets the keyed path past the L2 atomic rate (one RED sector per sample).  One persistent cooperative CTA per
-// SM; CTA p OWNS the histogram ids {p, p+P, p+2P, ...} and keeps their positive windows (uint32[ids_per][4368])
-// in shared memory for the whole launch.  The stream is processed in chunks; per chunk
-//   phase A  every CTA ("writer" w) bins its slice: bucket index via the fast path, a 16-bit record
-//            (lid*4368 + slot) per sample, counting-sorted by owner in shared memory and appended as contiguous
-//            runs to the (owner, writer) sub-queue in global memory -- every pair has its own region, so the
-//            append offsets live in shared memory and no global atomic is needed; at the end of the slice the
-//            writer publishes its P record counts;
+// ------------------------------------------------------------------- K1k/wc
+// Many histograms (H x window does not fit one CTA's shared memory): gets the keyed path past the L2 atomic
+// rate (one RED sector per sample, ~0.25 x HBM roofline) by routing every sample to the SM that OWNS its histogram.
+// One persistent cooperative CTA per SM; CTA p owns the ids {p, p+P, p+2P, ...} and keeps their positive windows
+// (uint32[ids_per][win]) in shared memory for the whole launch.  The stream is processed in chunks; per chunk
+//   phase A  every CTA ("writer") bins its slice: bucket index via the packed-FP32 fast path, one 16-bit record
+//            (lid*win + slot) per sample appended to a per-owner WRITE-COMBINING buffer in shared memory -- the
+//            position comes from one returning shared atomic on the owner's fill counter (measured 3.6 cycles per
+//            warp on ~148 spread addresses, profiles/r02/ubench_smem_primitives.txt; MATCH.ANY or ballot ranking
+//            cost 8-16x that).  After each tile of WC_TILE samples the full 128-byte lines are copied to the
+//            (owner, writer) sub-queue in global memory (L2-resident) with 128-bit stores and the remainder (< 64
+//            records) moves to the front of the buffer.  Every (owner, writer) pair has its own region, so the
+//            append offsets live in shared memory and no global atomic is needed;
 //   barrier  grid-wide (one per chunk; sub-queues are double-buffered by chunk parity);
-//   phase B  every owner drains its P sub-queues (L2 hits) into its shared-memory windows with shared atomics.
-// Samples the window does not cover (negative, |v| >= 2^63, NaN/Inf), ids >= H and records that do not fit their
-// sub-queue take the L2-atomic route of k_ingest_keyed.  At the end each CTA adds its windows into the hot window.
-constexpr int KP_MAX_PARTS = 320;             // owners = CTAs: up to 2 per SM
-constexpr int KP_SCAN_PER_LANE = KP_MAX_PARTS / 32;
+//   phase B  every owner drains its P sub-queues (L2 hits) into its shared-memory windows (ATOMS.POPC.INC).
+// Samples the window does not cover (negative, |v| >= 2^63, NaN/Inf, estimates within eps of a bucket boundary),
+// ids >= H, and records that do not fit their buffer or sub-queue (heavily skewed ids) take the exact L2-atomic
+// route of keyed_one().  At the end each CTA adds its windows into the uint32 hot window.
+constexpr int WC_THREADS = 512;
+constexpr int WC_MAX_PARTS = 160;             // owners = CTAs (one per SM)
+constexpr int WC_LINE = 64;                   // records per line (128 B)
 
-struct KpParams {
+template <int SPT> struct WcShape {           // SPT = samples per thread per tile
+    static constexpr int TILE = WC_THREADS * SPT;
+    // records one owner's buffer must hold: < WC_LINE carried over + one tile's share (TILE / P ~ TILE / 148)
+    // + 6 sigma of the binomial; beyond that the sample takes the L2 route
+    static constexpr int CAP = SPT == 16 ? 192 : 128;
+    // storage per owner: CAP + one spill line (the remainder copy reads a whole line) + 8 records of padding so that
+    // the 128-bit accesses of the per-owner flush (thread o <-> owner o) are bank-conflict free
+    static constexpr int STRIDE = CAP + WC_LINE + 8;
+};
+
+struct WcParams {
     const void *ids;                 // IdT[n], 4*sizeof(IdT)-aligned
     const void *vals;                // ValT[n], 32-byte aligned
-    size_t n;                        // multiple of 4
-    uint32_t H;
+    size_t n;                        // multiple of the tile size (the host sends the ragged tail to k_ingest_keyed)
     uint32_t ids_per;                // ceil(H / P)
-    uint32_t cap;                    // records per (owner, writer) sub-queue per parity, multiple of 8
+    uint32_t cap;                    // records per (owner, writer) sub-queue per parity, multiple of WC_LINE
     uint32_t slice_tiles;            // tiles per CTA per chunk
     uint32_t inv_p;                  // floor(2^32 / P) + 1: id / P == __umulhi(id, inv_p) for id < 65536
+    uint32_t inv_vq;                 // floor(2^32 / (cap / 8)) + 1: v / (cap / 8) == __umulhi(v, inv_vq) for v < P * cap / 8
     unsigned short *queues;          // [2][P owners][P writers][cap]
     unsigned int *q_cnt;             // [2][P owners][P writers]
     unsigned int *barrier;           // grid barrier counter, zeroed by the host before the launch
-    unsigned int *hot;               // [H][LH_SUBHIST]
-    unsigned long long *buckets;     // [H][65536]
-    unsigned long long *dropped;
+    KeyedOut o;
 };
 
-__device__ __forceinline__ void kp_grid_barrier(unsigned int *bar, unsigned int target) {
+__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int target) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -698,194 +630,215 @@ __device__ __forceinline__ void kp_grid_barrier(unsigned int *bar, unsigned int 
     __syncthreads();
 }
 
-template <typename IdT, typename ValT, int KP_THREADS, int KP_MINB>
-__global__ void __launch_bounds__(KP_THREADS, KP_MINB)
-k_ingest_keyed_part(KpParams prm) {
-    constexpr int KP_TILE = KP_THREADS * 8;       // samples per binning tile (8 per thread)
-    extern __shared__ __align__(16) unsigned char kp_smem[];
-    const int P = gridDim.x, p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned int *s_hist = reinterpret_cast<unsigned int *>(kp_smem);                       // [ids_per][LH_WIN]
-    const size_t hist_words = (size_t)prm.ids_per * LH_WIN;
-    unsigned int *s_cnt = s_hist + hist_words;                                              // per-owner count, this tile
-    unsigned int *s_start = s_cnt + KP_MAX_PARTS;                                           // exclusive scan of s_cnt
-    unsigned int *s_off = s_start + KP_MAX_PARTS;                                           // records appended this chunk
-    unsigned int *s_dst = s_off + KP_MAX_PARTS;                                             // [KP_TILE] global record index
-    unsigned short *s_rec = reinterpret_cast<unsigned short *>(s_dst + KP_TILE);            // [KP_TILE]
+// a record that could not be queued: add it to the hot window directly (exact, one L2 atomic)
+__device__ __forceinline__ void wc_spill(uint32_t rec, uint32_t owner, uint32_t P, const Prec &pc, const KeyedOut &o, uint64_t pol) {
+    const uint32_t lid = rec / pc.win, slot = rec - lid * pc.win;
+    red_add_u32_keep(&o.hot[(size_t)(lid * P + owner) * (2u * pc.win) + slot], 1u, pol);
+}
 
-    for (size_t i = tid; i < hist_words; i += KP_THREADS) s_hist[i] = 0;
-    for (unsigned int i = tid; i < KP_TILE; i += KP_THREADS) s_dst[i] = 0xFFFFFFFFu;
+// ids of one 4-sample group, kept PACKED while they wait in registers (unpacking right after the load would make the
+// prefetch wait for its own data)
+template <typename IdT> struct IdPack;
+template <> struct IdPack<unsigned short> {
+    unsigned int lo, hi;
+    __device__ __forceinline__ void load(const unsigned short *ids, size_t g) {
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "l"(reinterpret_cast<const char *>(ids) + g * 8));
+    }
+    __device__ __forceinline__ uint32_t get(int j) const { const unsigned int w = j < 2 ? lo : hi; return (j & 1) ? (w >> 16) : (w & 0xFFFFu); }
+};
+template <> struct IdPack<unsigned int> {
+    unsigned int w[4];
+    __device__ __forceinline__ void load(const unsigned int *ids, size_t g) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                     : "l"(reinterpret_cast<const char *>(ids) + g * 16));
+    }
+    __device__ __forceinline__ uint32_t get(int j) const { return w[j]; }
+};
+
+template <typename IdT, typename ValT, int SPT>
+__global__ void __launch_bounds__(WC_THREADS, 1)
+k_ingest_keyed_wc(WcParams prm, Prec pc) {
+    using S = WcShape<SPT>;
+    constexpr int GROUPS = SPT / 4;
+    constexpr int NWARPS = WC_THREADS / 32;
+    extern __shared__ __align__(16) unsigned char wc_smem[];
+    const uint32_t P = gridDim.x, p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned int *s_hist = reinterpret_cast<unsigned int *>(wc_smem);                       // [ids_per][win]
+    const uint32_t hist_words = prm.ids_per * pc.win;
+    unsigned int *s_fill = s_hist + ((hist_words + 3u) & ~3u);                              // records in each owner's buffer
+    unsigned int *s_off = s_fill + WC_MAX_PARTS;                                            // records appended to my sub-queues this chunk; phase B: record counts
+    unsigned short *s_buf = reinterpret_cast<unsigned short *>(s_off + WC_MAX_PARTS);       // [P + 1][STRIDE], row P = trash
+    const uint32_t fill_addr = smem_u32(s_fill), buf_addr = smem_u32(s_buf), hist_addr = smem_u32(s_hist);
+    const uint32_t trash_slot = P * (uint32_t)S::STRIDE + (uint32_t)S::CAP;                 // never read
+
+    for (uint32_t i = tid; i < hist_words; i += WC_THREADS) s_hist[i] = 0;
+    if (tid < WC_MAX_PARTS) { s_fill[tid] = 0; s_off[tid] = 0; }
     const uint64_t pol = policy_evict_last();
+    uint32_t one_bits;
+    asm volatile("mov.b32 %0, 0x3F800000;" : "=r"(one_bits));
     __syncthreads();
 
-    const size_t tiles_total = (prm.n + KP_TILE - 1) / KP_TILE;
+    const size_t tiles_total = prm.n / S::TILE;                  // the host passes whole tiles only
     const size_t chunk_tiles = (size_t)prm.slice_tiles * P;
     const size_t nchunks = (tiles_total + chunk_tiles - 1) / chunk_tiles;
     const IdT *ids = reinterpret_cast<const IdT *>(prm.ids);
-    const char *vals = reinterpret_cast<const char *>(prm.vals);
     const unsigned int cap = prm.cap;
+    const uint32_t vq = cap / 8;                                  // 16-byte vectors per sub-queue
+
+    unsigned long long cur[GROUPS][4], nxt[GROUPS][4];
+    IdPack<IdT> cur_id[GROUPS], nxt_id[GROUPS];
+    auto load_tile = [&](size_t tile, unsigned long long (&raw)[GROUPS][4], IdPack<IdT> (&idp)[GROUPS]) {
+#pragma unroll
+        for (int g = 0; g < GROUPS; g++) {
+            const size_t g4 = tile * (S::TILE / 4) + (size_t)g * WC_THREADS + tid;          // group of 4 consecutive samples
+            load_vals4(prm.vals, g4, raw[g]);
+            idp[g].load(ids, g4);
+        }
+    };
 
     for (size_t c = 0; c < nchunks; c++) {
         const size_t par = c & 1;
         unsigned short *qset = prm.queues + par * (size_t)P * P * cap;      // [owner][writer][cap]
         unsigned int *cset = prm.q_cnt + par * (size_t)P * P;              // [owner][writer]
-        if (tid < KP_MAX_PARTS) s_off[tid] = 0;
+        const bool last_chunk = c + 1 == nchunks;
         // ---------------- phase A: bin my slice of chunk c (I am writer p)
+        const size_t tile0 = c * chunk_tiles + (size_t)p * prm.slice_tiles;
+        if (tile0 < tiles_total) load_tile(tile0, cur, cur_id);
         for (uint32_t t = 0; t < prm.slice_tiles; t++) {
-            const size_t tile = c * chunk_tiles + (size_t)p * prm.slice_tiles + t;
+            const size_t tile = tile0 + t;
             if (tile >= tiles_total) break;                       // uniform per CTA
-            const size_t s0 = tile * KP_TILE;
-            if (tid < KP_MAX_PARTS) s_cnt[tid] = 0;
-            __syncthreads();
-            // Common path is branch-free: owner/record/position for every sample; samples that need anything
-            // else (id >= H, estimate too close to a boundary, |v| >= 2^63 / NaN / Inf, negative) raise one flag
-            // and are handled -- entirely, on the L2 route -- in a warp-voted fix-up.
-            uint32_t part[8], pos[8], rec[8];
-            bool any_rare = false;
+            if (t + 1 < prm.slice_tiles && tile + 1 < tiles_total) load_tile(tile + 1, nxt, nxt_id);
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const size_t g = s0 + (size_t)h * (KP_TILE / 2) + (size_t)tid * 4;   // 4 consecutive samples
-                uint32_t id4[4];
-                unsigned long long raw[4] = {0, 0, 0, 0};
-                const bool in = g < prm.n;                         // n is a multiple of 4
-                id4[0] = id4[1] = id4[2] = id4[3] = 0;
-                if (in) {
-                    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
-                                 : "=l"(raw[0]), "=l"(raw[1]), "=l"(raw[2]), "=l"(raw[3]) : "l"(vals + g * 8));
-                    if (sizeof(IdT) == 2) {
-                        unsigned int lo, hi;
-                        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi)
-                                     : "l"(reinterpret_cast<const char *>(ids) + g * 2));
-                        id4[0] = lo & 0xFFFFu; id4[1] = lo >> 16; id4[2] = hi & 0xFFFFu; id4[3] = hi >> 16;
-                    } else {
-                        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                     : "=r"(id4[0]), "=r"(id4[1]), "=r"(id4[2]), "=r"(id4[3])
-                                     : "l"(reinterpret_cast<const char *>(ids) + g * 4));
-                    }
-                }
+            for (int g = 0; g < GROUPS; g++) {
+                double v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) { ValT r; memcpy(&r, &cur[g][j], 8); v[j] = sample_to_f64<ValT>(r); }
+                uint32_t idx[4];
+                bool flag[4];
+                bucket_offsets_v2<4, false, 0>(v, pc, one_bits, idx, flag);      // slot indices (positive-only rows)
+                bool any = false;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const int q = h * 4 + j;
-                    const uint32_t id = id4[j];
-                    ValT rv;
-                    memcpy(&rv, &raw[j], 8);
-                    const double v = sample_to_f64<ValT>(rv);
-                    uint32_t idx; bool slow;
-                    fast_candidate(v, idx, slow);
-                    const bool rare = slow | (idx >= (uint32_t)LH_WIN) | (id >= prm.H);
-                    const uint32_t lid = __umulhi(id, prm.inv_p), owner = id - lid * (uint32_t)P;   // id / P, id % P
-                    rec[q] = lid * (uint32_t)LH_WIN + idx;
-                    // 0xFFFFFFFF = no record; 0xFFFFFFFE = rare (pending fix-up)
-                    part[q] = !in ? 0xFFFFFFFFu : rare ? 0xFFFFFFFEu : owner;
-                    any_rare |= in & rare;
-                    pos[q] = 0;
-                    if (in & !rare) pos[q] = atomicAdd(&s_cnt[owner], 1u);
+                    const uint32_t id = cur_id[g].get(j);
+                    const uint32_t lid = __umulhi(id, prm.inv_p), owner = id - lid * P;   // id / P, id % P
+                    const uint32_t rec = lid * pc.win + idx[j];
+                    const bool rare = flag[j] | (id >= prm.o.H);
+                    // branch-free append: rare samples draw from a trash counter / trash row
+                    const uint32_t oe = rare ? P : owner;
+                    uint32_t pos;
+                    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(fill_addr + oe * 4u) : "memory");
+                    const bool ok = pos < (uint32_t)S::CAP;
+                    const uint32_t slot = ok ? oe * (uint32_t)S::STRIDE + pos : trash_slot;
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(buf_addr + slot * 2u), "h"((unsigned short)rec) : "memory");
+                    flag[j] = rare | !ok;                                                  // !ok: buffer full (skewed ids), exact L2 route
+                    any |= flag[j];
                 }
-                if (__any_sync(0xFFFFFFFFu, any_rare)) {
+                if (__any_sync(0xFFFFFFFFu, any)) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int q = h * 4 + j;
-                        if (part[q] != 0xFFFFFFFEu) continue;
-                        part[q] = 0xFFFFFFFFu;
-                        ValT rv;
-                        memcpy(&rv, &raw[j], 8);
-                        keyed_one<ValT>(id4[j], rv, prm.H, prm.hot, prm.buckets, prm.dropped, pol);
-                    }
-                    any_rare = false;
+                    for (int j = 0; j < 4; j++)
+                        if (flag[j]) keyed_one_slow<ValT>(cur_id[g].get(j), cur[g][j], pc, prm.o, pol);
                 }
             }
             __syncthreads();
-            // exclusive scan of the per-owner counts (one warp, KP_SCAN_PER_LANE owners per lane)
-            if (warp == 0) {
-                unsigned int loc[KP_SCAN_PER_LANE], sum = 0;
-#pragma unroll
-                for (int k = 0; k < KP_SCAN_PER_LANE; k++) { int o = lane * KP_SCAN_PER_LANE + k; loc[k] = (o < P) ? s_cnt[o] : 0; sum += loc[k]; }
-                unsigned int incl = sum;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { unsigned int y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
-                unsigned int run = incl - sum;
-#pragma unroll
-                for (int k = 0; k < KP_SCAN_PER_LANE; k++) { int o = lane * KP_SCAN_PER_LANE + k; if (o < P) s_start[o] = run; run += loc[k]; }
-            }
-            __syncthreads();
-            {
-                const unsigned int wbase = (unsigned int)p * cap;
-                bool any_full = false;
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const uint32_t o = part[q];
-                    if (o < (uint32_t)KP_MAX_PARTS) {                   // has a record
-                        const unsigned int at = s_off[o] + pos[q];      // position inside my sub-queue for owner o
-                        const bool full = at >= cap;
-                        any_full |= full;
-                        if (!full) {
-                            const unsigned int si = s_start[o] + pos[q];
-                            s_rec[si] = (unsigned short)rec[q];
-                            s_dst[si] = o * ((unsigned int)P * cap) + wbase + at;
-                        }
+            // ---- flush: warp w takes owners w, w+16, ...; the 32 lanes copy each full 128-byte line to my sub-queue of
+            //      that owner with one coalesced 4-byte store each, then the remainder (< 64 records) moves to the front
+            for (uint32_t o = warp; o < P; o += NWARPS) {
+                const unsigned int n = min(s_fill[o], (unsigned int)S::CAP);
+                const unsigned int nfull = n / WC_LINE, rem = n - nfull * WC_LINE;
+                if (nfull == 0) { if (lane == 0) s_fill[o] = n; continue; }              // s_fill may have run past CAP
+                unsigned int off0 = s_off[o];
+                unsigned int *src = reinterpret_cast<unsigned int *>(s_buf + o * S::STRIDE);
+                unsigned int *dst = reinterpret_cast<unsigned int *>(qset + ((size_t)o * P + p) * cap + off0);
+                const unsigned int keep = src[nfull * 32 + lane];                          // the line holding the remainder
+                for (unsigned int l = 0; l < nfull; l++) {
+                    const unsigned int w = src[l * 32 + lane];
+                    if (off0 + WC_LINE <= cap) {
+                        dst[lane] = w;
+                        dst += 32;
+                        off0 += WC_LINE;
+                    } else {                                                               // sub-queue full: these records go the L2 route
+                        wc_spill(w & 0xFFFFu, o, P, pc, prm.o, pol);
+                        wc_spill(w >> 16, o, P, pc, prm.o, pol);
                     }
                 }
-                if (__any_sync(0xFFFFFFFFu, any_full)) {                // sub-queue full: those records take the L2 route
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const uint32_t o = part[q];
-                        if (o < (uint32_t)KP_MAX_PARTS && s_off[o] + pos[q] >= cap) {
-                            const uint32_t lid = rec[q] / (uint32_t)LH_WIN, slot = rec[q] - lid * (uint32_t)LH_WIN;
-                            red_add_u32_keep(&prm.hot[(size_t)(lid * (uint32_t)P + o) * LH_SUBHIST + slot], 1u, pol);
-                        }
-                    }
-                }
+                __syncwarp();
+                src[lane] = keep;
+                if (lane == 0) { s_off[o] = off0; s_fill[o] = rem; }
             }
             __syncthreads();
-            {   // copy out: consecutive threads write consecutive records of one owner's run
-                const unsigned int total = s_start[P - 1] + s_cnt[P - 1];
-                for (unsigned int i = tid; i < total; i += KP_THREADS) {
-                    const unsigned int d = s_dst[i];
-                    if (d != 0xFFFFFFFFu) { qset[d] = s_rec[i]; s_dst[i] = 0xFFFFFFFFu; }
-                }
+#pragma unroll
+            for (int g = 0; g < GROUPS; g++) {
+                cur_id[g] = nxt_id[g];
+#pragma unroll
+                for (int j = 0; j < 4; j++) cur[g][j] = nxt[g][j];
             }
-            if (tid < P) s_off[tid] += s_cnt[tid];
+        }
+        if (last_chunk) {   // the records still waiting in the buffers (< WC_LINE per owner) go out as one partial line
+            for (uint32_t o = warp; o < P; o += NWARPS) {
+                const unsigned int rem = s_fill[o];
+                if (!rem) continue;
+                const unsigned int off0 = s_off[o];
+                const unsigned int w = reinterpret_cast<unsigned int *>(s_buf + o * S::STRIDE)[lane];
+                if (off0 + WC_LINE <= cap) {
+                    reinterpret_cast<unsigned int *>(qset + ((size_t)o * P + p) * cap + off0)[lane] = w;
+                    if (lane == 0) s_off[o] = off0 + rem;
+                } else {
+                    if (2 * lane < rem) wc_spill(w & 0xFFFFu, o, P, pc, prm.o, pol);
+                    if (2 * lane + 1 < rem) wc_spill(w >> 16, o, P, pc, prm.o, pol);
+                }
+                __syncwarp();
+                if (lane == 0) s_fill[o] = 0;
+            }
             __syncthreads();
         }
-        // publish my P counts (zero for owners I sent nothing to), then the grid-wide barrier
-        if (tid < P) cset[(size_t)tid * P + p] = min(s_off[tid], cap);
-        kp_grid_barrier(prm.barrier, (unsigned int)((c + 1) * (size_t)P));
-        // ---------------- phase B: drain the P sub-queues I own; warp w takes writers w, w+32, ...
-        for (int w = warp; w < P; w += KP_THREADS / 32) {
-            unsigned int nrec = 0;
-            if (lane == 0) nrec = __ldcg(&cset[(size_t)p * P + w]);
-            nrec = __shfl_sync(0xFFFFFFFFu, nrec, 0);
-            const unsigned short *q = qset + ((size_t)p * P + w) * cap;
-            const unsigned int nvec = nrec / 8;
-            for (unsigned int i = lane; i < nvec; i += 32) {
-                const uint4 v4 = __ldcg(reinterpret_cast<const uint4 *>(q) + i);
+        // publish my P record counts (zero for owners I sent nothing to), then the grid-wide barrier
+        if (tid < P) { cset[(size_t)tid * P + p] = s_off[tid]; }
+        grid_barrier(prm.barrier, (unsigned int)((c + 1) * (size_t)P));
+        // ---------------- phase B: drain the P sub-queues I own.  The record counts go to shared memory first; then the
+        // P * vq 16-byte vectors of my region are dealt to the threads as ONE flat index space (vector v belongs to
+        // writer v / vq), so every thread has several independent L2 loads in flight instead of a count -> data chain.
+        if (tid < P) s_off[tid] = __ldcg(&cset[(size_t)p * P + tid]);
+        __syncthreads();
+        {
+            const uint4 *qv = reinterpret_cast<const uint4 *>(qset + (size_t)p * P * cap);
+            const uint32_t total = P * vq;
+#pragma unroll 4
+            for (uint32_t v = tid; v < total; v += WC_THREADS) {
+                const uint32_t w = __umulhi(v, prm.inv_vq), i = v - w * vq;               // writer, vector inside its sub-queue
+                const unsigned int cnt = s_off[w];
+                if (i * 8u >= cnt) continue;
+                const uint4 v4 = __ldcg(qv + v);
                 const unsigned int ww[4] = {v4.x, v4.y, v4.z, v4.w};
+                const unsigned int nrec = min(8u, cnt - i * 8u);
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    atomicAdd(&s_hist[ww[k] & 0xFFFFu], 1u);
-                    atomicAdd(&s_hist[ww[k] >> 16], 1u);
+                    if (2u * k < nrec) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + (ww[k] & 0xFFFFu) * 4u) : "memory");
+                    if (2u * k + 1 < nrec) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + (ww[k] >> 16) * 4u) : "memory");
                 }
             }
-            for (unsigned int i = nvec * 8 + lane; i < nrec; i += 32) atomicAdd(&s_hist[__ldcg(q + i)], 1u);
         }
-        // no barrier here: the next chunk writes the other parity; this parity is rewritten only after the
+        __syncthreads();
+        if (tid < P) s_off[tid] = 0;
+        // no grid barrier here: the next chunk writes the other parity; this parity is rewritten only after the
         // next grid barrier, which every CTA reaches after finishing this drain
     }
     __syncthreads();
     // ---------------- flush my windows into the uint32 hot window
-    for (size_t i = tid; i < hist_words; i += KP_THREADS) {
+    for (uint32_t i = tid; i < hist_words; i += WC_THREADS) {
         const unsigned int cnt = s_hist[i];
         if (!cnt) continue;
-        const uint32_t lid = (uint32_t)(i / LH_WIN), slot = (uint32_t)(i - (size_t)lid * LH_WIN);
-        const uint32_t id = lid * (uint32_t)P + (uint32_t)p;
-        if (id < prm.H) atomicAdd(&prm.hot[(size_t)id * LH_SUBHIST + slot], cnt);
+        const uint32_t lid = i / pc.win, slot = i - lid * pc.win;
+        const uint32_t id = lid * P + p;
+        if (id < prm.o.H) atomicAdd(&prm.o.hot[(size_t)id * (2u * pc.win) + slot], cnt);
     }
 }
 
 // Drain the hot window into the uint64 buckets.  atomicExch/atomicAdd so that ingest on other
 // streams may keep running against the same buffer.
-__global__ void k_fold_hot(unsigned int *__restrict__ hot, unsigned long long *__restrict__ buckets, size_t cells,
-                           uint32_t replicas) {
+__global__ void k_fold_hot(unsigned int *__restrict__ hot, unsigned long long *__restrict__ buckets, uint32_t *__restrict__ flags,
+                           size_t cells, uint32_t replicas, uint32_t win) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const uint32_t row = 2u * win;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += stride) {
         unsigned long long sum = 0;
         for (uint32_t r = 0; r < replicas; r++) {
@@ -893,9 +846,10 @@ __global__ void k_fold_hot(unsigned int *__restrict__ hot, unsigned long long *_
             if (*cell) sum += atomicExch(cell, 0u);
         }
         if (sum) {
-            size_t h = i / LH_SUBHIST;
-            uint32_t slot = (uint32_t)(i - h * LH_SUBHIST);
-            atomicAdd(&buckets[h * 65536u + slot_to_key16(slot)], sum);
+            size_t h = i / row;
+            uint32_t slot = (uint32_t)(i - h * row);
+            atomicAdd(&buckets[h * 65536u + slot_to_key16(slot, win)], sum);
+            mark(&flags[h], 1u);
         }
     }
 }
@@ -951,12 +905,13 @@ k_counter_add(const IdT *__restrict__ ids, const unsigned long long *__restrict_
 // into the bucket arrays: merging snapshots from other hosts / GPUs is the same commutative uint64 sum.
 __global__ void k_merge_sparse(const uint32_t *__restrict__ ids, const short *__restrict__ keys,
                                const unsigned long long *__restrict__ counts, size_t n, uint32_t H,
-                               unsigned long long *__restrict__ buckets, unsigned long long *__restrict__ dropped) {
+                               unsigned long long *__restrict__ buckets, uint32_t *__restrict__ flags,
+                               unsigned long long *__restrict__ dropped, uint32_t win) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint32_t id = ids[i];
         if (id >= H) { atomicAdd(dropped, 1ull); continue; }
-        atomicAdd(&buckets[(size_t)id * 65536u + ((uint32_t)(int)keys[i] & 0xFFFFu)], counts[i]);
+        add_bucket_global(buckets + (size_t)id * 65536u, flags + id, (uint32_t)(int)keys[i] & 0xFFFFu, counts[i], win);
     }
 }
 
@@ -969,11 +924,19 @@ __global__ void k_merge_sparse(const uint32_t *__restrict__ ids, const short *__
 // percentile's crossing walks its rows again (L2 hits) with a warp prefix sum
 // and applies the reference's rule float64(sofar)/float64(total) >= p
 // (metrics.go:413) to non-empty buckets only.
+// The histogram's flag prunes the scan: untouched histograms are answered without reading a bucket, and when
+// every count lies in the fast window only the (at most 6) warps that overlap it read anything.
 constexpr int K3_THREADS = 1024;
 constexpr int K3_WARP_KEYS = 2048;
 
+__device__ __forceinline__ bool warp_scans(int key0, uint32_t level, uint32_t win) {
+    if (level & 2u) return true;
+    return key0 <= (int)win - 1 && key0 + K3_WARP_KEYS - 1 >= -((int)win - 1);
+}
+
 __global__ void __launch_bounds__(K3_THREADS)
-k_reduce(const unsigned long long *__restrict__ buckets, const double *__restrict__ decomp,
+k_reduce(const unsigned long long *__restrict__ buckets, const uint32_t *__restrict__ flags, uint32_t win,
+         const double *__restrict__ decomp,
          const double *__restrict__ ps, int np, unsigned long long *__restrict__ out_count,
          double *__restrict__ out_sum, double *__restrict__ out_avg, int *__restrict__ out_pkeys,
          double *__restrict__ out_pvals, uint32_t *__restrict__ out_nnz) {
@@ -984,17 +947,31 @@ k_reduce(const unsigned long long *__restrict__ buckets, const double *__restric
     __shared__ int s_owner[LH_MAX_PCT];
     __shared__ unsigned long long s_total;
     const int h = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t level = flags[h];
+    if (level == 0) {   // untouched this interval: the caller reports the histogram as absent
+        if (t == 0) {
+            out_count[h] = 0; out_sum[h] = 0.0; out_avg[h] = __longlong_as_double(0x7FF8000000000000ll); out_nnz[h] = 0;
+            for (int j = 0; j < np; j++) {
+                out_pkeys[(size_t)h * np + j] = (int)0x80000000;
+                out_pvals[(size_t)h * np + j] = __longlong_as_double(0x7FF8000000000000ll);
+            }
+        }
+        return;
+    }
     const unsigned long long *hb = buckets + (size_t)h * 65536u;
     const int key0 = -32768 + warp * K3_WARP_KEYS;
+    const bool scans = warp_scans(key0, level, win);
 
     unsigned long long mine = 0;
     double msum = 0.0;
     unsigned int nnz = 0;
+    if (scans) {
 #pragma unroll 16
-    for (int r = 0; r < K3_WARP_KEYS / 32; r++) {      // 16 independent 256-byte rows in flight per warp
-        unsigned int slot = (unsigned int)(key0 + r * 32 + lane) & 0xFFFFu;
-        unsigned long long c = hb[slot];
-        if (c) { mine += c; msum += decomp[slot] * (double)c; nnz++; }
+        for (int r = 0; r < K3_WARP_KEYS / 32; r++) {      // 16 independent 256-byte rows in flight per warp
+            unsigned int slot = (unsigned int)(key0 + r * 32 + lane) & 0xFFFFu;
+            unsigned long long c = hb[slot];
+            if (c) { mine += c; msum += decomp[slot] * (double)c; nnz++; }
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -1093,16 +1070,21 @@ __global__ void k_scan_nnz(const uint32_t *__restrict__ nnz, uint32_t H, uint32_
 }
 
 __global__ void __launch_bounds__(K3_THREADS)
-k_export(const unsigned long long *__restrict__ buckets, const uint32_t *__restrict__ offsets,
-         short *__restrict__ out_keys, unsigned long long *__restrict__ out_counts) {
+k_export(const unsigned long long *__restrict__ buckets, const uint32_t *__restrict__ flags, uint32_t win,
+         const uint32_t *__restrict__ offsets, short *__restrict__ out_keys, unsigned long long *__restrict__ out_counts) {
     __shared__ unsigned int s_warp[32];
     const int h = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t level = flags[h];
+    if (level == 0) return;
     const unsigned long long *hb = buckets + (size_t)h * 65536u;
     const int key0 = -32768 + warp * K3_WARP_KEYS;
+    const bool scans = warp_scans(key0, level, win);
     unsigned int nnz = 0;
+    if (scans) {
 #pragma unroll 4
-    for (int r = 0; r < K3_WARP_KEYS / 32; r++)
-        nnz += __popc(__ballot_sync(0xFFFFFFFFu, hb[(unsigned int)(key0 + r * 32 + lane) & 0xFFFFu] != 0));
+        for (int r = 0; r < K3_WARP_KEYS / 32; r++)
+            nnz += __popc(__ballot_sync(0xFFFFFFFFu, hb[(unsigned int)(key0 + r * 32 + lane) & 0xFFFFu] != 0));
+    }
     if (lane == 0) s_warp[warp] = nnz;     // every lane holds the warp total
     __syncthreads();
     if (warp == 0) {
@@ -1127,28 +1109,187 @@ k_export(const unsigned long long *__restrict__ buckets, const uint32_t *__restr
     }
 }
 
+// Zero what an interval wrote: per touched histogram its window cells (all 65536 when it holds out-of-window
+// counts), then its flag.  Replaces a memset of the whole uint64[H][65536] array (512 MiB at H = 1024).
+// Window cell i of 2*win-1: i < win -> key i; otherwise key -(i - win + 1), i.e. index 65536 - (i - win + 1).
+__device__ __forceinline__ uint32_t window_cell(uint32_t i, uint32_t win) { return i < win ? i : 65536u - (i - win + 1u); }
+
+__global__ void __launch_bounds__(256)
+k_clear_touched(unsigned long long *__restrict__ buckets, uint32_t *__restrict__ flags, uint32_t win) {
+    const uint32_t h = blockIdx.x;
+    const uint32_t level = flags[h];
+    if (level == 0) return;
+    unsigned long long *hb = buckets + (size_t)h * 65536u;
+    if (level & 2u) {
+        for (uint32_t i = threadIdx.x; i < 65536u; i += 256) hb[i] = 0ull;
+    } else {
+        for (uint32_t i = threadIdx.x; i < 2u * win - 1u; i += 256) hb[window_cell(i, win)] = 0ull;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) flags[h] = 0;
+}
+
+// ---------------------------------------------------------------------- K5
+// Multi-GPU snapshot: one small kernel per rank sums, for every histogram some rank touched, the window cells of
+// ALL ranks' frozen arrays (peer-mapped device memory: direct NVLink loads, no staging copy, no library
+// collective) into this rank's `out` arrays, so every rank ends with the global histogram (the "tiny all-reduce of
+// the ~4K-entry bucket arrays").  uint64 sums are associative: bit-identical to a single-GPU run.
+// Protocol (comm block = uint64[32] per rank, slot r written only by rank r):
+//   arrive[r]  rank r's frozen arrays for snapshot `seq` are complete      (pushed into every peer's block)
+//   depart[r]  rank r has finished reading this rank's arrays for `seq`    (pushed when its last CTA is done)
+// The kernel ends only after every peer departed, so the caller may clear its frozen arrays right after it.
+// token = seq*2 + frozen buffer index: ranks must take their snapshots in lock-step (same count, same order).
+static_assert(LH_MAX_RANKS == 16, "comm block layout assumes 16 ranks");
+constexpr int K5_THREADS = 1024;
+constexpr int K5_CHUNK = 2 * K5_THREADS;     // cells per work item
+
+struct PeerParams {
+    uint32_t rank, world, H, C, win, do_counters, frozen, pad;
+    unsigned long long seq;
+    unsigned long long timeout_ns;
+    const unsigned long long *buckets[LH_MAX_RANKS];     // every rank's FROZEN uint64[H][65536] (own rank: local pointer)
+    const uint32_t *flags[LH_MAX_RANKS];
+    const unsigned long long *counters[LH_MAX_RANKS];
+    unsigned long long *comm[LH_MAX_RANKS];               // every rank's comm block
+    unsigned long long *out_buckets;                      // this rank's reduced arrays (zero outside what is written)
+    uint32_t *out_flags;
+    unsigned long long *out_counters;
+    unsigned int *block_counter;                          // local, zero between launches
+    unsigned int *status;                                 // local: 1 = a peer never arrived, 2 = buffer parity mismatch
+    unsigned long long *cells;                            // local: cells summed by this launch (zeroed by the host)
+};
+
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_sys_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until slot >= token (tokens grow with the snapshot sequence); false on timeout
+__device__ __forceinline__ bool wait_token(const unsigned long long *slot, unsigned long long token, unsigned long long timeout_ns,
+                                           unsigned long long *seen) {
+    const unsigned long long t0 = global_timer_ns();
+    unsigned int spins = 0;
+    for (;;) {
+        const unsigned long long v = ld_acquire_sys_u64(slot);
+        if ((v >> 1) >= (token >> 1)) { *seen = v; return true; }
+        if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > timeout_ns) return false;
+    }
+}
+
+__global__ void __launch_bounds__(K5_THREADS)
+k_peer_allreduce(PeerParams p) {
+    __shared__ uint32_t s_level;
+    __shared__ uint32_t s_lv[LH_MAX_RANKS];
+    const uint32_t t = threadIdx.x;
+    const unsigned long long token = p.seq * 2ull + p.frozen;
+    unsigned long long *mine = p.comm[p.rank];
+    // 1. announce: my frozen arrays were completed by earlier kernels on this stream
+    if (blockIdx.x == 0 && t < p.world && t != p.rank) {
+        __threadfence_system();
+        st_release_sys_u64(p.comm[t] + p.rank, token);
+    }
+    // 2. wait until every peer announced the same snapshot
+    if (t < p.world && t != p.rank) {
+        unsigned long long seen = 0;
+        if (!wait_token(mine + t, token, p.timeout_ns, &seen)) atomicMax(p.status, 1u);
+        else if ((seen >> 1) == p.seq && (seen & 1ull) != p.frozen) atomicMax(p.status, 2u);
+    }
+    __syncthreads();
+    const bool ok = ld_sys_u32(p.status) == 0;
+    // 3. sum.  Work item = (histogram, chunk of K5_CHUNK cells); the set of cells follows the OR of all ranks' flags.
+    if (ok) {
+        const uint32_t wcells = 2u * p.win - 1u;
+        const uint32_t chunks_w = (wcells + K5_CHUNK - 1) / K5_CHUNK, chunks_all = 65536u / K5_CHUNK;
+        const uint32_t per_h = chunks_all;                   // items are indexed as if every histogram were dense
+        for (uint32_t item = blockIdx.x; item < p.H * per_h; item += gridDim.x) {
+            const uint32_t h = item / per_h, chunk = item - h * per_h;
+            __syncthreads();
+            if (t < p.world) s_lv[t] = ld_sys_u32(p.flags[t] + h);
+            __syncthreads();
+            if (t == 0) { uint32_t lv = 0; for (uint32_t r = 0; r < p.world; r++) lv |= s_lv[r]; s_level = lv; }
+            __syncthreads();
+            const uint32_t level = s_level;
+            if (level == 0) continue;
+            const bool dense = (level & 2u) != 0;
+            if (!dense && chunk >= chunks_w) continue;
+            const uint32_t ncell = dense ? 65536u : wcells;
+            if (chunk == 0 && t == 0) { p.out_flags[h] = level; atomicAdd(p.cells, (unsigned long long)ncell); }
+#pragma unroll
+            for (int k = 0; k < K5_CHUNK / K5_THREADS; k++) {
+                const uint32_t i = chunk * K5_CHUNK + k * K5_THREADS + t;
+                if (i >= ncell) continue;
+                const size_t cell = (size_t)h * 65536u + (dense ? i : window_cell(i, p.win));
+                unsigned long long sum = 0;
+                for (uint32_t r = 0; r < p.world; r++) sum += ld_sys_u64(p.buckets[r] + cell);
+                if (sum) p.out_buckets[cell] = sum;
+            }
+        }
+        if (p.do_counters && blockIdx.x == 0) {
+            for (uint32_t i = t; i < p.C; i += K5_THREADS) {
+                unsigned long long sum = 0;
+                for (uint32_t r = 0; r < p.world; r++) sum += ld_sys_u64(p.counters[r] + i);
+                p.out_counters[i] = sum;
+            }
+        }
+    }
+    // 4. depart: the last CTA of this rank tells every peer it has finished reading them, then waits until
+    //    every peer has finished reading this rank
+    __syncthreads();
+    __shared__ bool s_last;
+    if (t == 0) {
+        __threadfence();
+        s_last = atomicAdd(p.block_counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (t == 0) *p.block_counter = 0;
+    if (t < p.world && t != p.rank) {
+        st_release_sys_u64(p.comm[t] + LH_MAX_RANKS + p.rank, token);
+        unsigned long long seen = 0;
+        if (!wait_token(mine + LH_MAX_RANKS + t, token, p.timeout_ns, &seen)) atomicMax(p.status, 1u);
+    }
+}
+
 // ----------------------------------------------------------- probes / tables
-__global__ void k_fill_decompress(double *__restrict__ table) {
+__global__ void k_fill_decompress(double *__restrict__ table, double precision) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 65536) table[i] = go_decompress((int)(short)i);
+    if (i < 65536) table[i] = go_decompress((int)(short)i, precision);
 }
 
-__global__ void k_compress_probe(const double *__restrict__ v, size_t n, short *__restrict__ out, int mode) {
+__global__ void k_compress_probe(const double *__restrict__ v, size_t n, short *__restrict__ out, int mode, Prec pc) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (short)(mode == 1 ? exact_key16(v[i]) : key16_of(v[i]));
+    if (i < n) out[i] = (short)(mode == 1 ? exact_key16(v[i], pc.precision) : key16_of(v[i], pc));
 }
 
-// max | estimate - 100 ln(x) | over samples inside the fast window, for both estimators that ship:
+// max | estimate - precision*ln(x) | over samples inside the fast window, for both estimators that ship:
 //   [0] fast_candidate()      (k_ingest_keyed*, probes, ragged tails)
-//   [2] bucket_samples_v2()   (packed-FP32 form with the -1023*c2 constant folded into the FMA; K1, keyed_small)
+//   [2] bucket_offsets_v2()   (packed-FP32 form with the -1023*c2 constant folded into the FMA; K1, keyed_small, keyed_wc)
 // plus [1] the tally of samples fast_candidate() sends to the exact path.
-__global__ void k_fastpath_margin(const double *__restrict__ v, size_t n, unsigned long long *__restrict__ out) {
+__global__ void k_fastpath_margin(const double *__restrict__ v, size_t n, unsigned long long *__restrict__ out, Prec pc) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double x = __dadd_rn(1.0, fabs(v[i]));
     uint32_t hi = (uint32_t)__double2hiint(x), lo = (uint32_t)__double2loint(x);
     uint32_t idx; bool slow;
-    fast_candidate(v[i], idx, slow);
+    fast_candidate(v[i], pc, idx, slow);
     if (slow) atomicAdd(&out[1], 1ull);
     if (hi >= 0x43E00000u) return;
     uint32_t t = __funnelshift_l(lo, hi, 3);
@@ -1156,18 +1297,16 @@ __global__ void k_fastpath_margin(const double *__restrict__ v, size_t n, unsign
     float lg;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(m));
     uint32_t eb = hi >> 20;
-    const double truth = 100.0 * log(x);
-    const double base = (double)(int)(eb - 1023u) * 69.0;
+    const double truth = pc.precision * log(x);
+    const double base = (double)(int)(eb - 1023u) * (double)pc.a_int;
     {   // estimator 1
         float ef = __fadd_rn(__uint_as_float(0x4B000000u | eb), -(8388608.0f + 1023.0f));
-        float w = __fmaf_rn(lg, 69.31471805599453f, __fmul_rn(ef, 0.31471805599453f));
+        float w = __fmaf_rn(lg, pc.c1, __fmul_rn(ef, pc.c2));
         atomicMax(&out[0], (unsigned long long)__double_as_longlong(fabs(base + (double)w - truth)));
     }
-    {   // estimator 2 (same constants as bucket_samples_v2 / k_ingest_keyed_small)
-        constexpr float C1 = 69.31471805599453f, C2 = 0.31471805599453f;
-        constexpr float KB = (float)(-1023.0 * (double)C2);
-        float a = __fmaf_rn(__uint2float_rn(eb), C2, KB);
-        float w = __fmaf_rn(lg, C1, a);
+    {   // estimator 2 (same constants as bucket_offsets_v2)
+        float a = __fmaf_rn(__uint2float_rn(eb), pc.c2, pc.kb);
+        float w = __fmaf_rn(lg, pc.c1, a);
         atomicMax(&out[2], (unsigned long long)__double_as_longlong(fabs(base + (double)w - truth)));
     }
 }
@@ -1198,6 +1337,7 @@ __device__ __forceinline__ uint64_t stream_bits(int kind, uint64_t seed, uint64_
         return (uint64_t)__double2ll_rz(d);
     }
     case 7: return 1 + (u >> 60);   // counter amounts 1..16
+    case 8: return ((u >> 11) & 0x8000000000000000ull) | ((uint64_t)(1023 + (u >> 52) % 63) << 52) | mant;   // N: stream U, random sign
     default: return u;
     }
 }

@@ -86,6 +86,17 @@ class ShardedEngine:
             self._views[ptr] = t
         return t
 
+    def _tensor32(self, ptr: int, words: int):
+        import torch
+        key = ("i32", ptr)
+        t = self._views.get(key)
+        if t is None or t.numel() != words:
+            view = _CudaView(ptr, words)
+            view.__cuda_array_interface__["typestr"] = "<i4"
+            t = torch.as_tensor(view, device="cuda:%d" % self.device_index)
+            self._views[key] = t
+        return t
+
     def _allreduce_frozen(self, counters: bool):
         """Enqueue the collective for the open snapshot; returns what allreduce_ms() needs to time it."""
         eng = self.engine
@@ -103,6 +114,9 @@ class ShardedEngine:
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(ext)
             allreduce_sum_u64(self._tensor(int(v.d_buckets), int(v.n_bucket_words)), self.group)
+            # the per-histogram flags (0 / 1 / 3) tell the reduction kernels what to scan: OR over ranks == MAX
+            import torch.distributed as dist
+            dist.all_reduce(self._tensor32(int(v.d_flags), int(v.n_flag_words)), op=dist.ReduceOp.MAX, group=self.group)
             if counters:
                 allreduce_sum_u64(self._tensor(int(v.d_counters), int(v.n_counter_words)), self.group)
             e1.record(ext)

@@ -135,11 +135,11 @@ class Sparse:
 
 class Engine:
     def __init__(self, device: int = 0, max_histograms: int = 1, max_counters: int = 1,
-                 staging_bytes: int = 0, staging_slots: int = 0):
+                 staging_bytes: int = 0, staging_slots: int = 0, precision: int = 0):
         self.lib = L.load()
         self.h = None
         cfg = L.lh_config(C.sizeof(L.lh_config), device, max_histograms, max_counters,
-                          staging_bytes, staging_slots, 0)
+                          staging_bytes, staging_slots, 0, precision)
         h = C.c_void_p()
         st = self.lib.lh_create(C.byref(cfg), C.byref(h))
         if st != L.LH_OK:
@@ -201,13 +201,36 @@ class Engine:
         return self.lib.lh_k1_variant_name(self.h, self.lib.lh_k1_variant_current(self.h)).decode()
 
     def keyed_kernel_name(self) -> str:
-        """Name of the kernel lh_ingest_keyed_* dispatches to for this context's histogram count."""
-        fn = getattr(self.lib, "lh_keyed_kernel_name", None)
-        if fn is None:
-            return "k_ingest_keyed_vec" if self.H > 44 else "k_ingest_keyed_small"
-        fn.restype = C.c_char_p
-        fn.argtypes = [C.c_void_p]
-        return fn(self.h).decode()
+        """Name of the kernel the most recent keyed ingest dispatched to."""
+        return self.lib.lh_keyed_kernel_name(self.h).decode()
+
+    # ---- multi-GPU (peer-memory all-reduce behind the ABI)
+    def comm_export(self) -> bytes:
+        buf = C.create_string_buffer(L.LH_PEER_HANDLE_BYTES)
+        self._check(self.lib.lh_comm_export(self.h, buf))
+        return buf.raw
+
+    def comm_import(self, rank: int, world: int, handles: bytes):
+        assert len(handles) == world * L.LH_PEER_HANDLE_BYTES
+        self._check(self.lib.lh_comm_import(self.h, rank, world, C.c_char_p(handles)))
+
+    def snapshot_allreduce(self, counters: bool = False) -> int:
+        seq = C.c_uint64()
+        self._check(self.lib.lh_snapshot_allreduce(self.h, 1 if counters else 0, C.byref(seq)))
+        return int(seq.value)
+
+    def comm_allreduce_ms(self, seq: int) -> float:
+        ms = C.c_float()
+        self._check(self.lib.lh_comm_allreduce_ms(self.h, seq, C.byref(ms)))
+        return float(ms.value)
+
+    def comm_info(self) -> dict:
+        st = L.lh_comm_stats()
+        self._check(self.lib.lh_comm_info(self.h, C.byref(st)))
+        return {f: int(getattr(st, f)) for f, _ in L.lh_comm_stats._fields_ if f != "reserved"}
+
+    def comm_last_bytes(self) -> int:
+        return self.comm_info()["last_bytes_from_peers"]
 
     def last_kernel_ms(self) -> float:
         ms = C.c_float()

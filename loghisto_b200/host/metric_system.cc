@@ -47,10 +47,63 @@ size_t this_thread_slot(size_t n) {
     return mine % n;
 }
 
+// ---- per-thread name -> id cache --------------------------------------------------------------------------
+// The reference pays an RWMutex RLock/RUnlock (two atomic RMWs on ONE shared cache line) plus two string-hashed
+// map lookups per sample (metrics.go:275-279); that line ping-pongs between cores and caps multi-core ingest.
+// Here the steady-state lookup touches only thread-local memory: a direct-mapped cache keyed by the hash of the
+// name's bytes, verified byte for byte (a collision can never send a sample to the wrong histogram).  A miss falls
+// back to the shared intern table (the reference's RLock / double-checked Lock idiom, metrics.go:275-294).
+inline uint64_t hash_bytes(const char *p, size_t n) {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xFF51AFD7ED558CCDull);
+    while (n >= 8) {
+        uint64_t w;
+        memcpy(&w, p, 8);
+        h = (h ^ w) * 0xC2B2AE3D27D4EB4Full;
+        h ^= h >> 29;
+        p += 8; n -= 8;
+    }
+    if (n) {
+        uint64_t w = 0;
+        memcpy(&w, p, n);
+        h = (h ^ w) * 0xC2B2AE3D27D4EB4Full;
+        h ^= h >> 29;
+    }
+    return h ^ (h >> 32);
+}
+
+struct NameCache {
+    static constexpr size_t kEntries = 2048;     // direct-mapped; >= the default max_histograms
+    struct Entry { uint64_t hash = 0; uint32_t id = 0; bool used = false; std::string name; };
+    uint64_t system_id = 0;                      // which MetricSystem the entries belong to
+    std::vector<Entry> e;
+    bool find(uint64_t h, const char *p, size_t n, uint32_t *id) const {
+        if (e.empty()) return false;
+        const Entry &x = e[h & (kEntries - 1)];
+        if (!x.used || x.hash != h || x.name.size() != n || memcmp(x.name.data(), p, n) != 0) return false;
+        *id = x.id;
+        return true;
+    }
+    void put(uint64_t h, const char *p, size_t n, uint32_t id) {
+        if (e.empty()) e.resize(kEntries);
+        Entry &x = e[h & (kEntries - 1)];
+        x.hash = h; x.id = id; x.used = true; x.name.assign(p, n);
+    }
+    void reset(uint64_t sys) { system_id = sys; e.clear(); }
+};
+thread_local NameCache tl_hcache, tl_ccache;
+
+std::atomic<uint64_t> g_system_ids{1};
+
 }  // namespace
 
+// One staging shard: a pinned staging slot for (id, value) samples and one for (id, amount) counter ops, filled
+// with plain stores.  Threads map onto shards round-robin (one shard per hardware thread by default), so in the
+// steady state a shard has ONE writer and its spinlock is uncontended (an exchange and a store, ~10 ns); the reaper
+// takes it once per interval to commit whatever is open.
 struct MetricSystem::Shard {
-    std::mutex mu;
+    std::atomic_flag busy = ATOMIC_FLAG_INIT;
+    void lock() { while (busy.test_and_set(std::memory_order_acquire)) { __builtin_ia32_pause(); } }
+    void unlock() { busy.clear(std::memory_order_release); }
     // histogram / timer samples
     lh_staging hs{};
     bool h_open = false;
@@ -63,11 +116,30 @@ struct MetricSystem::Shard {
     size_t c_n = 0, c_cap = 0;
     uint64_t *c_amounts = nullptr;
     uint16_t *c_ids = nullptr;
+    std::vector<uint8_t> c_touched;      // [max_counters] Counter(name, x) was called this interval, even with x == 0
+    bool c_any_touched = false;
+    uint64_t dropped = 0;                // samples lost to a failed staging call (never silent: dropped_samples())
+    char pad[64];                        // keep neighbouring shards off this one's cache lines
 };
+
+namespace {
+struct ShardGuard {
+    MetricSystem::Shard &s;
+    explicit ShardGuard(MetricSystem::Shard &sh) : s(sh) { s.lock(); }
+    ~ShardGuard() { s.unlock(); }
+};
+void log_once(std::atomic<bool> &flag, lh_ctx *ctx, lh_status st, const char *what) {
+    if (!flag.exchange(true))
+        fprintf(stderr, "loghisto: %s failed: %s (%s); samples are being dropped and counted\n", what, lh_strerror(st),
+                ctx ? lh_last_error(ctx) : "");
+}
+std::atomic<bool> g_logged_staging{false};
+}  // namespace
 
 std::chrono::nanoseconds TimerToken::Stop() {
     auto d = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - Start);
-    System->Histogram(Name, (double)d.count());   // float64(duration.Nanoseconds())
+    if (id_valid) System->histogram_id(id, (double)d.count());   // float64(duration.Nanoseconds()); name interned by StartTimer
+    else System->Histogram(Name, (double)d.count());
     return d;
 }
 
@@ -75,17 +147,23 @@ MetricSystem::MetricSystem(std::chrono::nanoseconds interval, bool /*sysStats*/,
     : interval_(interval.count() > 0 ? interval : std::chrono::nanoseconds(1)), opt_(opt) {
     percentiles_ = {{"%s_min", 0.0}, {"%s_50", .5}, {"%s_75", .75}, {"%s_90", .9}, {"%s_95", .95},
                     {"%s_99", .99}, {"%s_99.9", .999}, {"%s_99.99", .9999}, {"%s_max", 1.0}};   // metrics.go:145-155
-    uint32_t nshards = opt.shards ? opt.shards : std::min<uint32_t>(std::max(1u, std::thread::hardware_concurrency()), 8u);
+    // one shard per hardware thread: goroutines of print_benchmark.go:59-67 become OS threads here, each with its own
+    uint32_t nshards = opt.shards ? opt.shards : std::min<uint32_t>(std::max(1u, std::thread::hardware_concurrency()), 256u);
+    system_id_ = g_system_ids.fetch_add(1);
     lh_config cfg{};
     cfg.struct_size = sizeof(cfg);
     cfg.device = opt.device;
     cfg.max_histograms = opt.max_histograms;
     cfg.max_counters = opt.max_counters;
     cfg.staging_bytes = opt.staging_bytes;
-    cfg.staging_slots = 2 * nshards + 2;   // every shard may hold one histogram and one counter slot
+    cfg.staging_slots = 2 * nshards + 2;   // every shard may hold one histogram and one counter slot (memory is allocated on first use)
+    cfg.precision = opt.precision;
     lh_status st = lh_create(&cfg, &ctx_);
     if (st != LH_OK) throw std::runtime_error(std::string("lh_create: ") + lh_strerror(st));
-    for (uint32_t i = 0; i < nshards; i++) shards_.emplace_back(new Shard());
+    for (uint32_t i = 0; i < nshards; i++) {
+        shards_.emplace_back(new Shard());
+        shards_.back()->c_touched.assign(opt.max_counters, 0);
+    }
 }
 
 MetricSystem::~MetricSystem() {
@@ -118,18 +196,38 @@ uint16_t MetricSystem::intern(std::shared_mutex &mu, std::unordered_map<std::str
     return (uint16_t)id;
 }
 
-void MetricSystem::Histogram(const std::string &name, double value) {
+// name -> dense id through the calling thread's cache; false when the name table is full (sample dropped, counted)
+bool MetricSystem::lookup_histogram(const char *p, size_t n, uint32_t *id) {
+    if (tl_hcache.system_id != system_id_) tl_hcache.reset(system_id_);
+    const uint64_t h = hash_bytes(p, n);
+    if (tl_hcache.find(h, p, n, id)) return true;
     bool ok;
-    uint16_t id = intern(histo_mu_, histo_ids_, histo_names_, name, opt_.max_histograms, &ok);
-    if (!ok) {   // never fail the caller: drop and count (metrics.go's "drop and log" philosophy)
-        std::lock_guard<std::mutex> lk(counter_store_mu_);
-        dropped_over_limit_++;
-        return;
-    }
+    const uint16_t v = intern(histo_mu_, histo_ids_, histo_names_, std::string(p, n), opt_.max_histograms, &ok);
+    if (!ok) { dropped_over_limit_.fetch_add(1, std::memory_order_relaxed); return false; }
+    tl_hcache.put(h, p, n, v);
+    *id = v;
+    return true;
+}
+bool MetricSystem::lookup_counter(const char *p, size_t n, uint32_t *id) {
+    if (tl_ccache.system_id != system_id_) tl_ccache.reset(system_id_);
+    const uint64_t h = hash_bytes(p, n);
+    if (tl_ccache.find(h, p, n, id)) return true;
+    bool ok;
+    const uint16_t v = intern(counter_mu_, counter_ids_, counter_names_, std::string(p, n), opt_.max_counters, &ok);
+    if (!ok) { dropped_over_limit_.fetch_add(1, std::memory_order_relaxed); return false; }
+    tl_ccache.put(h, p, n, v);
+    *id = v;
+    return true;
+}
+
+// Ingest never fails the caller and never throws (metrics.go:570-573, 632-636: problems are logged and data is
+// dropped): a staging call that fails resets the shard, counts the samples it held as dropped and logs once.
+void MetricSystem::histogram_id(uint32_t id, double value) noexcept {
     Shard &s = *shards_[this_thread_slot(shards_.size())];
-    std::lock_guard<std::mutex> lk(s.mu);
+    ShardGuard g(s);
     if (!s.h_open) {
-        check(ctx_, lh_staging_acquire(ctx_, &s.hs), "lh_staging_acquire");
+        lh_status st = lh_staging_acquire(ctx_, &s.hs);
+        if (st != LH_OK) { s.dropped++; log_once(g_logged_staging, ctx_, st, "lh_staging_acquire"); return; }
         s.h_cap = ((size_t)s.hs.bytes / 10) & ~(size_t)15;
         s.h_vals = reinterpret_cast<double *>(s.hs.host);
         s.h_ids = reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(s.hs.host) + s.h_cap * 8);
@@ -137,25 +235,56 @@ void MetricSystem::Histogram(const std::string &name, double value) {
         s.h_open = true;
     }
     s.h_vals[s.h_n] = value;
-    s.h_ids[s.h_n] = id;
-    if (++s.h_n == s.h_cap) {
-        check(ctx_, lh_staging_commit_keyed_f64_u16(ctx_, &s.hs, s.h_n, s.h_cap * 8), "lh_staging_commit_keyed_f64_u16");
-        s.h_open = false;
-    }
+    s.h_ids[s.h_n] = (uint16_t)id;
+    if (++s.h_n == s.h_cap) commit_histograms(s);
 }
 
-void MetricSystem::Counter(const std::string &name, uint64_t amount) {
-    bool ok;
-    uint16_t id = intern(counter_mu_, counter_ids_, counter_names_, name, opt_.max_counters, &ok);
-    if (!ok) {
-        std::lock_guard<std::mutex> lk(counter_store_mu_);
-        dropped_over_limit_++;
-        return;
+void MetricSystem::commit_histograms(Shard &s) noexcept {
+    if (!s.h_open) return;
+    lh_status st = lh_staging_commit_keyed_f64_u16(ctx_, &s.hs, s.h_n, s.h_cap * 8);
+    if (st != LH_OK) {
+        s.dropped += s.h_n;
+        log_once(g_logged_staging, ctx_, st, "lh_staging_commit_keyed_f64_u16");
+        lh_staging_abandon(ctx_, &s.hs);      // harmless if the commit already recycled the slot
     }
+    s.h_open = false;
+    s.h_n = 0;
+}
+
+void MetricSystem::commit_counters(Shard &s) noexcept {
+    if (!s.c_open) return;
+    lh_status st = lh_staging_commit_counter_u16(ctx_, &s.cs, s.c_n, s.c_cap * 8);
+    if (st != LH_OK) {
+        s.dropped += s.c_n;
+        log_once(g_logged_staging, ctx_, st, "lh_staging_commit_counter_u16");
+        lh_staging_abandon(ctx_, &s.cs);
+    }
+    s.c_open = false;
+    s.c_n = 0;
+}
+
+void MetricSystem::Histogram(const std::string &name, double value) noexcept {
+    uint32_t id;
+    if (!lookup_histogram(name.data(), name.size(), &id)) return;   // name table full: dropped and counted
+    histogram_id(id, value);
+}
+void MetricSystem::Histogram(const char *name, size_t len, double value) noexcept {
+    uint32_t id;
+    if (!lookup_histogram(name, len, &id)) return;
+    histogram_id(id, value);
+}
+
+void MetricSystem::Counter(const std::string &name, uint64_t amount) noexcept {
+    uint32_t id;
+    if (!lookup_counter(name.data(), name.size(), &id)) return;
     Shard &s = *shards_[this_thread_slot(shards_.size())];
-    std::lock_guard<std::mutex> lk(s.mu);
+    ShardGuard g(s);
+    s.c_touched[id] = 1;                    // Counter(name, 0) still makes the name appear in Rates (metrics.go:430-433)
+    s.c_any_touched = true;
+    if (amount == 0) return;                // nothing to add on the device
     if (!s.c_open) {
-        check(ctx_, lh_staging_acquire(ctx_, &s.cs), "lh_staging_acquire");
+        lh_status st = lh_staging_acquire(ctx_, &s.cs);
+        if (st != LH_OK) { s.dropped++; log_once(g_logged_staging, ctx_, st, "lh_staging_acquire"); return; }
         s.c_cap = ((size_t)s.cs.bytes / 10) & ~(size_t)15;
         s.c_amounts = reinterpret_cast<uint64_t *>(s.cs.host);
         s.c_ids = reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(s.cs.host) + s.c_cap * 8);
@@ -163,15 +292,17 @@ void MetricSystem::Counter(const std::string &name, uint64_t amount) {
         s.c_open = true;
     }
     s.c_amounts[s.c_n] = amount;
-    s.c_ids[s.c_n] = id;
-    if (++s.c_n == s.c_cap) {
-        check(ctx_, lh_staging_commit_counter_u16(ctx_, &s.cs, s.c_n, s.c_cap * 8), "lh_staging_commit_counter_u16");
-        s.c_open = false;
-    }
+    s.c_ids[s.c_n] = (uint16_t)id;
+    if (++s.c_n == s.c_cap) commit_counters(s);
 }
 
 TimerToken MetricSystem::StartTimer(const std::string &name) {
-    return TimerToken{name, std::chrono::steady_clock::now(), this};
+    TimerToken t;
+    t.Name = name;
+    t.System = this;
+    t.id_valid = lookup_histogram(name.data(), name.size(), &t.id);   // interned once here; Stop() skips the lookup
+    t.Start = std::chrono::steady_clock::now();
+    return t;
 }
 
 void MetricSystem::RegisterGaugeFunc(const std::string &name, std::function<double()> f) {
@@ -183,23 +314,24 @@ void MetricSystem::DeregisterGaugeFunc(const std::string &name) {
     gauge_funcs_.erase(name);
 }
 
-void MetricSystem::flush_shard(Shard &s) {
-    std::lock_guard<std::mutex> lk(s.mu);
-    if (s.h_open) {
-        check(ctx_, lh_staging_commit_keyed_f64_u16(ctx_, &s.hs, s.h_n, s.h_cap * 8), "lh_staging_commit_keyed_f64_u16");
-        s.h_open = false;
-    }
-    if (s.c_open) {
-        check(ctx_, lh_staging_commit_counter_u16(ctx_, &s.cs, s.c_n, s.c_cap * 8), "lh_staging_commit_counter_u16");
-        s.c_open = false;
+// commit whatever the shard holds and hand over (and clear) its touched-counter marks
+void MetricSystem::flush_shard(Shard &s, std::vector<uint8_t> *touched) {
+    ShardGuard g(s);
+    commit_histograms(s);
+    commit_counters(s);
+    if (s.c_any_touched) {
+        for (size_t i = 0; i < s.c_touched.size(); i++)
+            if (s.c_touched[i]) { (*touched)[i] = 1; s.c_touched[i] = 0; }
+        s.c_any_touched = false;
     }
 }
 
 uint64_t MetricSystem::dropped_samples() {
     lh_stats st{};
     lh_get_stats(ctx_, &st);
-    std::lock_guard<std::mutex> lk(counter_store_mu_);
-    return st.dropped + dropped_over_limit_;
+    uint64_t d = st.dropped + dropped_over_limit_.load();
+    for (auto &s : shards_) { ShardGuard g(*s); d += s->dropped; }
+    return d;
 }
 
 // collectRawMetrics, metrics.go:420-479.
@@ -216,7 +348,8 @@ std::shared_ptr<RawMetricSet> MetricSystem::collectRawMetrics() {
         raw->percentile_labels = percentiles_;
     }
 
-    for (auto &s : shards_) flush_shard(*s);
+    std::vector<uint8_t> touched(opt_.max_counters, 0);
+    for (auto &s : shards_) flush_shard(*s, &touched);
     check(ctx_, lh_snapshot_begin(ctx_), "lh_snapshot_begin");   // the cache swaps of :425-428 and :460-463
 
     std::vector<std::string> hnames, cnames;
@@ -255,13 +388,13 @@ std::shared_ptr<RawMetricSet> MetricSystem::collectRawMetrics() {
         raw->reduced[hnames[h]] = std::move(r);
     }
     // counters: Rates = interval deltas of the names touched (:430-433); Counters = cumulative store (:435-458).
-    // A counter whose delta is zero because only Counter(name, 0) was called still counts as touched in Go;
-    // the device cannot tell that apart from "untouched", so a zero delta is reported as untouched.
+    // "Touched" is tracked on the host (a name appears in Rates even when only Counter(name, 0) was called, or when
+    // its amounts wrapped to a zero delta); the deltas themselves come from the device.
     {
         std::lock_guard<std::mutex> lk(counter_store_mu_);
         for (size_t c = 0; c < cnames.size(); c++) {
             uint64_t d = sp.counter_deltas[c];
-            if (d) {
+            if (d || touched[c]) {
                 raw->Rates[cnames[c]] = d;
                 counter_store_[cnames[c]] += d;
             }
@@ -455,22 +588,35 @@ LHMS_API void *lhms_new(int64_t interval_ns, int device, uint32_t max_histograms
     }
 }
 LHMS_API void lhms_free(void *ms) { delete static_cast<MetricSystem *>(ms); }
-LHMS_API void lhms_histogram(void *ms, const char *name, double v) { static_cast<MetricSystem *>(ms)->Histogram(name, v); }
-LHMS_API void lhms_counter(void *ms, const char *name, uint64_t a) { static_cast<MetricSystem *>(ms)->Counter(name, a); }
+// Nothing may unwind through these C entry points (ctypes / cgo callers): the ingest methods are noexcept, the
+// remaining allocations are guarded.
+LHMS_API void lhms_histogram(void *ms, const char *name, double v) {
+    if (!ms || !name) return;
+    static_cast<MetricSystem *>(ms)->Histogram(name, strlen(name), v);
+}
+LHMS_API void lhms_counter(void *ms, const char *name, uint64_t a) {
+    if (!ms || !name) return;
+    try { static_cast<MetricSystem *>(ms)->Counter(std::string(name), a); } catch (...) {}
+}
 LHMS_API void lhms_histogram_many(void *ms, const char *name, const double *v, size_t n) {
-    std::string nm(name);
+    if (!ms || !name) return;
     auto *m = static_cast<MetricSystem *>(ms);
-    for (size_t i = 0; i < n; i++) m->Histogram(nm, v[i]);
+    const size_t len = strlen(name);
+    for (size_t i = 0; i < n; i++) m->Histogram(name, len, v[i]);
 }
 LHMS_API void *lhms_start_timer(void *ms, const char *name) {
-    return new TimerToken(static_cast<MetricSystem *>(ms)->StartTimer(name));
+    if (!ms || !name) return nullptr;
+    try { return new TimerToken(static_cast<MetricSystem *>(ms)->StartTimer(name)); } catch (...) { return nullptr; }
 }
+// consumes the token; a NULL token (failed start, or a second stop through a cleared handle) returns 0
 LHMS_API int64_t lhms_timer_stop(void *token) {
+    if (!token) return 0;
     auto *t = static_cast<TimerToken *>(token);
     int64_t ns = t->Stop().count();
     delete t;
     return ns;
 }
+LHMS_API void lhms_timer_free(void *token) { delete static_cast<TimerToken *>(token); }
 LHMS_API void lhms_specify_percentiles(void *ms, int n, const char *const *labels, const double *ps) {
     std::map<std::string, double> m;
     for (int i = 0; i < n; i++) m[labels[i]] = ps[i];

@@ -13,6 +13,7 @@
 //     per-histogram statistics were reduced on the GPU for exactly that snapshot and travel with it.
 #pragma once
 
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdint>
@@ -99,6 +100,8 @@ struct TimerToken {
     std::string Name;
     std::chrono::steady_clock::time_point Start;
     MetricSystem *System = nullptr;
+    uint32_t id = 0;                   // dense histogram id interned by StartTimer (not in the Go type): Stop() skips the lookup
+    bool id_valid = false;
     std::chrono::nanoseconds Stop();   // metrics.go:242-246
 };
 
@@ -106,8 +109,9 @@ struct Options {
     int device = 0;
     uint32_t max_histograms = 1024;
     uint32_t max_counters = 1024;
-    uint32_t shards = 0;             // staging shards (0 = min(hardware_concurrency, 8))
+    uint32_t shards = 0;             // staging shards (0 = one per hardware thread, at most 256)
     uint64_t staging_bytes = 4u << 20;
+    uint32_t precision = 0;          // compress/decompress precision (0 = the reference's 100, metrics.go:40-43)
 };
 
 class MetricSystem {
@@ -124,8 +128,11 @@ class MetricSystem {
     void SubscribeToProcessedMetrics(std::shared_ptr<Channel<std::shared_ptr<ProcessedMetricSet>>> ch);   // :218
     void UnsubscribeFromProcessedMetrics(std::shared_ptr<Channel<std::shared_ptr<ProcessedMetricSet>>> ch);
     TimerToken StartTimer(const std::string &name);                       // :232
-    void Counter(const std::string &name, uint64_t amount);               // :251
-    void Histogram(const std::string &name, double value);                // :273
+    // Ingest never throws and never fails the caller (problems are logged, samples dropped and counted).
+    void Counter(const std::string &name, uint64_t amount) noexcept;      // :251
+    void Histogram(const std::string &name, double value) noexcept;       // :273
+    void Histogram(const char *name, size_t len, double value) noexcept;  // same, without building a std::string
+    void histogram_id(uint32_t id, double value) noexcept;                // body of Histogram once the name is interned
     void RegisterGaugeFunc(const std::string &name, std::function<double()> f);   // :299
     void DeregisterGaugeFunc(const std::string &name);                    // :306
     void Start();                                                         // :644
@@ -138,11 +145,17 @@ class MetricSystem {
     lh_ctx *context() const { return ctx_; }
     uint64_t dropped_samples();   // ids beyond max_histograms / max_counters (never silent)
 
- private:
+ public:
     struct Shard;
+
+ private:
     uint16_t intern(std::shared_mutex &mu, std::unordered_map<std::string, uint32_t> &ids,
                     std::vector<std::string> &names, const std::string &name, uint32_t limit, bool *ok);
-    void flush_shard(Shard &s);
+    bool lookup_histogram(const char *p, size_t n, uint32_t *id);
+    bool lookup_counter(const char *p, size_t n, uint32_t *id);
+    void commit_histograms(Shard &s) noexcept;
+    void commit_counters(Shard &s) noexcept;
+    void flush_shard(Shard &s, std::vector<uint8_t> *touched);
     void reaper();
     void add_aggregates(const RawMetricSet &raw, ProcessedMetricSet &out);
 
@@ -177,7 +190,8 @@ class MetricSystem {
     std::mutex run_mu_;
     std::condition_variable run_cv_;
     bool reaping_ = false, shutdown_ = false;
-    uint64_t dropped_over_limit_ = 0;
+    std::atomic<uint64_t> dropped_over_limit_{0};
+    uint64_t system_id_ = 0;
 };
 
 // print_benchmark.go:49: run `op` from `concurrency` threads between StartTimer/Stop and print every interval's

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <thread>
 #include <vector>
@@ -23,10 +24,14 @@ double PrintBenchmark(const std::string &name, unsigned concurrency, std::functi
     std::vector<std::thread> workers;
     for (unsigned i = 0; i < concurrency; i++)
         workers.emplace_back([&] {
-            while (!stop.load(std::memory_order_relaxed)) {
-                TimerToken timer = ms.StartTimer(name);   // print_benchmark.go:62-64
-                op();
-                timer.Stop();
+            try {
+                while (!stop.load(std::memory_order_relaxed)) {
+                    TimerToken timer = ms.StartTimer(name);   // print_benchmark.go:62-64
+                    op();
+                    timer.Stop();
+                }
+            } catch (const std::exception &e) {               // an exception from op() must not reach std::terminate
+                fprintf(stderr, "PrintBenchmark worker: %s\n", e.what());
             }
         });
     static const char *suffixes[] = {"_count", "_max", "_99.99", "_99.9", "_99", "_95", "_90", "_75", "_50", "_min",
@@ -56,6 +61,116 @@ double PrintBenchmark(const std::string &name, unsigned concurrency, std::functi
 }
 
 }  // namespace loghisto
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-call API load generator.  `threads` OS threads call MetricSystem::Histogram(name, value) -- or the
+// StartTimer/Stop pair of print_benchmark.go:62-64 -- in a tight loop, one call per sample, the way an instrumented
+// service would.  Values and name indices come from the repo's synthetic streams (splitmix64 of
+// the sample index, integer-only), so a checker can regenerate exactly what was fed.
+namespace {
+inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+const unsigned char kStreamLExp[16] = {17, 18, 18, 19, 19, 19, 20, 20, 20, 20, 21, 21, 21, 22, 22, 23};
+inline double stream_value(int kind, uint64_t seed, uint64_t i) {     // kinds 0 (U) and 1 (L)
+    const uint64_t u = splitmix64(seed + i), mant = u & 0x000FFFFFFFFFFFFFull;
+    const uint64_t bits = kind == 0 ? (((uint64_t)(1023 + (u >> 52) % 63) << 52) | mant)
+                                    : (((uint64_t)(1023 + kStreamLExp[(u >> 52) & 15]) << 52) | mant);
+    double d;
+    memcpy(&d, &bits, 8);
+    return d;
+}
+inline uint32_t stream_id(uint64_t seed, uint64_t i, uint32_t H) {    // ids kind 0: uniform
+    const uint64_t u = splitmix64((seed ^ 0xA5A5A5A5DEADBEEFull) + i);
+    return (uint32_t)((u & 0xFFFFFFFFu) % H);
+}
+}  // namespace
+
+extern "C" __attribute__((visibility("default")))
+// Feeds samples [start, start + n) of stream `kind` through ms.Histogram(names[id_i], value_i) from `threads` threads
+// (contiguous slices); returns the seconds the calls took (excluding thread start-up).  The caller then collects.
+double lhms_histogram_stream(void *msp, const char *const *names, uint32_t n_names, int kind, uint64_t seed, uint64_t start,
+                             uint64_t n, unsigned threads) {
+    auto *ms = static_cast<loghisto::MetricSystem *>(msp);
+    if (!ms || !names || !n_names || !threads) return -1.0;
+    std::vector<std::string> nm(names, names + n_names);
+    std::atomic<unsigned> ready{0};
+    std::atomic<bool> go{false};
+    std::vector<std::thread> workers;
+    const uint64_t per = n / threads;
+    for (unsigned t = 0; t < threads; t++)
+        workers.emplace_back([&, t] {
+            const uint64_t a = start + per * t, b = (t + 1 == threads) ? start + n : a + per;
+            ready.fetch_add(1);
+            while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
+            for (uint64_t i = a; i < b; i++) ms->Histogram(nm[n_names == 1 ? 0 : stream_id(seed, i, n_names)], stream_value(kind, seed, i));
+        });
+    while (ready.load() < threads) std::this_thread::yield();
+    const auto t0 = std::chrono::steady_clock::now();
+    go.store(true, std::memory_order_release);
+    for (auto &w : workers) w.join();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+extern "C" __attribute__((visibility("default")))
+// print_benchmark.go:59-67 as a measurement: `threads` threads loop { t := StartTimer(name); Stop() } for `seconds`
+// against a running MetricSystem (reaper at `interval_ns`); returns calls per second summed over the threads and
+// writes the total number of calls and the sum of every interval's <name>_count as the reaper reported them.
+double lhms_timer_loop(const char *name, unsigned threads, double seconds, int64_t interval_ns, int device,
+                       uint64_t *total_calls, double *reported_count) {
+    loghisto::Options o;
+    o.device = device;
+    o.max_histograms = 16;
+    o.max_counters = 16;
+    try {
+        loghisto::MetricSystem ms(std::chrono::nanoseconds(interval_ns), true, o);
+        auto mc = std::make_shared<loghisto::Channel<std::shared_ptr<loghisto::ProcessedMetricSet>>>(64);
+        ms.SubscribeToProcessedMetrics(mc);
+        ms.Start();
+        const std::string nm(name);
+        std::atomic<bool> stop{false};
+        std::atomic<uint64_t> calls{0};
+        std::vector<std::thread> workers;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (unsigned i = 0; i < threads; i++)
+            workers.emplace_back([&] {
+                uint64_t mine = 0;
+                while (!stop.load(std::memory_order_relaxed)) {
+                    for (int k = 0; k < 256; k++) {
+                        loghisto::TimerToken timer = ms.StartTimer(nm);
+                        timer.Stop();
+                    }
+                    mine += 256;
+                }
+                calls.fetch_add(mine);
+            });
+        std::this_thread::sleep_for(std::chrono::duration<double>(seconds));
+        stop.store(true);
+        for (auto &w : workers) w.join();
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        ms.Stop();
+        // what the reaper delivered, plus one last collection for the tail of the run
+        double reported = 0;
+        std::shared_ptr<loghisto::ProcessedMetricSet> m;
+        while (mc->Receive(&m, std::chrono::milliseconds(1))) {
+            auto it = m->Metrics.find(nm + "_count");
+            if (it != m->Metrics.end()) reported += it->second;
+        }
+        auto raw = ms.collectRawMetrics();
+        auto last = ms.processMetrics(*raw);
+        auto it = last->Metrics.find(nm + "_count");
+        if (it != last->Metrics.end()) reported += it->second;
+        if (total_calls) *total_calls = calls.load();
+        if (reported_count) *reported_count = reported;
+        return (double)calls.load() / dt;
+    } catch (const std::exception &e) {
+        fprintf(stderr, "lhms_timer_loop: %s\n", e.what());
+        return -1.0;
+    }
+}
 
 extern "C" __attribute__((visibility("default")))
 double lhms_print_benchmark(const char *name, unsigned concurrency, double seconds, int64_t interval_ns, int device, int print) {

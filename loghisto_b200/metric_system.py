@@ -44,6 +44,11 @@ def _bind(L):
     L.lhms_stop.argtypes = [vp]
     L.lhms_dropped.restype = C.c_uint64
     L.lhms_dropped.argtypes = [vp]
+    L.lhms_timer_free.argtypes = [vp]
+    L.lhms_histogram_stream.restype = C.c_double
+    L.lhms_histogram_stream.argtypes = [vp, C.POINTER(C.c_char_p), C.c_uint32, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint]
+    L.lhms_timer_loop.restype = C.c_double
+    L.lhms_timer_loop.argtypes = [C.c_char_p, C.c_uint, C.c_double, C.c_int64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
     L.lhms_print_benchmark.restype = C.c_double
     L.lhms_print_benchmark.argtypes = [C.c_char_p, C.c_uint, C.c_double, C.c_int64, C.c_int, C.c_int]
     for kind in ("processed", "raw"):
@@ -82,10 +87,22 @@ class TimerToken:
         self._lib, self._h = lib, handle
 
     def Stop(self) -> int:
-        """Submits the duration as a histogram sample and returns it in nanoseconds (metrics.go:242-246)."""
+        """Submits the duration as a histogram sample and returns it in nanoseconds (metrics.go:242-246).  The Go token
+        may be stopped repeatedly (one sample each time); this handle is consumed by the first Stop, later calls
+        return 0 without submitting anything."""
+        if self._h is None:
+            return 0
         ns = self._lib.lhms_timer_stop(self._h)
         self._h = None
         return int(ns)
+
+    def __del__(self):
+        try:
+            if self._h is not None:      # never stopped: release the C++ token
+                self._lib.lhms_timer_free(self._h)
+                self._h = None
+        except Exception:
+            pass
 
 
 class Subscription:
@@ -104,7 +121,21 @@ class Subscription:
         return None
 
     def unsubscribe(self):
-        getattr(self._ms._lib, "lhms_unsubscribe_" + self._kind)(self._ms._h, self._ch)
+        if self._ch is not None and self._ms._h:
+            getattr(self._ms._lib, "lhms_unsubscribe_" + self._kind)(self._ms._h, self._ch)
+
+    def close(self):
+        """Unsubscribe and free the channel (with whatever metric sets are still queued in it)."""
+        if self._ch is not None:
+            self.unsubscribe()
+            getattr(self._ms._lib, "lhms_free_%s_channel" % self._kind)(self._ch)
+            self._ch = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class MetricSystem:
@@ -112,6 +143,8 @@ class MetricSystem:
 
     def __init__(self, interval_s: float, sysStats: bool = False, device: int = 0, max_histograms: int = 1024,
                  max_counters: int = 1024):
+        """A Channel(capacity=0) is treated as capacity 1 by the C++ mirror (Go's unbuffered rendezvous has no
+        equivalent for a non-blocking sender; the reaper never blocks either way, metrics.go:570-573)."""
         self._lib = _load()
         err = C.create_string_buffer(512)
         self._h = self._lib.lhms_new(max(int(interval_s * 1e9), 1), device, max_histograms, max_counters, err, 512)
@@ -173,6 +206,21 @@ class MetricSystem:
 
     def dropped(self) -> int:
         return int(self._lib.lhms_dropped(self._h))
+
+    def histogram_stream(self, names, kind: int, seed: int, start: int, n: int, threads: int) -> float:
+        """Per-call load generator: `threads` OS threads call Histogram(names[id_i], value_i) once per sample for the
+        samples [start, start + n) of synthetic stream `kind`; returns the seconds the calls took."""
+        arr = (C.c_char_p * len(names))(*[x.encode() for x in names])
+        return float(self._lib.lhms_histogram_stream(self._h, arr, len(names), kind, seed, start, n, threads))
+
+
+def timer_loop(name: str, threads: int, seconds: float, interval_s: float = 0.1, device: int = 0):
+    """print_benchmark.go:59-67 as a measurement: returns (calls per second, total calls, sum of the <name>_count
+    values every interval reported)."""
+    total = C.c_uint64()
+    rep = C.c_double()
+    rate = _load().lhms_timer_loop(name.encode(), threads, seconds, int(interval_s * 1e9), device, C.byref(total), C.byref(rep))
+    return float(rate), int(total.value), float(rep.value)
 
 
 def PrintBenchmark(name: str, concurrency: int, seconds: float = 3.0, interval_s: float = 1.0, device: int = 0,

@@ -194,20 +194,23 @@ static inline int32_t amd64_cvttsd2sl(double t) {
     return (int32_t)t;
 }
 
-/* compress, metrics.go:316-322. */
-LHO_EXPORT int16_t lho_compress(double value) {
-    double t = 100.0 * lho_go_log(1.0 + fabs(value)) + 0.5;
+/* compress, metrics.go:316-322, with the package constant `precision` (metrics.go:40-43, 100 in the reference)
+ * as a parameter: i := int16(precision*math.Log(1.0+math.Abs(value)) + 0.5). */
+LHO_EXPORT int16_t lho_compress_p(double value, double precision) {
+    double t = precision * lho_go_log(1.0 + fabs(value)) + 0.5;
     int16_t i = (int16_t)(uint16_t)(uint32_t)amd64_cvttsd2sl(t);
     if (value < 0) return (int16_t)(uint16_t)(0u - (uint16_t)i); /* -1*i, wraps */
     return i;
 }
+LHO_EXPORT int16_t lho_compress(double value) { return lho_compress_p(value, 100.0); }
 
-/* decompress, metrics.go:326-332. */
-LHO_EXPORT double lho_decompress(int16_t k) {
-    double f = lho_go_exp(fabs((double)k) / 100.0) - 1.0;
+/* decompress, metrics.go:326-332: math.Exp(math.Abs(float64(compressedValue))/precision) - 1. */
+LHO_EXPORT double lho_decompress_p(int16_t k, double precision) {
+    double f = lho_go_exp(fabs((double)k) / precision) - 1.0;
     if (k < 0) return -1.0 * f;
     return f;
 }
+LHO_EXPORT double lho_decompress(int16_t k) { return lho_decompress_p(k, 100.0); }
 
 LHO_EXPORT double lho_decompress_purego(int16_t k) {
     double f = lho_go_exp_purego(fabs((double)k) / 100.0) - 1.0;
@@ -233,6 +236,12 @@ LHO_EXPORT void lho_ingest(const double *v, size_t n, uint64_t *counts65536) {
 
 LHO_EXPORT void lho_compress_many(const double *v, size_t n, int16_t *out) {
     for (size_t i = 0; i < n; i++) out[i] = lho_compress(v[i]);
+}
+LHO_EXPORT void lho_compress_many_p(const double *v, size_t n, int16_t *out, double precision) {
+    for (size_t i = 0; i < n; i++) out[i] = lho_compress_p(v[i], precision);
+}
+LHO_EXPORT void lho_ingest_p(const double *v, size_t n, uint64_t *counts65536, double precision) {
+    for (size_t i = 0; i < n; i++) counts65536[(uint16_t)lho_compress_p(v[i], precision)]++;
 }
 
 LHO_EXPORT void lho_ingest_keyed(const uint32_t *ids, const double *v, size_t n,
@@ -273,15 +282,21 @@ LHO_EXPORT void lho_counter_add(const uint32_t *ids, const uint64_t *amounts, si
  *   out_pkeys[np] chosen bucket keys;  INT32_MIN where percentile() errors
  * Returns the exact uint64 total count.
  */
+LHO_EXPORT uint64_t lho_process_histogram_p(const uint64_t *counts65536, const double *ps, int np,
+                                            double *out_stats, double *out_pvals, int32_t *out_pkeys, double precision);
 LHO_EXPORT uint64_t lho_process_histogram(const uint64_t *counts65536, const double *ps, int np,
                                           double *out_stats, double *out_pvals,
                                           int32_t *out_pkeys) {
+    return lho_process_histogram_p(counts65536, ps, np, out_stats, out_pvals, out_pkeys, 100.0);
+}
+LHO_EXPORT uint64_t lho_process_histogram_p(const uint64_t *counts65536, const double *ps, int np,
+                                            double *out_stats, double *out_pvals, int32_t *out_pkeys, double precision) {
     double total_sum = 0.0;
     uint64_t total_count = 0;
     for (int key = -32768; key <= 32767; key++) {
         uint64_t c = counts65536[(uint16_t)(int16_t)key];
         if (!c) continue;
-        total_sum += lho_decompress((int16_t)key) * (double)c;
+        total_sum += lho_decompress_p((int16_t)key, precision) * (double)c;
         total_count += c;
     }
     out_stats[0] = (double)total_count;
@@ -296,7 +311,7 @@ LHO_EXPORT uint64_t lho_process_histogram(const uint64_t *counts65536, const dou
             if (!c) continue;
             sofar += c;
             if ((double)sofar / (double)total_count >= ps[j]) {
-                out_pvals[j] = lho_decompress((int16_t)key);
+                out_pvals[j] = lho_decompress_p((int16_t)key, precision);
                 out_pkeys[j] = key;
                 break;
             }
@@ -376,6 +391,8 @@ LHO_EXPORT uint64_t lho_stream_bits(int kind, uint64_t seed, uint64_t i) {
     }
     case 7: /* A: counter amounts 1..16 */
         return 1 + (u >> 60);
+    case 8: /* N: stream U with a random sign (50 % negative durations, readme.md:43) */
+        return ((u >> 11) & 0x8000000000000000ull) | ((uint64_t)(1023 + (u >> 52) % 63) << 52) | mant;
     default:
         return u;
     }

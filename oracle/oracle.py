@@ -17,6 +17,7 @@ _SO = os.path.join(_HERE, "build", "liblh_oracle.so")
 
 STREAM_U, STREAM_L, STREAM_S, STREAM_C, STREAM_Z = 0, 1, 2, 3, 4
 STREAM_RAW, STREAM_TIMER_NS, STREAM_AMOUNTS = 5, 6, 7   # raw u64 bits / int64 ns / counter amounts 1..16
+STREAM_N = 8                                            # stream U with a random sign
 DEFAULT_SEED = 0x10C415C0
 
 DEFAULT_PERCENTILES = {
@@ -60,6 +61,14 @@ def lib() -> C.CDLL:
     L.lho_decompress_purego.argtypes = [C.c_int16]
     L.lho_go_f64_to_u64.restype = C.c_uint64
     L.lho_go_f64_to_u64.argtypes = [C.c_double]
+    L.lho_compress_p.restype = C.c_int16
+    L.lho_compress_p.argtypes = [C.c_double, C.c_double]
+    L.lho_decompress_p.restype = C.c_double
+    L.lho_decompress_p.argtypes = [C.c_int16, C.c_double]
+    L.lho_compress_many_p.argtypes = [dp, C.c_size_t, C.POINTER(C.c_int16), C.c_double]
+    L.lho_ingest_p.argtypes = [dp, C.c_size_t, u64p, C.c_double]
+    L.lho_process_histogram_p.restype = C.c_uint64
+    L.lho_process_histogram_p.argtypes = [u64p, dp, C.c_int, dp, dp, C.POINTER(C.c_int32), C.c_double]
     L.lho_ingest.argtypes = [dp, C.c_size_t, u64p]
     L.lho_ingest_mt.argtypes = [dp, C.c_size_t, u64p, C.c_int]
     L.lho_compress_many.argtypes = [dp, C.c_size_t, C.POINTER(C.c_int16)]
@@ -105,26 +114,37 @@ def _u32p(a):
     return a.ctypes.data_as(C.POINTER(C.c_uint32))
 
 
-def compress(v: float) -> int:
-    return int(lib().lho_compress(float(v)))
+def compress(v: float, precision: float = 100.0) -> int:
+    return int(lib().lho_compress_p(float(v), float(precision)))
 
 
-def decompress(k: int) -> float:
-    return float(lib().lho_decompress(int(k)))
+def decompress(k: int, precision: float = 100.0) -> float:
+    return float(lib().lho_decompress_p(int(k), float(precision)))
 
 
-def compress_many(vals: np.ndarray) -> np.ndarray:
+def compress_many(vals: np.ndarray, precision: float = 100.0) -> np.ndarray:
     vals = np.ascontiguousarray(vals, dtype=np.float64)
     out = np.empty(vals.size, dtype=np.int16)
-    lib().lho_compress_many(_dp(vals), vals.size, out.ctypes.data_as(C.POINTER(C.c_int16)))
+    lib().lho_compress_many_p(_dp(vals), vals.size, out.ctypes.data_as(C.POINTER(C.c_int16)), float(precision))
     return out
 
 
-def ingest(vals: np.ndarray, counts: np.ndarray | None = None, threads: int = 1) -> np.ndarray:
+def decompress_table(precision: float = 100.0) -> np.ndarray:
+    """out[(uint16)key] = decompress(key) for every int16 key."""
+    out = np.empty(65536, dtype=np.float64)
+    for k in range(-32768, 32768):
+        out[k & 0xFFFF] = lib().lho_decompress_p(k, float(precision))
+    return out
+
+
+def ingest(vals: np.ndarray, counts: np.ndarray | None = None, threads: int = 1, precision: float = 100.0) -> np.ndarray:
     """Dense histogram: counts[(uint16)compress(v)] += 1 (uint64[65536])."""
     vals = np.ascontiguousarray(vals, dtype=np.float64)
     if counts is None:
         counts = np.zeros(65536, dtype=np.uint64)
+    if precision != 100.0:
+        lib().lho_ingest_p(_dp(vals), vals.size, _u64p(counts), float(precision))
+        return counts
     if threads > 1:
         lib().lho_ingest_mt(_dp(vals), vals.size, _u64p(counts), threads)
     else:
@@ -194,15 +214,15 @@ def counter_add(ids: np.ndarray, amounts: np.ndarray, n_counters: int,
     return counters
 
 
-def process_histogram(counts: np.ndarray, ps) -> dict:
+def process_histogram(counts: np.ndarray, ps, precision: float = 100.0) -> dict:
     """processHistograms on one dense uint64[65536] histogram."""
     counts = np.ascontiguousarray(counts, dtype=np.uint64)
     ps = np.ascontiguousarray(ps, dtype=np.float64)
     stats = np.zeros(3, dtype=np.float64)
     pv = np.zeros(ps.size, dtype=np.float64)
     pk = np.zeros(ps.size, dtype=np.int32)
-    total = lib().lho_process_histogram(_u64p(counts), _dp(ps), ps.size, _dp(stats), _dp(pv),
-                                        pk.ctypes.data_as(C.POINTER(C.c_int32)))
+    total = lib().lho_process_histogram_p(_u64p(counts), _dp(ps), ps.size, _dp(stats), _dp(pv),
+                                          pk.ctypes.data_as(C.POINTER(C.c_int32)), float(precision))
     return {"total": int(total), "count": stats[0], "sum": stats[1], "avg": stats[2],
             "pvals": pv, "pkeys": pk}
 

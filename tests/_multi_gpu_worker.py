@@ -1,4 +1,5 @@
-"""torchrun worker for tests/test_gpu_multi.py: one rank per GPU, NCCL all-reduce of the bucket arrays."""
+"""torchrun worker for tests/test_gpu_multi.py and tests/test_gpu_comm.py: one rank per GPU; the bucket arrays are
+summed by the library's peer-memory all-reduce (argv[1] == "peer") or by an NCCL all-reduce ("nccl", default)."""
 import os
 import sys
 
@@ -23,7 +24,7 @@ def main():
     a, b = shard_range(rank, world, n_total)
     H = 3
     with lh.Engine(device=local, max_histograms=H, max_counters=4) as eng:
-        sh = ShardedEngine(eng, local)
+        sh = ShardedEngine(eng, local, collective=sys.argv[1] if len(sys.argv) > 1 else "nccl")
         d = eng.gen_stream(lh.STREAM_S, b - a, lh.DEFAULT_SEED, start=a)
         eng.ingest_f64(1, d, b - a)
         ids = o.gen_ids(0, b - a, H, lh.DEFAULT_SEED, start=a).astype(np.uint16)
@@ -51,7 +52,7 @@ def main():
                 assert int(red.counts.sum()) == 0 and int(sp.offsets[-1]) == 0
     dist.barrier()
     if rank == 0:
-        print("MULTI_GPU_OK world=%d" % world)
+        print("MULTI_GPU_OK world=%d collective=%s" % (world, sh.collective))
     dist.destroy_process_group()
 
 

@@ -169,6 +169,12 @@ static lh_status lh_get_stats_impl(lh_ctx *c, lh_stats *out) {
     return LH_OK;
 }
 
+static lh_status lh_staging_abandon_impl(lh_ctx *c, const lh_staging *s) {
+    if (!s || s->slot >= c->nslots) return LH_ERR_INVALID;
+    c->slot_busy[s->slot] = 0;
+    return LH_OK;
+}
+LH_API lh_status lh_staging_abandon(lh_ctx *c, const lh_staging *s) { LOCKED(lh_staging_abandon_impl(c, s)); }
 LH_API lh_status lh_staging_acquire(lh_ctx *c, lh_staging *out) { LOCKED(lh_staging_acquire_impl(c, out)); }
 
 LH_API lh_status lh_staging_commit_keyed_f64_u16(lh_ctx *c, const lh_staging *s, size_t n, uint64_t ids_offset) { LOCKED(lh_staging_commit_keyed_f64_u16_impl(c, s, n, ids_offset)); }

@@ -29,19 +29,34 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_abi_version_and_strerror():
     from loghisto_b200 import _lib
     lib = _lib.load()
-    assert lib.lh_abi_version() == 1
+    assert lib.lh_abi_version() == 2
     assert lib.lh_strerror(0) == b"ok"
     assert b"no CPU fallback" in lib.lh_strerror(_lib.LH_ERR_NO_DEVICE)
     assert lib.lh_k1_variant_count() >= 4
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of every struct of the header, as a C compiler sees them, against the ctypes mirror."""
+    import subprocess
     from loghisto_b200 import _lib
-    assert ctypes.sizeof(_lib.lh_config) == 32
-    assert ctypes.sizeof(_lib.lh_staging) == 24
-    assert ctypes.sizeof(_lib.lh_device_view) == 40
-    assert ctypes.sizeof(_lib.lh_sparse) == 40
-    assert ctypes.sizeof(_lib.lh_stats) == 56
+    structs = {"lh_config": _lib.lh_config, "lh_staging": _lib.lh_staging, "lh_device_view": _lib.lh_device_view,
+               "lh_sparse": _lib.lh_sparse, "lh_stats": _lib.lh_stats, "lh_comm_stats": _lib.lh_comm_stats}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "loghisto_b200.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        src.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for f, _ in cls._fields_:
+            src.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, f, name, f))
+    src.append('printf("lh_peer_handle %zu\\n", sizeof(lh_peer_handle)); return 0; }')
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(c)], check=True)
+    want = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert ctypes.sizeof(cls) == int(want[name]), name
+        for f, _ in cls._fields_:
+            assert getattr(cls, f).offset == int(want["%s.%s" % (name, f)]), (name, f)
+    assert int(want["lh_peer_handle"]) == _lib.LH_PEER_HANDLE_BYTES
 
 
 def test_no_cpu_fallback_without_gpu():

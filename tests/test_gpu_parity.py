@@ -363,14 +363,15 @@ def test_host_and_staging_paths(lh, oracle):
 
 
 def test_full_size_properties(lh, oracle):
-    """BASELINE config 2 size (1e9 samples, 8 GB): linearity and conservation instead of an oracle run."""
+    """BASELINE config 2 size (1e9 samples, 8 GB): linearity and conservation across ragged pieces and kernels, then the
+    whole histogram against the oracle."""
     n = 1_000_000_000
     with lh.Engine(device=0, max_histograms=3, max_counters=1) as e:
         d = e.gen_stream(lh.STREAM_U, n, SEED)
         e.ingest_f64(0, d, n)                                   # one call
         cuts = [0, 1, 333_333_335, 900_000_002, n]
         default = e.lib.lh_k1_variant_current(e.h)
-        for vi, (a, b) in zip((0, 5, 21, 13), zip(cuts[:-1], cuts[1:])):   # ragged pieces, different kernels
+        for vi, (a, b) in zip((0, 1, 2, 3), zip(cuts[:-1], cuts[1:])):   # ragged pieces, different kernels
             e.tune("k1", vi)
             e.ingest_f64(1, d.offset(a), b - a)
         e.tune("k1", default)
@@ -388,7 +389,30 @@ def test_full_size_properties(lh, oracle):
         for k, c in sp.histogram(2).items():
             got[k & 0xFFFF] = c
         assert (got == want).all()
+        # ... and the WHOLE 1e9-sample histogram bucket for bucket: the oracle regenerates the stream on every host core
+        want_full = oracle.stream_ingest(lh.STREAM_U, n, SEED)
+        assert (dense_from_sparse(sp, 0) == want_full).all()
+        ref = oracle.process_histogram(want_full, PS)
+        assert (red.pkeys[0] == ref["pkeys"]).all() and int(red.counts[0]) == ref["total"] == n
         d.free()
+
+
+def test_full_size_keyed_1024(lh, oracle):
+    """BASELINE configs[2] at full size: 1024 keyed histograms x 1e9 (id, value) pairs, every bucket of every
+    histogram against the oracle (which regenerates both streams on every host core), for the default dispatch."""
+    H, n = 1024, 1_000_000_000
+    with lh.Engine(device=0, max_histograms=H, max_counters=1) as e:
+        d_v = e.gen_stream(lh.STREAM_U, n, SEED)
+        d_i = e.gen_ids_u16(0, n, H, SEED)
+        e.ingest_keyed_f64_u16(d_i, d_v, n)
+        red, sp = e.snapshot(PS)
+        want = oracle.stream_ingest_keyed(lh.STREAM_U, n, H, SEED)
+        got = np.zeros((H, 65536), dtype=np.uint64)
+        got[np.repeat(np.arange(H), np.diff(sp.offsets.astype(np.int64))), sp.keys.view(np.uint16)] = sp.counts
+        assert (got == want).all(), e.keyed_kernel_name()
+        assert (red.counts == want.sum(axis=1)).all()
+        for h in (0, 511, 1023):
+            assert (red.pkeys[h] == oracle.process_histogram(want[h], PS)["pkeys"]).all()
 
 
 def test_mixed_ops_interval_pipeline(lh, oracle):
@@ -435,15 +459,16 @@ def test_mixed_ops_interval_pipeline(lh, oracle):
             assert (dense_from_sparse(sp, h) == want[h]).all()
 
 
-@pytest.mark.parametrize("chunk,shape", [(65536, 0), (1 << 20, 0), (65536, 1), (1 << 20, 1)])
-def test_keyed_owner_partitioned_kernel(lh, oracle, chunk, shape):
-    """The owner-partitioned keyed kernel (bin -> per-owner queues -> shared-memory windows) against the oracle:
-    several chunks (grid barriers, queue parity), signed/edge values, skewed ids, out-of-range ids, and a
-    single-id stream that overflows one owner's queue and must fall back without losing a sample."""
+@pytest.mark.parametrize("chunk,spt", [(65536, 16), (1 << 20, 16), (65536, 8), (1 << 20, 8)])
+def test_keyed_owner_partitioned_kernel(lh, oracle, chunk, spt):
+    """The owner-partitioned write-combining keyed kernel (bin -> per-owner buffers -> per-(owner, writer) queues ->
+    shared-memory windows) against the oracle: several chunks (grid barriers, queue parity), signed/edge values,
+    skewed ids, out-of-range ids, and a single-id stream that overflows one owner's buffer and queue and must fall
+    back without losing a sample."""
     H, n = 1024, 1_500_001
     with lh.Engine(device=0, max_histograms=H, max_counters=1) as e:
         e.tune("keyed_mode", 2)
-        e.tune("kp_shape", shape)
+        e.tune("wc_spt", spt)
         e.tune("kp_chunk", chunk)
         for stream, idkind in ((lh.STREAM_S, 0), (lh.STREAM_U, 1), (lh.STREAM_L, 0)):
             vals = oracle.gen_stream(stream, n, SEED ^ 0x31)
@@ -451,6 +476,7 @@ def test_keyed_owner_partitioned_kernel(lh, oracle, chunk, shape):
             want = oracle.ingest_keyed(ids, vals, H)
             d_v, d_i16, d_i32 = e.upload(vals), e.upload(ids.astype(np.uint16)), e.upload(ids)
             e.ingest_keyed_f64_u16(d_i16, d_v, n)
+            assert e.keyed_kernel_name() == "k_ingest_keyed_wc"
             red, sp = e.snapshot(PS)
             assert (red.counts == want.sum(axis=1)).all(), (stream, idkind)
             for h in (0, 1, 147, 148, 500, 1023):

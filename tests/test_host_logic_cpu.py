@@ -99,3 +99,24 @@ def test_print_benchmark_driver(stub_host_lib, monkeypatch):
     monkeypatch.setattr(m, "_lib", m._bind(ctypes.CDLL(stub_host_lib)))
     count = m.PrintBenchmark("benchmark1234", 4, seconds=0.6, interval_s=0.1)
     assert count > 100
+
+
+def test_counter_zero_amount_appears_in_rates(MS):
+    _cases().test_counter_zero_amount_appears_in_rates(MS)
+
+
+def test_per_call_api_small(MS):
+    """The per-call fast path (thread-local name cache, spin-locked shards) against the oracle-backed stub."""
+    import numpy as np
+    from oracle import oracle as o
+    H, n = 16, 300_000
+    names = ["h%d" % i for i in range(H)]
+    ms = MS(interval_s=3600.0, max_histograms=H)
+    ms.histogram_stream(names, o.STREAM_U, o.DEFAULT_SEED, 7, n, 4)
+    raw, _ = ms.collect_and_process()
+    want = o.stream_ingest_keyed(o.STREAM_U, n, H, o.DEFAULT_SEED, val_start=7, ids_start=7)
+    for h in range(H):
+        got = np.zeros(65536, dtype=np.uint64)
+        for k, c in raw["Histograms"].get(names[h], {}).items():
+            got[k & 0xFFFF] = c
+        assert (got == want[h]).all(), h

@@ -184,3 +184,50 @@ def test_names_beyond_capacity_are_dropped_and_counted(MS):
     assert len(raw["Histograms"]) == 4 and len(raw["Counters"]) == 4
     assert ms.dropped() == 4
 
+
+
+def test_per_call_api_parity_and_rate(MS):
+    """The per-call path an instrumented service uses -- Histogram(name, value) once per sample from many threads
+    (thread-local name cache, one staging shard per thread) -- must land every sample in exactly the bucket the
+    oracle's structure-faithful port puts it in (lho_ms_histogram: metrics.go:273-295)."""
+    import os
+    import numpy as np
+    from oracle import oracle as o
+    o.build()
+    H, n, threads = 64, 20_000_000, min(32, os.cpu_count() or 1)
+    names = ["histogram%d" % i for i in range(H)]
+    ms = MS(interval_s=3600.0, max_histograms=H)
+    dt = ms.histogram_stream(names, o.STREAM_L, o.DEFAULT_SEED, 12345, n, threads)
+    raw, metrics = ms.collect_and_process()
+    want = o.stream_ingest_keyed(o.STREAM_L, n, H, o.DEFAULT_SEED, val_start=12345, ids_start=12345)
+    # a few samples through the oracle's own MetricSystem port as well: same name -> same bucket
+    oms = o.OracleMetricSystem()
+    vals = o.gen_stream(o.STREAM_L, 1000, o.DEFAULT_SEED, start=12345)
+    ids = o.gen_ids(0, 1000, H, o.DEFAULT_SEED, start=12345)
+    for i in range(1000):
+        oms.Histogram(names[ids[i]], float(vals[i]))
+    oraw, _ = oms.collect_and_process()
+    oms.close()
+    for name, buckets in oraw["Histograms"].items():
+        for k, c in buckets.items():
+            assert raw["Histograms"][name].get(k, 0) >= c
+    assert ms.dropped() == 0
+    for h in range(H):
+        got = np.zeros(65536, dtype=np.uint64)
+        for k, c in raw["Histograms"].get(names[h], {}).items():
+            got[k & 0xFFFF] = c
+        assert (got == want[h]).all(), h
+        assert metrics[names[h] + "_count"] == float(want[h].sum())
+    print("per-call Histogram(): %d calls from %d threads in %.3f s = %.1f M calls/s" % (n, threads, dt, n / dt / 1e6))
+
+
+def test_counter_zero_amount_appears_in_rates(MS):
+    """metrics.go:430-433: a counter touched this interval is in Rates even when only Counter(name, 0) was called."""
+    ms = MS()
+    ms.Counter("quiet", 0)
+    ms.Counter("busy", 5)
+    raw, metrics = ms.collect_and_process()
+    assert raw["Rates"] == {"quiet": 0, "busy": 5}
+    assert metrics["quiet_rate"] == 0.0 and metrics["quiet"] == 0.0
+    raw, _ = ms.collect_and_process()
+    assert raw["Rates"] == {} and raw["Counters"] == {"quiet": 0, "busy": 5}
