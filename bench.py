@@ -349,16 +349,22 @@ def api_leg(device, kind):
     ncpu = os.cpu_count() or 1
     out = {"published_reference_samples_per_s": PUBLISHED_SAMPLES_PER_S,
            "published_reference_source": "readme.md:34 (StartTimer/Stop from 100 goroutines, 2014, unnamed CPU)"}
-    rate, calls, reported = timer_loop("benchmark1234", 100, 2.0, 0.1, device)
+    rate, calls, reported = timer_loop("benchmark1234", 100, 3.0, 0.1, device)
     out["timer_loop"] = {"value": rate, "unit": "calls/s", "threads": 100, "op": "StartTimer + Stop (print_benchmark.go:59-67, empty op)",
                          "calls": calls, "reported_count": reported, "count_ok": float(calls) == reported, "host_cpus": ncpu}
-    n_api = 500_000_000
+    n_api = 1_000_000_000
     ms = MetricSystem(3600.0, False, device=device, max_histograms=16, max_counters=16)
-    dt = ms.histogram_stream(["benchmark1234"], kind if kind in (0, 1) else 0, SEED, 0, n_api, ncpu)
-    raw, metrics = ms.collect_and_process()
-    got = sum(raw["Histograms"].get("benchmark1234", {}).values())
-    out["histogram_calls"] = {"value": n_api / dt, "unit": "calls/s", "threads": ncpu, "calls": n_api,
-                              "op": "MetricSystem.Histogram(name, value), one call per sample, 1 name", "count_ok": got == n_api,
+    k = kind if kind in (0, 1) else 0
+    # pass 0 warms the staging ring up (every shard pins its slots on first use: cudaMallocHost is slow); pass 1 is reported
+    passes = []
+    for i in range(2):
+        dt = ms.histogram_stream(["benchmark1234"], k, SEED, i * n_api, n_api, ncpu)
+        raw, metrics = ms.collect_and_process()
+        got = sum(raw["Histograms"].get("benchmark1234", {}).values())
+        passes.append({"calls_per_s": n_api / dt, "count_ok": got == n_api})
+    out["histogram_calls"] = {"value": passes[1]["calls_per_s"], "unit": "calls/s", "threads": ncpu, "calls": n_api,
+                              "op": "MetricSystem.Histogram(name, value), one call per sample, 1 name",
+                              "count_ok": all(p_["count_ok"] for p_ in passes), "warmup_pass_calls_per_s": passes[0]["calls_per_s"],
                               "dropped": ms.dropped()}
     ms.close()
     return out

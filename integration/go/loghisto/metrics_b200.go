@@ -1,18 +1,25 @@
-// UNVERIFIED SOURCE: this image has no Go toolchain, so this file has never been
-// compiled.  It shows the binding a loghisto maintainer would add: it replaces the
-// bodies of Histogram / Counter / collectRawMetrics / processHistograms in
-// metrics.go (same exported API, same RawMetricSet / ProcessedMetricSet types) with
-// calls into libloghisto_b200.so.  Everything else in metrics.go (reaper,
-// subscriptions, gauges, Submitter, serializers, PrintBenchmark) is unchanged.
+// Go side of the drop-in: the bodies of MetricSystem.Counter, MetricSystem.Histogram, collectRawMetrics,
+// processMetrics and processHistograms (reference metrics.go:251-295, 336-387, 420-506) over the C ABI in
+// include/loghisto_b200.h.  Everything else in the package -- the exported API, RawMetricSet / ProcessedMetricSet /
+// TimerToken, StartTimer / Stop, the reaper and its subscription bookkeeping, gauges, Submitter, the Graphite and
+// OpenTSDB serializers, PrintBenchmark, compress / decompress -- stays the reference's own source, untouched.
 //
-// Build: CGO_CFLAGS=-I<repo>/include CGO_LDFLAGS="-L<repo>/loghisto_b200 -lloghisto_b200" go build -tags b200
+// STATUS: complete, self-consistent source, but NEVER COMPILED: the build image has no Go toolchain (INTEGRATION.md).
+// Every lh_* call below is exercised by the C++ mirror (loghisto_b200/host/) and the ctypes / C clients in tests/.
+//
+// How it is wired in (INTEGRATION.md has the commands):
+//   1. integration/go/split_reference.py moves the five replaced method bodies of metrics.go into metrics_cpu.go
+//      under `//go:build !b200` (nothing else changes, a plain `go build` still gives the pure-Go package);
+//   2. this file is copied next to it; it is compiled only with `-tags b200`;
+//   3. include/loghisto_b200.h and libloghisto_b200.so are made visible through CGO_CFLAGS / CGO_LDFLAGS.
 
 //go:build b200
 
 package loghisto
 
 /*
-#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 #include "loghisto_b200.h"
 */
 import "C"
@@ -23,183 +30,505 @@ import (
 	"runtime"
 	"sync"
 	"sync/atomic"
+	"time"
 	"unsafe"
+
+	"github.com/golang/glog"
 )
 
-// b200Engine owns the device context, the name->id tables and the staging shards.
-type b200Engine struct {
-	ctx *C.lh_ctx
+// Limits of one engine.  Names beyond them are dropped and counted (b200Dropped), never silently.
+const (
+	b200MaxHistograms = 4096
+	b200MaxCounters   = 4096
+	b200StagingBytes  = 4 << 20 // per pinned staging slot: 419 424 (id, value) pairs
+)
 
-	histoMu  sync.RWMutex // same RLock fast path / Lock-and-recheck idiom as metrics.go:275-294
-	histoIDs map[string]uint16
-	histoNames []string
-
-	counterMu  sync.RWMutex
-	counterIDs map[string]uint16
-	counterNames []string
-
-	shards []*stagingShard // one per P; picked by a cheap per-goroutine hash
-}
-
-// stagingShard batches (id,value) pairs into a C-owned pinned slot (cgo forbids C code from keeping
-// Go pointers past the call, so Go writes into C memory through unsafe.Slice).
-type stagingShard struct {
-	mu    sync.Mutex
-	slot  C.lh_staging
-	vals  []float64 // view of slot.host[0 : cap*8]
-	ids   []uint16  // view of slot.host[idsOff : idsOff+cap*2]
-	n     int
-	cap   int
+// stagingBuf is one C-owned pinned slot being filled: n 8-byte items at offset 0, n uint16 ids at idsOff.
+// cgo forbids C code from keeping Go pointers after a call returns, so Go writes into C memory instead.
+type stagingBuf struct {
+	slot   C.lh_staging
+	open   bool
+	n, cap int
+	items  []uint64 // float64 bits or counter amounts, view of slot.host
+	ids    []uint16
 	idsOff uint64
 }
 
-const maxHistograms, maxCounters = 1024, 1024
+// b200Shard is what one goroutine at a time appends to.  Goroutines spread over 4*GOMAXPROCS shards by a hash of
+// their stack address, so the mutex is almost always uncontended and the slot's cache lines stay on one core.
+type b200Shard struct {
+	mu      sync.Mutex
+	hist    stagingBuf
+	counter stagingBuf
+	touched []bool // counter ids Counter() was called for this interval, even with amount 0 (metrics.go:430-433)
+	anyC    bool
+	_       [64]byte
+}
 
-func newB200Engine(device int) (*b200Engine, error) {
-	cfg := C.lh_config{struct_size: C.uint32_t(unsafe.Sizeof(C.lh_config{})), device: C.int32_t(device),
-		max_histograms: maxHistograms, max_counters: maxCounters}
+// reducedHistogram is what the device computed for one histogram of one snapshot (metrics.go:336-387).
+type reducedHistogram struct {
+	count    uint64
+	sum, avg float64
+	pkeys    []int32
+	pvals    []float64
+}
+
+// reducedSet travels beside a RawMetricSet from collectRawMetrics to processMetrics.
+type reducedSet struct {
+	labels []string  // percentile labels ("%s_99.9", ...) in the order the device reduced them
+	ps     []float64 // the matching percentiles
+	byName map[string]*reducedHistogram
+}
+
+type b200Engine struct {
+	ctx *C.lh_ctx
+
+	histoMu    sync.RWMutex // RLock fast path, Lock-and-recheck slow path: the idiom of metrics.go:275-294
+	histoIDs   map[string]uint16
+	histoNames []string
+
+	counterMu    sync.RWMutex
+	counterIDs   map[string]uint16
+	counterNames []string
+
+	shards  []*b200Shard
+	dropped uint64
+
+	snapshotMu sync.Mutex // one collectRawMetrics at a time
+
+	// device reductions waiting for processMetrics: the reaper hands every set to a worker right away
+	// (metrics.go:583-587), so a short ring suffices; sets that are never processed (raw-only subscribers) age out
+	reducedMu   sync.Mutex
+	reducedRing [16]struct {
+		raw *RawMetricSet
+		red *reducedSet
+	}
+	reducedNext int
+}
+
+func (e *b200Engine) putReduced(raw *RawMetricSet, red *reducedSet) {
+	e.reducedMu.Lock()
+	e.reducedRing[e.reducedNext].raw, e.reducedRing[e.reducedNext].red = raw, red
+	e.reducedNext = (e.reducedNext + 1) % len(e.reducedRing)
+	e.reducedMu.Unlock()
+}
+
+func (e *b200Engine) takeReduced(raw *RawMetricSet) *reducedSet {
+	e.reducedMu.Lock()
+	defer e.reducedMu.Unlock()
+	for i := range e.reducedRing {
+		if e.reducedRing[i].raw == raw {
+			red := e.reducedRing[i].red
+			e.reducedRing[i].raw, e.reducedRing[i].red = nil, nil
+			return red
+		}
+	}
+	return nil
+}
+
+var (
+	b200Engines   sync.Map // *MetricSystem -> *b200Engine
+	b200EnginesMu sync.Mutex
+	// B200Device is the CUDA ordinal new engines are created on.
+	B200Device = 0
+)
+
+func b200Status(st C.lh_status, ctx *C.lh_ctx, what string) error {
+	if st == C.LH_OK {
+		return nil
+	}
+	detail := ""
+	if ctx != nil {
+		detail = C.GoString(C.lh_last_error(ctx))
+	}
+	return fmt.Errorf("%s: %s (%s)", what, C.GoString(C.lh_strerror(st)), detail)
+}
+
+// engineFor returns the engine of a MetricSystem, creating it on first use.  There is no CPU fallback under the
+// b200 tag: without a usable B200 the process stops here (build without the tag for the pure-Go package).
+func engineFor(ms *MetricSystem) *b200Engine {
+	if e, ok := b200Engines.Load(ms); ok {
+		return e.(*b200Engine)
+	}
+	b200EnginesMu.Lock()
+	defer b200EnginesMu.Unlock()
+	if e, ok := b200Engines.Load(ms); ok {
+		return e.(*b200Engine)
+	}
+	nshards := 4 * runtime.GOMAXPROCS(0)
+	var cfg C.lh_config
+	cfg.struct_size = C.uint32_t(C.sizeof_lh_config)
+	cfg.device = C.int32_t(B200Device)
+	cfg.max_histograms = b200MaxHistograms
+	cfg.max_counters = b200MaxCounters
+	cfg.staging_bytes = b200StagingBytes
+	cfg.staging_slots = C.uint32_t(2*nshards + 2) // memory of a slot is allocated on first use
+	cfg.precision = C.uint32_t(precision)          // the package constant of metrics.go:40-43
 	e := &b200Engine{histoIDs: map[string]uint16{}, counterIDs: map[string]uint16{}}
-	if st := C.lh_create(&cfg, &e.ctx); st != C.LH_OK {
-		return nil, fmt.Errorf("lh_create: %s", C.GoString(C.lh_strerror(st)))
+	if err := b200Status(C.lh_create(&cfg, &e.ctx), nil, "lh_create"); err != nil {
+		glog.Fatalf("loghisto (b200 build): %v", err)
 	}
-	e.shards = make([]*stagingShard, runtime.GOMAXPROCS(0))
+	e.shards = make([]*b200Shard, nshards)
 	for i := range e.shards {
-		e.shards[i] = &stagingShard{}
+		e.shards[i] = &b200Shard{touched: make([]bool, b200MaxCounters)}
 	}
-	return e, nil
+	runtime.SetFinalizer(e, func(e *b200Engine) { C.lh_destroy(e.ctx) })
+	b200Engines.Store(ms, e)
+	return e
 }
 
-func (e *b200Engine) acquire(s *stagingShard) {
-	C.lh_staging_acquire(e.ctx, &s.slot) // blocks only if every slot is still in flight
-	s.cap = int(uint64(s.slot.bytes)/10) &^ 15
-	s.idsOff = uint64(s.cap) * 8
-	base := unsafe.Pointer(s.slot.host)
-	s.vals = unsafe.Slice((*float64)(base), s.cap)
-	s.ids = unsafe.Slice((*uint16)(unsafe.Add(base, s.idsOff)), s.cap)
-	s.n = 0
+// B200Dropped is the number of samples / counter ops that could not be recorded (name table full, or a staging
+// call failed); the reference's philosophy is "log and drop, never block or fail the caller" (metrics.go:570-573).
+func (ms *MetricSystem) B200Dropped() uint64 {
+	e := engineFor(ms)
+	var st C.lh_stats
+	C.lh_get_stats(e.ctx, &st)
+	return atomic.LoadUint64(&e.dropped) + uint64(st.dropped)
 }
 
-func (e *b200Engine) flush(s *stagingShard) { // caller holds s.mu
-	if s.n > 0 {
-		C.lh_staging_commit_keyed_f64_u16(e.ctx, &s.slot, C.size_t(s.n), C.uint64_t(s.idsOff)) // ONE cgo call per batch
-		s.vals, s.ids, s.n = nil, nil, 0
-	}
+func (e *b200Engine) shard() *b200Shard {
+	var marker byte
+	h := uintptr(unsafe.Pointer(&marker)) // goroutine stacks are disjoint: a cheap, stable per-goroutine hash
+	h ^= h >> 17
+	return e.shards[(h>>10)%uintptr(len(e.shards))]
 }
 
-func (e *b200Engine) histoID(name string) uint16 {
-	e.histoMu.RLock()
-	id, ok := e.histoIDs[name]
-	e.histoMu.RUnlock()
+func intern(mu *sync.RWMutex, ids map[string]uint16, names *[]string, name string, limit int) (uint16, bool) {
+	mu.RLock()
+	id, ok := ids[name]
+	mu.RUnlock()
 	if ok {
-		return id
+		return id, true
 	}
-	e.histoMu.Lock()
-	defer e.histoMu.Unlock()
-	if id, ok = e.histoIDs[name]; !ok {
-		id = uint16(len(e.histoNames))
-		e.histoIDs[name] = id
-		e.histoNames = append(e.histoNames, name)
+	mu.Lock()
+	defer mu.Unlock()
+	if id, ok = ids[name]; ok {
+		return id, true
 	}
-	return id
+	if len(*names) >= limit || len(*names) >= 65536 {
+		return 0, false
+	}
+	id = uint16(len(*names))
+	ids[name] = id
+	*names = append(*names, name)
+	return id, true
 }
 
-var shardPick uint32
-
-// Histogram keeps metrics.go:273's signature and "never fails, never blocks on consumers" contract.
-func (ms *MetricSystem) Histogram(name string, value float64) {
-	e := ms.b200
-	id := e.histoID(name)
-	s := e.shards[atomic.AddUint32(&shardPick, 1)%uint32(len(e.shards))]
-	s.mu.Lock()
-	if s.vals == nil {
-		e.acquire(s)
+// openBuf acquires a pinned staging slot for b.  Called with the shard locked.
+func (e *b200Engine) openBuf(b *stagingBuf) bool {
+	if err := b200Status(C.lh_staging_acquire(e.ctx, &b.slot), e.ctx, "lh_staging_acquire"); err != nil {
+		glog.Errorf("loghisto (b200): %v; dropping", err)
+		return false
 	}
-	s.vals[s.n], s.ids[s.n] = value, id
-	s.n++
-	if s.n == s.cap {
-		e.flush(s)
-	}
-	s.mu.Unlock()
+	b.cap = int(uint64(b.slot.bytes)/10) &^ 15
+	b.idsOff = uint64(b.cap) * 8
+	base := unsafe.Pointer(b.slot.host)
+	b.items = unsafe.Slice((*uint64)(base), b.cap)
+	b.ids = unsafe.Slice((*uint16)(unsafe.Add(base, uintptr(b.idsOff))), b.cap)
+	b.n = 0
+	b.open = true
+	return true
 }
 
-// Counter keeps metrics.go:251's signature; amounts ride in a second staging slot per shard and are committed with
-// lh_staging_commit_counter_u16 (uint64 amounts at offset 0, uint16 ids at idsOff), exactly like Histogram.
+// commitHist / commitCounter hand the slot to the device (async H2D + kernel) and forget it.
+func (e *b200Engine) commitHist(b *stagingBuf) {
+	if !b.open {
+		return
+	}
+	st := C.lh_staging_commit_keyed_f64_u16(e.ctx, &b.slot, C.size_t(b.n), C.uint64_t(b.idsOff))
+	if err := b200Status(st, e.ctx, "lh_staging_commit_keyed_f64_u16"); err != nil {
+		glog.Errorf("loghisto (b200): %v; dropping %d samples", err, b.n)
+		atomic.AddUint64(&e.dropped, uint64(b.n))
+		C.lh_staging_abandon(e.ctx, &b.slot)
+	}
+	b.open, b.n, b.items, b.ids = false, 0, nil, nil
+}
+
+func (e *b200Engine) commitCounter(b *stagingBuf) {
+	if !b.open {
+		return
+	}
+	st := C.lh_staging_commit_counter_u16(e.ctx, &b.slot, C.size_t(b.n), C.uint64_t(b.idsOff))
+	if err := b200Status(st, e.ctx, "lh_staging_commit_counter_u16"); err != nil {
+		glog.Errorf("loghisto (b200): %v; dropping %d counter ops", err, b.n)
+		atomic.AddUint64(&e.dropped, uint64(b.n))
+		C.lh_staging_abandon(e.ctx, &b.slot)
+	}
+	b.open, b.n, b.items, b.ids = false, 0, nil, nil
+}
+
+// Counter is used for recording a running count of the total occurrences of
+// a particular event.  A rate is also exported for the amount that a counter
+// has increased during an interval of this MetricSystem.  (metrics.go:251-269)
 func (ms *MetricSystem) Counter(name string, amount uint64) {
-	e := ms.b200
-	id := e.counterID(name) // same interning idiom as histoID, over counterIDs / counterNames
-	s := e.counterShards[atomic.AddUint32(&shardPick, 1)%uint32(len(e.counterShards))]
+	e := engineFor(ms)
+	id, ok := intern(&e.counterMu, e.counterIDs, &e.counterNames, name, b200MaxCounters)
+	if !ok {
+		atomic.AddUint64(&e.dropped, 1)
+		return
+	}
+	s := e.shard()
 	s.mu.Lock()
-	if s.amounts == nil {
-		e.acquireCounter(s)
+	defer s.mu.Unlock()
+	s.touched[id] = true // the name shows up in Rates even when amount == 0
+	s.anyC = true
+	if amount == 0 {
+		return
 	}
-	s.amounts[s.n], s.ids[s.n] = amount, id
-	s.n++
-	if s.n == s.cap {
-		C.lh_staging_commit_counter_u16(e.ctx, &s.slot, C.size_t(s.n), C.uint64_t(s.idsOff))
-		s.amounts, s.ids, s.n = nil, nil, 0
+	b := &s.counter
+	if !b.open && !e.openBuf(b) {
+		atomic.AddUint64(&e.dropped, 1)
+		return
 	}
-	s.mu.Unlock()
+	b.items[b.n] = amount
+	b.ids[b.n] = id
+	b.n++
+	if b.n == b.cap {
+		e.commitCounter(b)
+	}
 }
 
-// StartTimer / TimerToken.Stop (metrics.go:232-246) are unchanged Go: Stop() calls Histogram(name, float64(ns)).
+// Histogram is used for generating rich metrics, such as percentiles, from
+// periodically occurring continuous values.  (metrics.go:273-295; compress() runs on the device, bit-exactly)
+func (ms *MetricSystem) Histogram(name string, value float64) {
+	e := engineFor(ms)
+	id, ok := intern(&e.histoMu, e.histoIDs, &e.histoNames, name, b200MaxHistograms)
+	if !ok {
+		atomic.AddUint64(&e.dropped, 1)
+		return
+	}
+	s := e.shard()
+	s.mu.Lock()
+	defer s.mu.Unlock()
+	b := &s.hist
+	if !b.open && !e.openBuf(b) {
+		atomic.AddUint64(&e.dropped, 1)
+		return
+	}
+	b.items[b.n] = math.Float64bits(value)
+	b.ids[b.n] = id
+	b.n++
+	if b.n == b.cap {
+		e.commitHist(b)
+	}
+}
 
-// collectRawMetrics keeps metrics.go:420's contract: interval-delta histograms (absent when untouched),
-// Rates = interval deltas, Counters = cumulative store.
+// collectRawMetrics, metrics.go:420-479: the cache swaps become lh_snapshot_begin (double-buffered device arrays),
+// the maps are rebuilt from the sparse export, and the percentile statistics the device reduced for exactly this
+// snapshot are parked beside the returned set for processMetrics.
 func (ms *MetricSystem) collectRawMetrics() *RawMetricSet {
-	e := ms.b200
+	e := engineFor(ms)
+	e.snapshotMu.Lock()
+	defer e.snapshotMu.Unlock()
+
+	normalizedInterval := time.Unix(0, time.Now().UnixNano()/
+		ms.interval.Nanoseconds()*
+		ms.interval.Nanoseconds())
+
+	// everything the shards hold goes to the device before the swap
+	touched := make([]bool, b200MaxCounters)
 	for _, s := range e.shards {
 		s.mu.Lock()
-		e.flush(s)
+		e.commitHist(&s.hist)
+		e.commitCounter(&s.counter)
+		if s.anyC {
+			for i, t := range s.touched {
+				if t {
+					touched[i] = true
+					s.touched[i] = false
+				}
+			}
+			s.anyC = false
+		}
 		s.mu.Unlock()
 	}
-	C.lh_snapshot_begin(e.ctx) // the cache swap of metrics.go:425-428 / 460-463
-	var sp C.lh_sparse
-	C.lh_snapshot_export(e.ctx, &sp)
-	H := len(e.histoNames)
-	offs := unsafe.Slice((*uint32)(unsafe.Pointer(sp.offsets)), maxHistograms+1)
-	keys := unsafe.Slice((*int16)(unsafe.Pointer(sp.keys)), int(sp.total_entries))
-	cnts := unsafe.Slice((*uint64)(unsafe.Pointer(sp.counts)), int(sp.total_entries))
-	histograms := make(map[string]map[int16]*uint64)
-	for h := 0; h < H; h++ {
-		if offs[h] == offs[h+1] {
-			continue // untouched this interval: absent, like a swapped-out empty cache
+
+	// percentile labels in one fixed order for this snapshot (map iteration order is random in Go)
+	red := &reducedSet{byName: map[string]*reducedHistogram{}}
+	for label, p := range ms.percentiles {
+		if len(red.labels) == C.LH_MAX_PERCENTILES {
+			glog.Errorf("loghisto (b200): more than %d percentiles configured; %q ignored", C.LH_MAX_PERCENTILES, label)
+			continue
 		}
-		m := make(map[int16]*uint64, offs[h+1]-offs[h])
-		for i := offs[h]; i < offs[h+1]; i++ {
-			c := cnts[i]
-			m[keys[i]] = &c
-		}
-		histograms[e.histoNames[h]] = m
+		red.labels = append(red.labels, label)
+		red.ps = append(red.ps, p)
 	}
-	// ... counter deltas from sp.counter_deltas -> rates; fold into ms.counterStore exactly as metrics.go:435-458
-	// ... gauges, normalized timestamp: unchanged Go code
-	// processMetrics may call lh_snapshot_reduce on the same frozen buffers; lh_snapshot_end releases them.
-	return &RawMetricSet{Histograms: histograms /* Time, Counters, Rates, Gauges as before */}
+	np := len(red.ps)
+
+	e.histoMu.RLock()
+	hnames := append([]string(nil), e.histoNames...)
+	e.histoMu.RUnlock()
+	e.counterMu.RLock()
+	cnames := append([]string(nil), e.counterNames...)
+	e.counterMu.RUnlock()
+
+	histograms := make(map[string]map[int16]*uint64)
+	rates := make(map[string]uint64)
+	deltas := make([]uint64, len(cnames))
+
+	if err := b200Status(C.lh_snapshot_begin(e.ctx), e.ctx, "lh_snapshot_begin"); err != nil {
+		glog.Errorf("loghisto (b200): %v; this interval's histograms and rates are lost", err)
+	} else {
+		const H = b200MaxHistograms
+		counts := make([]uint64, H)
+		sums := make([]float64, H)
+		avgs := make([]float64, H)
+		pkeys := make([]int32, H*np+1)
+		pvals := make([]float64, H*np+1)
+		var psPtr *C.double
+		if np > 0 {
+			psPtr = (*C.double)(unsafe.Pointer(&red.ps[0]))
+		}
+		st := C.lh_snapshot_reduce(e.ctx, psPtr, C.uint32_t(np),
+			(*C.uint64_t)(unsafe.Pointer(&counts[0])), (*C.double)(unsafe.Pointer(&sums[0])),
+			(*C.double)(unsafe.Pointer(&avgs[0])), (*C.int32_t)(unsafe.Pointer(&pkeys[0])),
+			(*C.double)(unsafe.Pointer(&pvals[0])))
+		var sp C.lh_sparse
+		if err := b200Status(st, e.ctx, "lh_snapshot_reduce"); err != nil {
+			glog.Errorf("loghisto (b200): %v", err)
+		} else if err := b200Status(C.lh_snapshot_export(e.ctx, &sp), e.ctx, "lh_snapshot_export"); err != nil {
+			glog.Errorf("loghisto (b200): %v", err)
+		} else {
+			// the pointers in sp are library-owned host memory, valid until the next export
+			offsets := unsafe.Slice((*uint32)(unsafe.Pointer(sp.offsets)), H+1)
+			total := int(sp.total_entries)
+			var keys []int16
+			var cnts []uint64
+			if total > 0 {
+				keys = unsafe.Slice((*int16)(unsafe.Pointer(sp.keys)), total)
+				cnts = unsafe.Slice((*uint64)(unsafe.Pointer(sp.counts)), total)
+			}
+			for h, name := range hnames {
+				a, b := int(offsets[h]), int(offsets[h+1])
+				if a == b {
+					continue // untouched this interval: absent, like a name missing from the swapped-out cache
+				}
+				backing := make([]uint64, b-a) // the RawMetricSet owns its counts forever (metrics.go:427, 462)
+				copy(backing, cnts[a:b])
+				m := make(map[int16]*uint64, b-a)
+				for i := a; i < b; i++ {
+					m[keys[i]] = &backing[i-a]
+				}
+				histograms[name] = m
+				red.byName[name] = &reducedHistogram{
+					count: counts[h], sum: sums[h], avg: avgs[h],
+					pkeys: append([]int32(nil), pkeys[h*np:(h+1)*np]...),
+					pvals: append([]float64(nil), pvals[h*np:(h+1)*np]...),
+				}
+			}
+			cd := unsafe.Slice((*uint64)(unsafe.Pointer(sp.counter_deltas)), b200MaxCounters)
+			copy(deltas, cd[:len(cnames)])
+		}
+		if err := b200Status(C.lh_snapshot_end(e.ctx), e.ctx, "lh_snapshot_end"); err != nil {
+			glog.Errorf("loghisto (b200): %v", err)
+		}
+	}
+
+	// Rates = this interval's deltas of the counters touched (metrics.go:430-433); Counters = cumulative store,
+	// including counters not touched this interval (metrics.go:435-458).  The store is the reference's own field.
+	counters := make(map[string]uint64)
+	ms.counterStoreMu.Lock()
+	for c, name := range cnames {
+		if deltas[c] == 0 && !touched[c] {
+			continue
+		}
+		rates[name] = deltas[c]
+		p, exists := ms.counterStore[name]
+		if !exists {
+			var z uint64
+			p = &z
+			ms.counterStore[name] = p
+		}
+		atomic.AddUint64(p, deltas[c])
+	}
+	for name, count := range ms.counterStore {
+		counters[name] = *count
+	}
+	ms.counterStoreMu.Unlock()
+
+	ms.gaugeFuncsMu.Lock()
+	gauges := make(map[string]float64)
+	for name, f := range ms.gaugeFuncs {
+		gauges[name] = f()
+	}
+	ms.gaugeFuncsMu.Unlock()
+
+	raw := &RawMetricSet{
+		Time:       normalizedInterval,
+		Counters:   counters,
+		Rates:      rates,
+		Histograms: histograms,
+		Gauges:     gauges,
+	}
+	e.putReduced(raw, red)
+	return raw
 }
 
-// processHistograms keeps metrics.go:336's signature and output keys; the numbers come from lh_snapshot_reduce,
-// which collectRawMetrics called once for the whole snapshot (results cached per histogram id in ms.b200.reduced).
-func (ms *MetricSystem) processHistograms(name string, valuesToCounts map[int16]*uint64) map[string]float64 {
-	e := ms.b200
-	r := e.reduced[name] // {count uint64; sum, avg float64; pkeys []int32; pvals []float64}
-	output := map[string]float64{
-		fmt.Sprintf("%s_count", name): float64(r.count),
-		fmt.Sprintf("%s_sum", name):   r.sum,
-		fmt.Sprintf("%s_avg", name):   r.avg,
+// processHistograms, metrics.go:336-387, for one histogram of a snapshot the device reduced: interval count / sum /
+// avg, the aggregate store update (uint64(totalSum) truncation included) and one value per percentile label.
+func (ms *MetricSystem) processHistograms(name string, r *reducedHistogram, labels []string) map[string]float64 {
+	output := make(map[string]float64)
+	sumName := fmt.Sprintf("%s_sum", name)
+	countName := fmt.Sprintf("%s_count", name)
+	avgName := fmt.Sprintf("%s_avg", name)
+
+	output[countName] = float64(r.count)
+	output[sumName] = r.sum
+	output[avgName] = r.avg
+
+	ms.histogramCountMu.Lock()
+	if _, present := ms.histogramCountStore[sumName]; !present {
+		var x, z uint64
+		ms.histogramCountStore[sumName] = &x
+		ms.histogramCountStore[countName] = &z
 	}
-	// aggregate store: unchanged Go (metrics.go:359-376), including uint64(totalSum)
-	ms.addToHistogramCountStore(name, uint64(r.sum), r.count)
-	i := 0
-	for label := range ms.percentiles { // e.percentileOrder fixes the label -> column mapping used at reduce time
-		if r.pkeys[i] != math.MinInt32 { // percentile() error (p > 1, NaN): logged and omitted, metrics.go:380-382
-			output[fmt.Sprintf(label, name)] = r.pvals[i]
+	atomic.AddUint64(ms.histogramCountStore[sumName], uint64(r.sum))
+	atomic.AddUint64(ms.histogramCountStore[countName], r.count)
+	ms.histogramCountMu.Unlock()
+
+	for j, label := range labels {
+		if r.pkeys[j] == math.MinInt32 { // percentile() returned its error (p > 1 or NaN): logged, key omitted
+			glog.Errorf("unable to calculate percentile: %s", "Invalid percentile.  Should be between 0 and 1.")
+			continue
 		}
-		i++
+		output[fmt.Sprintf(label, name)] = r.pvals[j]
 	}
 	return output
 }
 
-// In words: processHistograms (metrics.go:336) becomes a lookup into the arrays lh_snapshot_reduce filled:
-// <name>_count, _sum, _avg and one entry per percentile label whose pkeys[] is not INT32_MIN
-// (percentile()'s error case: key omitted, metrics.go:380-382).  The cumulative store update
-// (uint64(totalSum), metrics.go:374) and the reaper's integer _agg_avg (metrics.go:601-606) stay in Go.
+// processMetrics, metrics.go:483-506.  Accepts the sets collectRawMetrics produced (every caller in the reference:
+// the reaper at metrics.go:587 and metrics_test.go); a hand-built RawMetricSet has no device reduction to go with it,
+// so its histograms are reported as an error and skipped.
+func (ms *MetricSystem) processMetrics(rawMetrics *RawMetricSet) *ProcessedMetricSet {
+	e := engineFor(ms)
+	metrics := make(map[string]float64)
+
+	for name, count := range rawMetrics.Counters {
+		metrics[name] = float64(count)
+	}
+
+	for name, count := range rawMetrics.Rates {
+		metrics[fmt.Sprintf("%s_rate", name)] = float64(count)
+	}
+
+	red := e.takeReduced(rawMetrics)
+	for name := range rawMetrics.Histograms {
+		var r *reducedHistogram
+		if red != nil {
+			r = red.byName[name]
+		}
+		if r == nil {
+			glog.Errorf("loghisto (b200): no device reduction for histogram %q of this RawMetricSet; skipped", name)
+			continue
+		}
+		for histoName, histoValue := range ms.processHistograms(name, r, red.labels) {
+			metrics[histoName] = histoValue
+		}
+	}
+
+	for name, value := range rawMetrics.Gauges {
+		metrics[name] = value
+	}
+
+	return &ProcessedMetricSet{Time: rawMetrics.Time, Metrics: metrics}
+}

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -32,7 +33,7 @@ struct Buffer {
     std::vector<WriterEvent> writers;          // last ingest per stream
 };
 
-enum SlotState { SLOT_FREE = 0, SLOT_ACQUIRED = 1, SLOT_INFLIGHT = 2 };
+enum SlotState { SLOT_FREE = 0, SLOT_ACQUIRED = 1, SLOT_INFLIGHT = 2, SLOT_WAITED = 3 /* a thread is waiting for its kernel, mutex released */ };
 struct Slot {
     void *h = nullptr; void *d = nullptr;
     cudaEvent_t done = nullptr;      // kernel that consumed the slot has finished
@@ -87,7 +88,7 @@ K1Variant g_k1_variants[] = {
     BULK_VARIANT(16, 3, 65536, 1, 0),   // 6
 };
 constexpr int kNumK1Variants = (int)(sizeof(g_k1_variants) / sizeof(g_k1_variants[0]));
-constexpr int kDefaultK1Variant = 0;   // bulk2_w16_s4_32768_b1: best burst and sustained time (profiles/r01/k1_variants_sustained.txt)
+constexpr int kDefaultK1Variant = 6;   // 3 x 64 KB stages, negatives through the fix-up: best sustained time on streams U and N (profiles/r02/k1_sustained_r02c.txt)
 
 // Everything the kernels derive from `precision` (metrics.go:40-43), see lh_device.cuh.
 Prec make_prec(uint32_t precision) {
@@ -207,6 +208,7 @@ struct lh_ctx {
     // stats
     lh_stats stats{};
     std::mutex mu;
+    std::condition_variable slot_cv;     // a staging slot came back (see slot_wait_free)
     std::string last_error;
 };
 
@@ -337,9 +339,10 @@ lh_status launch_keyed_wc_spt(lh_ctx *ctx, int b, const IdT *ids, const ValT *va
     n4x4 = n4x4 / S::TILE * S::TILE;
     if (n4x4 == 0) return LH_OK;
     const size_t slice_tiles = std::max<size_t>(1, ((size_t)ctx->kp_chunk + (size_t)P * S::TILE - 1) / ((size_t)P * S::TILE));
-    // every (owner, writer) pair has its own sub-queue: 1.5x the expected records per pair per chunk, plus slack
+    // every (owner, writer) pair has its own sub-queue: 1.25x the expected records per pair per chunk, plus slack
+    // (records that do not fit take the exact L2 route, so this only trades speed on heavily skewed ids)
     const size_t expect = slice_tiles * S::TILE / P;
-    const size_t cap = ((expect * 3 / 2 + 4 * WC_LINE + WC_LINE - 1) / WC_LINE) * WC_LINE;
+    const size_t cap = ((expect * 5 / 4 + 3 * WC_LINE + WC_LINE - 1) / WC_LINE) * WC_LINE;
     if (!ctx->d_kp_queues || ctx->kp_cap != cap || ctx->kp_parts != P) {
         cudaFree(ctx->d_kp_queues); cudaFree(ctx->d_kp_cnt);
         ctx->d_kp_queues = nullptr; ctx->d_kp_cnt = nullptr;
@@ -485,47 +488,55 @@ lh_status launch_counter(lh_ctx *ctx, const IdT *d_ids, const uint64_t *d_amount
 
 // ---- staging ring (locked) ----
 // Called with ctx->mu held through `lk`.  The host-side wait for an in-flight slot happens with the mutex RELEASED
-// (the slot is parked as SLOT_ACQUIRED meanwhile so nobody else takes it): other ingest threads are never held up.
+// (the slot is parked as SLOT_WAITED meanwhile so nobody else takes it): other ingest threads are never held up by
+// it, and a thread that finds every slot either acquired or being waited for sleeps on slot_cv until one comes back.
 lh_status slot_wait_free(lh_ctx *ctx, std::unique_lock<std::mutex> &lk, int *out) {
-    // prefer a free slot that already has memory, then an in-flight one that has already finished, then a fresh
-    // slot (allocating its pinned + device memory), and only then wait for the oldest in-flight one
-    int best = -1, fresh = -1;
-    for (size_t i = 0; i < ctx->slots.size(); i++) {
-        if (ctx->slots[i].state != SLOT_FREE) continue;
-        if (ctx->slots[i].h) { *out = (int)i; return LH_OK; }
-        if (fresh < 0) fresh = (int)i;
-    }
-    for (size_t i = 0; i < ctx->slots.size(); i++)
-        if (ctx->slots[i].state == SLOT_INFLIGHT && cudaEventQuery(ctx->slots[i].done) == cudaSuccess) {
-            ctx->slots[i].state = SLOT_FREE;
-            *out = (int)i;
+    for (;;) {
+        // prefer a free slot that already has memory, then an in-flight one that has already finished, then a fresh
+        // slot (allocating its pinned + device memory), and only then wait for the oldest in-flight one
+        int best = -1, fresh = -1, waited = 0;
+        for (size_t i = 0; i < ctx->slots.size(); i++) {
+            if (ctx->slots[i].state == SLOT_WAITED) waited++;
+            if (ctx->slots[i].state != SLOT_FREE) continue;
+            if (ctx->slots[i].h) { *out = (int)i; return LH_OK; }
+            if (fresh < 0) fresh = (int)i;
+        }
+        for (size_t i = 0; i < ctx->slots.size(); i++)
+            if (ctx->slots[i].state == SLOT_INFLIGHT && cudaEventQuery(ctx->slots[i].done) == cudaSuccess) {
+                ctx->slots[i].state = SLOT_FREE;
+                *out = (int)i;
+                return LH_OK;
+            }
+        cudaGetLastError();   // cudaErrorNotReady from the queries above is not an error
+        if (fresh >= 0) {
+            Slot &sl = ctx->slots[fresh];
+            cudaError_t e = cudaMallocHost(&sl.h, ctx->staging_bytes);
+            if (e == cudaSuccess) e = cudaMalloc(&sl.d, ctx->staging_bytes);
+            if (e != cudaSuccess) {
+                if (sl.h) cudaFreeHost(sl.h);
+                sl.h = nullptr; sl.d = nullptr;
+                return fail(ctx, e == cudaErrorMemoryAllocation ? LH_ERR_NOMEM : LH_ERR_CUDA, "allocating a staging slot", e);
+            }
+            *out = fresh;
             return LH_OK;
         }
-    cudaGetLastError();   // cudaErrorNotReady from the queries above is not an error
-    if (fresh >= 0) {
-        Slot &sl = ctx->slots[fresh];
-        cudaError_t e = cudaMallocHost(&sl.h, ctx->staging_bytes);
-        if (e == cudaSuccess) e = cudaMalloc(&sl.d, ctx->staging_bytes);
-        if (e != cudaSuccess) {
-            if (sl.h) cudaFreeHost(sl.h);
-            sl.h = nullptr; sl.d = nullptr;
-            return fail(ctx, e == cudaErrorMemoryAllocation ? LH_ERR_NOMEM : LH_ERR_CUDA, "allocating a staging slot", e);
+        for (size_t i = 0; i < ctx->slots.size(); i++)
+            if (ctx->slots[i].state == SLOT_INFLIGHT && (best < 0 || ctx->slots[i].seq < ctx->slots[best].seq)) best = (int)i;
+        if (best >= 0) {
+            ctx->slots[best].state = SLOT_WAITED;
+            cudaEvent_t ev = ctx->slots[best].done;
+            lk.unlock();
+            cudaError_t e = cudaEventSynchronize(ev);
+            lk.lock();
+            ctx->slots[best].state = SLOT_FREE;
+            ctx->slot_cv.notify_all();
+            if (e != cudaSuccess) return fail(ctx, LH_ERR_CUDA, "cudaEventSynchronize(slot)", e);
+            *out = best;
+            return LH_OK;
         }
-        *out = fresh;
-        return LH_OK;
+        if (!waited) return fail(ctx, LH_ERR_STATE, "every staging slot is acquired and none is in flight");
+        ctx->slot_cv.wait(lk);   // other threads are waiting for kernels: one of them will free a slot (or take it; then retry)
     }
-    for (size_t i = 0; i < ctx->slots.size(); i++)
-        if (ctx->slots[i].state == SLOT_INFLIGHT && (best < 0 || ctx->slots[i].seq < ctx->slots[best].seq)) best = (int)i;
-    if (best < 0) return fail(ctx, LH_ERR_STATE, "every staging slot is acquired and none is in flight");
-    ctx->slots[best].state = SLOT_ACQUIRED;
-    cudaEvent_t ev = ctx->slots[best].done;
-    lk.unlock();
-    cudaError_t e = cudaEventSynchronize(ev);
-    lk.lock();
-    ctx->slots[best].state = SLOT_FREE;
-    if (e != cudaSuccess) return fail(ctx, LH_ERR_CUDA, "cudaEventSynchronize(slot)", e);
-    *out = best;
-    return LH_OK;
 }
 
 // close the IPC mappings of the peers (lh_comm_import), if any
@@ -681,11 +692,21 @@ extern "C" lh_status lh_create(const lh_config *cfg, lh_ctx **out) {
     for (int i = 0; i < kNumK1Variants; i++) {
         ctx->k1[i] = g_k1_variants[i];
         const bool probe = ctx->k1[i].launch == launch_probe;
-        ctx->k1[i].smem = probe ? 0 : ctx->k1[i].smem_fixed + ((size_t)2 * ctx->pc.win + 8) * 4;
-        if (ctx->k1[i].smem > kSmemBudget) {   // this shape does not fit at this precision: fall back to the register-pipelined kernel
-            ctx->k1[i] = g_k1_variants[3];
-            ctx->k1[i].name = g_k1_variants[i].name;
-            ctx->k1[i].smem = ((size_t)2 * ctx->pc.win + 8) * 4;
+        const size_t hist = ((size_t)2 * ctx->pc.win + 8) * 4;
+        ctx->k1[i].smem = probe ? 0 : ctx->k1[i].smem_fixed + hist;
+        if (ctx->k1[i].smem > kSmemBudget) {
+            // this ring does not fit beside the sub-histogram at this precision: take the next smaller ring with the same
+            // arithmetic, and the register-pipelined kernel when none fits
+            static const int smaller[] = {5, 0, 2, 3};
+            for (int j : smaller) {
+                if (g_k1_variants[j].smem_fixed + hist <= kSmemBudget) {
+                    const char *name = ctx->k1[i].name;
+                    ctx->k1[i] = g_k1_variants[j];
+                    ctx->k1[i].name = name;
+                    ctx->k1[i].smem = g_k1_variants[j].smem_fixed + hist;
+                    break;
+                }
+            }
         }
         LH_CREATE_CUDA(cudaFuncSetAttribute(ctx->k1[i].func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->k1[i].smem));
         int nb = 0;
@@ -839,6 +860,7 @@ lh_status ingest_host(lh_ctx *ctx, std::unique_lock<std::mutex> &lk, HostKind ki
         LH_CUDA(ctx, cudaEventRecord(sl.done, s));
         sl.state = SLOT_INFLIGHT;
         sl.seq = ++ctx->slot_seq;
+        ctx->slot_cv.notify_all();
         done += m;
     }
     if (pinned && last_copied) {
@@ -946,6 +968,7 @@ lh_status staging_commit(lh_ctx *ctx, const lh_staging *sg, HostKind kind, uint3
     LH_CUDA(ctx, cudaEventRecord(sl.done, s));
     sl.state = SLOT_INFLIGHT;
     sl.seq = ++ctx->slot_seq;
+    ctx->slot_cv.notify_all();
     return st;
 }
 }  // namespace
@@ -968,6 +991,7 @@ extern "C" lh_status lh_staging_abandon(lh_ctx *ctx, const lh_staging *s) {
     if (!s || s->slot >= ctx->slots.size()) return fail(ctx, LH_ERR_INVALID, "bad staging handle");
     if (ctx->slots[s->slot].state != SLOT_ACQUIRED) return fail(ctx, LH_ERR_STATE, "staging slot was not acquired");
     ctx->slots[s->slot].state = SLOT_FREE;
+    ctx->slot_cv.notify_all();
     return LH_OK;
 }
 

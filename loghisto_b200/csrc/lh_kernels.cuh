@@ -594,9 +594,10 @@ constexpr int WC_LINE = 64;                   // records per line (128 B)
 
 template <int SPT> struct WcShape {           // SPT = samples per thread per tile
     static constexpr int TILE = WC_THREADS * SPT;
-    // records one owner's buffer must hold: < WC_LINE carried over + one tile's share (TILE / P ~ TILE / 148)
-    // + 6 sigma of the binomial; beyond that the sample takes the L2 route
-    static constexpr int CAP = SPT == 16 ? 192 : 128;
+    static constexpr int FLUSH_EVERY = 16384 / TILE;            // tiles binned between two flushes (16384 samples)
+    // records one owner's buffer must hold: < WC_LINE carried over + the share of 16384 samples (~111 at P = 148)
+    // + 6 sigma of the binomial (63); beyond that the sample takes the L2 route
+    static constexpr int CAP = 256;
     // storage per owner: CAP + one spill line (the remainder copy reads a whole line) + 8 records of padding so that
     // the 128-bit accesses of the per-owner flush (thread o <-> owner o) are bank-conflict free
     static constexpr int STRIDE = CAP + WC_LINE + 8;
@@ -660,9 +661,8 @@ __global__ void __launch_bounds__(WC_THREADS, 1)
 k_ingest_keyed_wc(WcParams prm, Prec pc) {
     using S = WcShape<SPT>;
     constexpr int GROUPS = SPT / 4;
-    constexpr int NWARPS = WC_THREADS / 32;
     extern __shared__ __align__(16) unsigned char wc_smem[];
-    const uint32_t P = gridDim.x, p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t P = gridDim.x, p = blockIdx.x, tid = threadIdx.x;
     unsigned int *s_hist = reinterpret_cast<unsigned int *>(wc_smem);                       // [ids_per][win]
     const uint32_t hist_words = prm.ids_per * pc.win;
     unsigned int *s_fill = s_hist + ((hist_words + 3u) & ~3u);                              // records in each owner's buffer
@@ -687,6 +687,7 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
 
     unsigned long long cur[GROUPS][4], nxt[GROUPS][4];
     IdPack<IdT> cur_id[GROUPS], nxt_id[GROUPS];
+    uint32_t since_flush = 0;
     auto load_tile = [&](size_t tile, unsigned long long (&raw)[GROUPS][4], IdPack<IdT> (&idp)[GROUPS]) {
 #pragma unroll
         for (int g = 0; g < GROUPS; g++) {
@@ -739,33 +740,39 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
                         if (flag[j]) keyed_one_slow<ValT>(cur_id[g].get(j), cur[g][j], pc, prm.o, pol);
                 }
             }
-            __syncthreads();
-            // ---- flush: warp w takes owners w, w+16, ...; the 32 lanes copy each full 128-byte line to my sub-queue of
-            //      that owner with one coalesced 4-byte store each, then the remainder (< 64 records) moves to the front
-            for (uint32_t o = warp; o < P; o += NWARPS) {
-                const unsigned int n = min(s_fill[o], (unsigned int)S::CAP);
-                const unsigned int nfull = n / WC_LINE, rem = n - nfull * WC_LINE;
-                if (nfull == 0) { if (lane == 0) s_fill[o] = n; continue; }              // s_fill may have run past CAP
-                unsigned int off0 = s_off[o];
-                unsigned int *src = reinterpret_cast<unsigned int *>(s_buf + o * S::STRIDE);
-                unsigned int *dst = reinterpret_cast<unsigned int *>(qset + ((size_t)o * P + p) * cap + off0);
-                const unsigned int keep = src[nfull * 32 + lane];                          // the line holding the remainder
-                for (unsigned int l = 0; l < nfull; l++) {
-                    const unsigned int w = src[l * 32 + lane];
-                    if (off0 + WC_LINE <= cap) {
-                        dst[lane] = w;
-                        dst += 32;
-                        off0 += WC_LINE;
-                    } else {                                                               // sub-queue full: these records go the L2 route
-                        wc_spill(w & 0xFFFFu, o, P, pc, prm.o, pol);
-                        wc_spill(w >> 16, o, P, pc, prm.o, pol);
+            // ---- flush every FLUSH_EVERY tiles: thread o copies owner o's full 128-byte lines to my sub-queue of owner o
+            //      with 128-bit loads / stores and moves the remainder (< 64 records) to the front.  No barrier is needed
+            //      between tiles that do not flush: appends are atomic.
+            if (++since_flush == (uint32_t)S::FLUSH_EVERY) {
+                since_flush = 0;
+                __syncthreads();
+                if (tid < P) {
+                    const uint32_t o = tid;
+                    const unsigned int n = min(s_fill[o], (unsigned int)S::CAP);
+                    const unsigned int nfull = n / WC_LINE;
+                    unsigned int off0 = s_off[o];
+                    uint4 *src = reinterpret_cast<uint4 *>(s_buf + o * S::STRIDE);
+                    uint4 *dst = reinterpret_cast<uint4 *>(qset + ((size_t)o * P + p) * cap + off0);
+                    for (unsigned int l = 0; l < nfull; l++) {
+                        if (off0 + WC_LINE <= cap) {
+#pragma unroll
+                            for (int k = 0; k < 8; k++) dst[k] = src[l * 8 + k];
+                            dst += 8;
+                            off0 += WC_LINE;
+                        } else {                                                           // sub-queue full: these records go the L2 route
+                            const unsigned short *r = s_buf + o * S::STRIDE + l * WC_LINE;
+                            for (unsigned int k = 0; k < (unsigned int)WC_LINE; k++) wc_spill(r[k], o, P, pc, prm.o, pol);
+                        }
                     }
+                    s_off[o] = off0;
+                    if (nfull) {                                                           // remainder (a whole line is copied; only n % 64 records count)
+#pragma unroll
+                        for (int k = 0; k < 8; k++) src[k] = src[nfull * 8 + k];
+                    }
+                    s_fill[o] = n - nfull * WC_LINE;
                 }
-                __syncwarp();
-                src[lane] = keep;
-                if (lane == 0) { s_off[o] = off0; s_fill[o] = rem; }
+                __syncthreads();
             }
-            __syncthreads();
 #pragma unroll
             for (int g = 0; g < GROUPS; g++) {
                 cur_id[g] = nxt_id[g];
@@ -773,21 +780,27 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
                 for (int j = 0; j < 4; j++) cur[g][j] = nxt[g][j];
             }
         }
-        if (last_chunk) {   // the records still waiting in the buffers (< WC_LINE per owner) go out as one partial line
-            for (uint32_t o = warp; o < P; o += NWARPS) {
-                const unsigned int rem = s_fill[o];
-                if (!rem) continue;
-                const unsigned int off0 = s_off[o];
-                const unsigned int w = reinterpret_cast<unsigned int *>(s_buf + o * S::STRIDE)[lane];
-                if (off0 + WC_LINE <= cap) {
-                    reinterpret_cast<unsigned int *>(qset + ((size_t)o * P + p) * cap + off0)[lane] = w;
-                    if (lane == 0) s_off[o] = off0 + rem;
-                } else {
-                    if (2 * lane < rem) wc_spill(w & 0xFFFFu, o, P, pc, prm.o, pol);
-                    if (2 * lane + 1 < rem) wc_spill(w >> 16, o, P, pc, prm.o, pol);
+        __syncthreads();    // every append of this chunk's tiles is in the buffers
+        if (last_chunk) {   // everything still waiting in the buffers goes out, the last line of each owner partially filled
+            if (tid < P) {
+                const uint32_t o = tid;
+                const unsigned int n = min(s_fill[o], (unsigned int)S::CAP);
+                unsigned int off0 = s_off[o];
+                const uint4 *src = reinterpret_cast<const uint4 *>(s_buf + o * S::STRIDE);
+                for (unsigned int l = 0; l * WC_LINE < n; l++) {
+                    const unsigned int nrec = min((unsigned int)WC_LINE, n - l * WC_LINE);
+                    if (off0 + WC_LINE <= cap) {
+                        uint4 *dst = reinterpret_cast<uint4 *>(qset + ((size_t)o * P + p) * cap + off0);
+#pragma unroll
+                        for (int k = 0; k < 8; k++) dst[k] = src[l * 8 + k];
+                        off0 += nrec;
+                    } else {
+                        const unsigned short *r = s_buf + o * S::STRIDE + l * WC_LINE;
+                        for (unsigned int k = 0; k < nrec; k++) wc_spill(r[k], o, P, pc, prm.o, pol);
+                    }
                 }
-                __syncwarp();
-                if (lane == 0) s_fill[o] = 0;
+                s_off[o] = off0;
+                s_fill[o] = 0;
             }
             __syncthreads();
         }
@@ -802,18 +815,25 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
         {
             const uint4 *qv = reinterpret_cast<const uint4 *>(qset + (size_t)p * P * cap);
             const uint32_t total = P * vq;
-#pragma unroll 4
+#pragma unroll 2
             for (uint32_t v = tid; v < total; v += WC_THREADS) {
                 const uint32_t w = __umulhi(v, prm.inv_vq), i = v - w * vq;               // writer, vector inside its sub-queue
                 const unsigned int cnt = s_off[w];
                 if (i * 8u >= cnt) continue;
                 const uint4 v4 = __ldcg(qv + v);
                 const unsigned int ww[4] = {v4.x, v4.y, v4.z, v4.w};
-                const unsigned int nrec = min(8u, cnt - i * 8u);
+                if (i * 8u + 8u <= cnt) {                                                  // full vector: 8 unconditional increments
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (2u * k < nrec) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + (ww[k] & 0xFFFFu) * 4u) : "memory");
-                    if (2u * k + 1 < nrec) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + (ww[k] >> 16) * 4u) : "memory");
+                    for (int k = 0; k < 4; k++) {
+                        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + ((ww[k] << 2) & 0x3FFFCu)) : "memory");
+                        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + ((ww[k] >> 14) & 0x3FFFCu)) : "memory");
+                    }
+                } else {                                                                   // the last, partial vector of a sub-queue
+                    const unsigned int nrec = cnt - i * 8u;
+                    for (unsigned int k = 0; k < nrec; k++) {
+                        const unsigned int r = (ww[k >> 1] >> ((k & 1u) * 16u)) & 0xFFFFu;
+                        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + r * 4u) : "memory");
+                    }
                 }
             }
         }

@@ -137,20 +137,24 @@ double lhms_timer_loop(const char *name, unsigned threads, double seconds, int64
         const auto t0 = std::chrono::steady_clock::now();
         for (unsigned i = 0; i < threads; i++)
             workers.emplace_back([&] {
-                uint64_t mine = 0;
                 while (!stop.load(std::memory_order_relaxed)) {
                     for (int k = 0; k < 256; k++) {
                         loghisto::TimerToken timer = ms.StartTimer(nm);
                         timer.Stop();
                     }
-                    mine += 256;
+                    calls.fetch_add(256, std::memory_order_relaxed);
                 }
-                calls.fetch_add(mine);
             });
-        std::this_thread::sleep_for(std::chrono::duration<double>(seconds));
+        // the rate is taken over the last 60 % of the run: the first part pins the staging slots (a one-time cost)
+        std::this_thread::sleep_for(std::chrono::duration<double>(seconds * 0.4));
+        const uint64_t c0 = calls.load();
+        const auto t1 = std::chrono::steady_clock::now();
+        std::this_thread::sleep_for(std::chrono::duration<double>(seconds * 0.6));
+        const uint64_t c1 = calls.load();
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
         stop.store(true);
         for (auto &w : workers) w.join();
-        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        (void)t0;
         ms.Stop();
         // what the reaper delivered, plus one last collection for the tail of the run
         double reported = 0;
@@ -165,7 +169,7 @@ double lhms_timer_loop(const char *name, unsigned threads, double seconds, int64
         if (it != last->Metrics.end()) reported += it->second;
         if (total_calls) *total_calls = calls.load();
         if (reported_count) *reported_count = reported;
-        return (double)calls.load() / dt;
+        return (double)(c1 - c0) / dt;
     } catch (const std::exception &e) {
         fprintf(stderr, "lhms_timer_loop: %s\n", e.what());
         return -1.0;
