@@ -112,6 +112,8 @@ LH_API lh_status lh_counter_add_u32(lh_ctx *ctx, const uint32_t *d_ids, const ui
 LH_API lh_status lh_ingest_f64_host(lh_ctx *ctx, uint32_t histogram_id, const double *h_values, size_t n);
 LH_API lh_status lh_ingest_keyed_f64_u16_host(lh_ctx *ctx, const uint16_t *h_ids, const double *h_values,
                                        size_t n);
+LH_API lh_status lh_ingest_keyed_i64ns_u16_host(lh_ctx *ctx, const uint16_t *h_ids, const int64_t *h_nanos,
+                                         size_t n);
 LH_API lh_status lh_counter_add_u16_host(lh_ctx *ctx, const uint16_t *h_ids, const uint64_t *h_amounts,
                                   size_t n);
 

@@ -87,6 +87,7 @@ SIGNATURES = {
     "lh_counter_add_u32": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "lh_ingest_f64_host": (_i32, [_vp, _u32, _vp, _sz]),
     "lh_ingest_keyed_f64_u16_host": (_i32, [_vp, _vp, _vp, _sz]),
+    "lh_ingest_keyed_i64ns_u16_host": (_i32, [_vp, _vp, _vp, _sz]),
     "lh_counter_add_u16_host": (_i32, [_vp, _vp, _vp, _sz]),
     "lh_merge_counts_host": (_i32, [_vp, _vp, _vp, _vp, _sz]),
     "lh_staging_acquire": (_i32, [_vp, C.POINTER(lh_staging)]),

@@ -33,7 +33,9 @@ struct Buffer {
     std::vector<WriterEvent> writers;          // last ingest per stream
 };
 
-enum SlotState { SLOT_FREE = 0, SLOT_ACQUIRED = 1, SLOT_INFLIGHT = 2, SLOT_WAITED = 3 /* a thread is waiting for its kernel, mutex released */ };
+enum SlotState { SLOT_FREE = 0, SLOT_ACQUIRED = 1 /* handed to the caller (lh_staging_acquire) */, SLOT_INFLIGHT = 2,
+                 SLOT_WAITED = 3 /* a thread is waiting for its kernel, mutex released */,
+                 SLOT_FILLING = 4 /* lh_*_host is copying pageable memory into it, mutex released */ };
 struct Slot {
     void *h = nullptr; void *d = nullptr;
     cudaEvent_t done = nullptr;      // kernel that consumed the slot has finished
@@ -175,11 +177,12 @@ struct lh_ctx {
     int keyed_blocks_per_sm = 8;
     uint32_t hot_replicas = 1;          // copies of the hot window (all L2-resident); only the vector RED kernel spreads over them
     int keyed_mode = 0;                 // 0 auto, 1 force L2-atomic kernel, 2 force the write-combining owner kernel
-    int64_t kp_chunk = 16 << 20;        // samples per chunk of the owner-partitioned kernel
-    int wc_spt = 16;                    // samples per thread per tile of that kernel (8 or 16)
+    int64_t kp_chunk = 32 << 20;        // samples per chunk of the owner-partitioned kernel
+    int wc_spt = 4;                     // samples per thread per tile of that kernel (4: 1024 threads; 8, 16: 512 threads)
     // owner-partitioned keyed kernel scratch (allocated on first use)
     unsigned short *d_kp_queues = nullptr;
     unsigned int *d_kp_cnt = nullptr;     // per-(owner, writer) record counts, then the grid-barrier word
+    uint4 *d_kp_rare = nullptr;           // per-CTA lists of samples set aside for the exact path
     size_t kp_cap = 0;
     int kp_parts = 0;
     const char *keyed_kernel = "";       // kernel the last keyed launch used
@@ -344,8 +347,9 @@ lh_status launch_keyed_wc_spt(lh_ctx *ctx, int b, const IdT *ids, const ValT *va
     const size_t expect = slice_tiles * S::TILE / P;
     const size_t cap = ((expect * 5 / 4 + 3 * WC_LINE + WC_LINE - 1) / WC_LINE) * WC_LINE;
     if (!ctx->d_kp_queues || ctx->kp_cap != cap || ctx->kp_parts != P) {
-        cudaFree(ctx->d_kp_queues); cudaFree(ctx->d_kp_cnt);
-        ctx->d_kp_queues = nullptr; ctx->d_kp_cnt = nullptr;
+        cudaFree(ctx->d_kp_queues); cudaFree(ctx->d_kp_cnt); cudaFree(ctx->d_kp_rare);
+        ctx->d_kp_queues = nullptr; ctx->d_kp_cnt = nullptr; ctx->d_kp_rare = nullptr;
+        LH_CUDA(ctx, cudaMalloc(&ctx->d_kp_rare, (size_t)P * WC_RARE_CAP * sizeof(uint4)));
         LH_CUDA(ctx, cudaMalloc(&ctx->d_kp_queues, (size_t)2 * P * P * cap * sizeof(unsigned short)));
         LH_CUDA(ctx, cudaMalloc(&ctx->d_kp_cnt, ((size_t)2 * P * P + 1) * sizeof(unsigned int)));
         ctx->kp_cap = cap; ctx->kp_parts = P;
@@ -359,10 +363,10 @@ lh_status launch_keyed_wc_spt(lh_ctx *ctx, int b, const IdT *ids, const ValT *va
     prm.inv_p = (uint32_t)(((uint64_t)1 << 32) / (uint64_t)P) + 1u;
     prm.inv_vq = (uint32_t)(((uint64_t)1 << 32) / (uint64_t)(cap / 8)) + 1u;
     prm.slice_tiles = (uint32_t)slice_tiles; prm.queues = ctx->d_kp_queues; prm.q_cnt = ctx->d_kp_cnt;
-    prm.barrier = d_barrier; prm.o = keyed_out(ctx, b);
+    prm.barrier = d_barrier; prm.rare = ctx->d_kp_rare; prm.o = keyed_out(ctx, b);
     Prec pc = ctx->pc;
     void *args[] = {&prm, &pc};
-    LH_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(P), dim3(WC_THREADS), args, smem, s));
+    LH_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(P), dim3(S::THREADS), args, smem, s));
     ctx->stats.kernel_launches++;
     *used = true;
     *taken = n4x4;
@@ -370,7 +374,8 @@ lh_status launch_keyed_wc_spt(lh_ctx *ctx, int b, const IdT *ids, const ValT *va
 }
 template <typename IdT, typename ValT>
 lh_status launch_keyed_wc(lh_ctx *ctx, int b, const IdT *ids, const ValT *vals, size_t n4x4, cudaStream_t s, bool *used, size_t *taken) {
-    return ctx->wc_spt == 8 ? launch_keyed_wc_spt<IdT, ValT, 8>(ctx, b, ids, vals, n4x4, s, used, taken)
+    return ctx->wc_spt == 4 ? launch_keyed_wc_spt<IdT, ValT, 4>(ctx, b, ids, vals, n4x4, s, used, taken)
+         : ctx->wc_spt == 8 ? launch_keyed_wc_spt<IdT, ValT, 8>(ctx, b, ids, vals, n4x4, s, used, taken)
                             : launch_keyed_wc_spt<IdT, ValT, 16>(ctx, b, ids, vals, n4x4, s, used, taken);
 }
 
@@ -389,7 +394,7 @@ lh_status launch_keyed(lh_ctx *ctx, const IdT *d_ids, const ValT *d_vals, size_t
     while (done < n) {
         // no uint32 cell of the hot window may wrap: drain it before 2^32 samples have gone in
         const unsigned long long kCap = 0xFFFFFFFFull;
-        if (ctx->buf[b].hot_pending >= kCap) { st = fold_hot(ctx, b, s); if (st != LH_OK) return st; }
+        if (ctx->buf[b].hot_pending >= kCap - (1ull << 30)) { st = fold_hot(ctx, b, s); if (st != LH_OK) return st; }
         size_t m = (size_t)std::min<unsigned long long>(n - done, kCap - ctx->buf[b].hot_pending);
         const IdT *ids = d_ids + done;
         const ValT *vals = d_vals + done;
@@ -403,6 +408,7 @@ lh_status launch_keyed(lh_ctx *ctx, const IdT *d_ids, const ValT *d_vals, size_t
             k_ingest_keyed<IdT, ValT, T><<<1, T, 0, s>>>(ids, vals, head, ko, ctx->pc);
             ctx->stats.kernel_launches++;
         }
+        size_t hot_used = 0;
         if (n4) {
             bool used = false;
             // few histograms: their windows fit in shared memory (K1-style privatisation).  Up to KS_MAX_PASSES
@@ -425,6 +431,7 @@ lh_status launch_keyed(lh_ctx *ctx, const IdT *d_ids, const ValT *d_vals, size_t
                     ctx->stats.kernel_launches++;
                 }
                 used = true;
+                hot_used = n4 * 4;
                 ctx->keyed_kernel = "k_ingest_keyed_small";
             }
             if (!used && ctx->keyed_mode != 1) {
@@ -440,6 +447,7 @@ lh_status launch_keyed(lh_ctx *ctx, const IdT *d_ids, const ValT *d_vals, size_t
                 int grid = grid_1d(ctx, n4, T, 1, ctx->keyed_blocks_per_sm);
                 k_ingest_keyed_vec<IdT, ValT, T><<<grid, T, 0, s>>>(ids + head, vals + head, n4, ctx->hot_replicas, ko, ctx->pc);
                 ctx->stats.kernel_launches++;
+                hot_used = n4 * 4;
                 ctx->keyed_kernel = "k_ingest_keyed_vec";
             }
         }
@@ -450,7 +458,7 @@ lh_status launch_keyed(lh_ctx *ctx, const IdT *d_ids, const ValT *d_vals, size_t
             ctx->stats.kernel_launches++;
         }
         LH_CUDA(ctx, cudaGetLastError());
-        ctx->buf[b].hot_pending += m;
+        ctx->buf[b].hot_pending += hot_used;     // only k_ingest_keyed_small / _vec count into the uint32 hot window
         done += m;
     }
     LH_CUDA(ctx, cudaEventRecord(ctx->ev_t1, s));
@@ -470,15 +478,34 @@ lh_status launch_counter(lh_ctx *ctx, const IdT *d_ids, const uint64_t *d_amount
         constexpr int T = 512;
         const unsigned long long *amts = reinterpret_cast<const unsigned long long *>(d_amounts);
         if (ctx->C <= (uint32_t)K2_SMEM_COUNTERS) {
-            // privatised per CTA; one CTA per SM keeps the flush (C global atomics per CTA) small
-            int grid = grid_1d(ctx, n, T, 8, 2);
-            k_counter_add_smem<IdT, T><<<grid, T, (size_t)ctx->C * 8, s>>>(d_ids, amts, n, ctx->buf[b].d_counters, ctx->C, ctx->d_dropped);
+            // privatised per CTA (lo/hi halves in shared memory).  Vector body where the alignment allows: 4 ops per
+            // thread and iteration; ragged head / tail through the scalar form of the same kernel.
+            size_t head = std::min<size_t>(n, ((32u - ((uintptr_t)amts & 31u)) & 31u) / 8u);
+            const bool vec_ok = (((uintptr_t)(d_ids + head)) & (4 * sizeof(IdT) - 1)) == 0 && (((uintptr_t)amts & 7u) == 0);
+            size_t n4 = vec_ok ? (n - head) / 4 : 0;
+            if (n4 < 4096) { head = 0; n4 = 0; }
+            const size_t tail_off = head + n4 * 4;
+            if (head) {
+                k_counter_add_smem<IdT, T><<<1, T, (size_t)ctx->C * 8, s>>>(d_ids, amts, head, ctx->buf[b].d_counters, ctx->C, ctx->d_dropped);
+                ctx->stats.kernel_launches++;
+            }
+            if (n4) {
+                // one CTA per SM (the per-CTA flush is C global atomics), fewer for small batches
+                const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, ctx->sm_count - ctx->k1_reserve_sms) * 2, n4 / (T * 4)));
+                k_counter_add_smem_vec<IdT, T><<<grid, T, (size_t)ctx->C * 8, s>>>(d_ids + head, amts + head, n4, ctx->buf[b].d_counters, ctx->C, ctx->d_dropped);
+                ctx->stats.kernel_launches++;
+            }
+            if (tail_off < n) {
+                int grid = grid_1d(ctx, n - tail_off, T, 8, 2);
+                k_counter_add_smem<IdT, T><<<grid, T, (size_t)ctx->C * 8, s>>>(d_ids + tail_off, amts + tail_off, n - tail_off, ctx->buf[b].d_counters, ctx->C, ctx->d_dropped);
+                ctx->stats.kernel_launches++;
+            }
         } else {
             int grid = grid_1d(ctx, n, T, 4, 4);
             k_counter_add<IdT, T><<<grid, T, 0, s>>>(d_ids, amts, n, ctx->buf[b].d_counters, ctx->C, ctx->d_dropped);
+            ctx->stats.kernel_launches++;
         }
         LH_CUDA(ctx, cudaGetLastError());
-        ctx->stats.kernel_launches++;
     }
     LH_CUDA(ctx, cudaEventRecord(ctx->ev_t1, s));
     ctx->timing_valid = true;
@@ -496,7 +523,7 @@ lh_status slot_wait_free(lh_ctx *ctx, std::unique_lock<std::mutex> &lk, int *out
         // slot (allocating its pinned + device memory), and only then wait for the oldest in-flight one
         int best = -1, fresh = -1, waited = 0;
         for (size_t i = 0; i < ctx->slots.size(); i++) {
-            if (ctx->slots[i].state == SLOT_WAITED) waited++;
+            if (ctx->slots[i].state == SLOT_WAITED || ctx->slots[i].state == SLOT_FILLING) waited++;   // will come back by itself
             if (ctx->slots[i].state != SLOT_FREE) continue;
             if (ctx->slots[i].h) { *out = (int)i; return LH_OK; }
             if (fresh < 0) fresh = (int)i;
@@ -689,6 +716,8 @@ extern "C" lh_status lh_create(const lh_config *cfg, lh_ctx **out) {
 
     LH_CREATE_CUDA(cudaFuncSetAttribute((const void *)k_counter_add_smem<unsigned short, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_COUNTERS * 8));
     LH_CREATE_CUDA(cudaFuncSetAttribute((const void *)k_counter_add_smem<unsigned int, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_COUNTERS * 8));
+    LH_CREATE_CUDA(cudaFuncSetAttribute((const void *)k_counter_add_smem_vec<unsigned short, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_COUNTERS * 8));
+    LH_CREATE_CUDA(cudaFuncSetAttribute((const void *)k_counter_add_smem_vec<unsigned int, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_COUNTERS * 8));
     for (int i = 0; i < kNumK1Variants; i++) {
         ctx->k1[i] = g_k1_variants[i];
         const bool probe = ctx->k1[i].launch == launch_probe;
@@ -736,7 +765,7 @@ extern "C" lh_status lh_destroy(lh_ctx *ctx) {
         for (auto &w : ctx->buf[b].writers) cudaEventDestroy(w.ev);
     }
     cudaFree(ctx->d_decomp); cudaFree(ctx->d_dropped);
-    cudaFree(ctx->d_kp_queues); cudaFree(ctx->d_kp_cnt);
+    cudaFree(ctx->d_kp_queues); cudaFree(ctx->d_kp_cnt); cudaFree(ctx->d_kp_rare);
     for (int i = 0; i < 3; i++) {
         cudaFree(ctx->d_ps[i]); cudaFree(ctx->d_res[i]);
         if (ctx->h_res[i]) cudaFreeHost(ctx->h_res[i]);
@@ -808,7 +837,7 @@ extern "C" lh_status lh_counter_add_u32(lh_ctx *ctx, const uint32_t *d_ids, cons
 // Chunks of staging_bytes go through the slot ring: (memcpy into pinned if the
 // source is pageable) -> async H2D -> kernel, all on the ingest stream.
 namespace {
-enum HostKind { HK_SINGLE, HK_KEYED_U16, HK_COUNTER_U16 };
+enum HostKind { HK_SINGLE, HK_KEYED_U16, HK_COUNTER_U16, HK_KEYED_I64_U16 };
 
 lh_status ingest_host(lh_ctx *ctx, std::unique_lock<std::mutex> &lk, HostKind kind, uint32_t hid,
                       const void *h_a /* 8-byte items */, const uint16_t *h_ids, size_t n) {
@@ -834,7 +863,7 @@ lh_status ingest_host(lh_ctx *ctx, std::unique_lock<std::mutex> &lk, HostKind ki
         if (!pinned) {
             // pageable source: stage through the slot's pinned buffer.  The memcpy (milliseconds per 32 MiB) runs with
             // the context mutex RELEASED -- the slot is parked as ACQUIRED so no other thread can take it.
-            sl.state = SLOT_ACQUIRED;
+            sl.state = SLOT_FILLING;
             lk.unlock();
             memcpy(sl.h, src_a, m * 8);
             if (h_ids) memcpy((char *)sl.h + per * 8, h_ids + done, m * 2);
@@ -855,6 +884,7 @@ lh_status ingest_host(lh_ctx *ctx, std::unique_lock<std::mutex> &lk, HostKind ki
         ctx->stats.h2d_bytes += m * item;
         if (kind == HK_SINGLE) st = launch_single(ctx, hid, (const double *)d_a, m, s);
         else if (kind == HK_KEYED_U16) st = launch_keyed<unsigned short, double>(ctx, (const unsigned short *)d_i, (const double *)d_a, m, s);
+        else if (kind == HK_KEYED_I64_U16) st = launch_keyed<unsigned short, long long>(ctx, (const unsigned short *)d_i, (const long long *)d_a, m, s);
         else st = launch_counter<unsigned short>(ctx, (const unsigned short *)d_i, (const uint64_t *)d_a, m, s);
         if (st != LH_OK) { sl.state = SLOT_FREE; return st; }
         LH_CUDA(ctx, cudaEventRecord(sl.done, s));
@@ -885,6 +915,11 @@ extern "C" lh_status lh_ingest_keyed_f64_u16_host(lh_ctx *ctx, const uint16_t *h
     LH_ENTER(ctx);
     if (n && (!h_ids || !h_values)) return fail(ctx, LH_ERR_INVALID, "NULL input");
     return ingest_host(ctx, _lk, HK_KEYED_U16, 0, h_values, h_ids, n);
+}
+extern "C" lh_status lh_ingest_keyed_i64ns_u16_host(lh_ctx *ctx, const uint16_t *h_ids, const int64_t *h_nanos, size_t n) {
+    LH_ENTER(ctx);
+    if (n && (!h_ids || !h_nanos)) return fail(ctx, LH_ERR_INVALID, "NULL input");
+    return ingest_host(ctx, _lk, HK_KEYED_I64_U16, 0, h_nanos, h_ids, n);
 }
 extern "C" lh_status lh_counter_add_u16_host(lh_ctx *ctx, const uint16_t *h_ids, const uint64_t *h_amounts, size_t n) {
     LH_ENTER(ctx);
@@ -1527,7 +1562,7 @@ extern "C" lh_status lh_tune(lh_ctx *ctx, const char *key, int64_t value) {
         return LH_OK;
     }
     if (!strcmp(key, "wc_spt")) {
-        if (value != 8 && value != 16) return fail(ctx, LH_ERR_RANGE, "wc_spt is 8 or 16");
+        if (value != 4 && value != 8 && value != 16) return fail(ctx, LH_ERR_RANGE, "wc_spt is 4, 8 or 16");
         ctx->wc_spt = (int)value;
         return LH_OK;
     }

@@ -427,15 +427,22 @@ __device__ __forceinline__ void keyed_one(uint32_t id, ValT raw, const Prec &pc,
     }
     red_add_u32_keep(&hot[(size_t)id * (2u * pc.win) + idx], 1u, pol);
 }
+// The same sample straight into the uint64 arrays (one 64-bit atomic + the histogram's flag): for the few samples
+// that reach the scalar kernel (ragged heads / tails) and the rare paths of the write-combining kernel, so that those
+// launches leave nothing in the uint32 hot window for the snapshot to fold.
+template <typename ValT>
+__device__ __forceinline__ void keyed_one_direct(uint32_t id, ValT raw, const Prec &pc, const KeyedOut &o) {
+    if (id >= o.H) { atomicAdd(o.dropped, 1ull); return; }
+    add_bucket_global(o.buckets + (size_t)id * 65536u, o.flags + id, key16_of(sample_to_f64<ValT>(raw), pc), 1ull, pc.win);
+}
 
 // Out-of-line form for kernels whose common path must stay small (the write-combining kernel calls it for the
 // ~0.05 % of samples its fast path does not cover).
 template <typename ValT>
-__device__ __noinline__ void keyed_one_slow(uint32_t id, unsigned long long raw, Prec pc, KeyedOut o, uint64_t pol) {
-    if (id == 0xFFFFFFFFu) return;            // padding lane past the end of the batch
+__device__ __noinline__ void keyed_one_slow(uint32_t id, unsigned long long raw, Prec pc, KeyedOut o) {
     ValT r;
     memcpy(&r, &raw, 8);
-    keyed_one<ValT>(id, r, pc, o, o.hot, pol);
+    keyed_one_direct<ValT>(id, r, pc, o);
 }
 
 template <typename IdT>
@@ -454,6 +461,25 @@ __device__ __forceinline__ void load_vals4(const void *vals, size_t g, unsigned 
     asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
                  : "=l"(raw[0]), "=l"(raw[1]), "=l"(raw[2]), "=l"(raw[3]) : "l"(reinterpret_cast<const char *>(vals) + g * 32));
 }
+
+// ids of one 4-sample group, kept PACKED while they wait in registers (unpacking right after the load would make the
+// prefetch wait for its own data)
+template <typename IdT> struct IdPack;
+template <> struct IdPack<unsigned short> {
+    unsigned int lo, hi;
+    __device__ __forceinline__ void load(const unsigned short *ids, size_t g) {
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "l"(reinterpret_cast<const char *>(ids) + g * 8));
+    }
+    __device__ __forceinline__ uint32_t get(int j) const { const unsigned int w = j < 2 ? lo : hi; return (j & 1) ? (w >> 16) : (w & 0xFFFFu); }
+};
+template <> struct IdPack<unsigned int> {
+    unsigned int w[4];
+    __device__ __forceinline__ void load(const unsigned int *ids, size_t g) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                     : "l"(reinterpret_cast<const char *>(ids) + g * 16));
+    }
+    __device__ __forceinline__ uint32_t get(int j) const { return w[j]; }
+};
 
 // Vector body: every thread takes 4 consecutive pairs (one 256-bit value load, one 64/128-bit id load).
 // vals must be 32-byte aligned and ids 4*sizeof(IdT)-aligned; n4 = number of 4-sample groups.
@@ -484,10 +510,9 @@ k_ingest_keyed_vec(const IdT *__restrict__ ids, const ValT *__restrict__ vals, s
 template <typename IdT, typename ValT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_ingest_keyed(const IdT *__restrict__ ids, const ValT *__restrict__ vals, size_t n, KeyedOut o, Prec pc) {
-    const uint64_t pol = policy_evict_last();
     const size_t stride = (size_t)gridDim.x * THREADS;
     for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += stride)
-        keyed_one<ValT>((uint32_t)ids[i], vals[i], pc, o, o.hot, pol);
+        keyed_one_direct<ValT>((uint32_t)ids[i], vals[i], pc, o);
 }
 
 // ------------------------------------------------------------------ K1k/small
@@ -588,12 +613,12 @@ k_ingest_keyed_small(const IdT *__restrict__ ids, const ValT *__restrict__ vals,
 // Samples the window does not cover (negative, |v| >= 2^63, NaN/Inf, estimates within eps of a bucket boundary),
 // ids >= H, and records that do not fit their buffer or sub-queue (heavily skewed ids) take the exact L2-atomic
 // route of keyed_one().  At the end each CTA adds its windows into the uint32 hot window.
-constexpr int WC_THREADS = 512;
 constexpr int WC_MAX_PARTS = 160;             // owners = CTAs (one per SM)
 constexpr int WC_LINE = 64;                   // records per line (128 B)
 
 template <int SPT> struct WcShape {           // SPT = samples per thread per tile
-    static constexpr int TILE = WC_THREADS * SPT;
+    static constexpr int THREADS = SPT == 4 ? 1024 : 512;      // SPT 4 fits 64 registers per thread: twice the warps per SM
+    static constexpr int TILE = THREADS * SPT;
     static constexpr int FLUSH_EVERY = 16384 / TILE;            // tiles binned between two flushes (16384 samples)
     // records one owner's buffer must hold: < WC_LINE carried over + the share of 16384 samples (~111 at P = 148)
     // + 6 sigma of the binomial (63); beyond that the sample takes the L2 route
@@ -615,8 +640,10 @@ struct WcParams {
     unsigned short *queues;          // [2][P owners][P writers][cap]
     unsigned int *q_cnt;             // [2][P owners][P writers]
     unsigned int *barrier;           // grid barrier counter, zeroed by the host before the launch
+    uint4 *rare;                     // [P][WC_RARE_CAP] samples set aside for the exact path: {raw lo, raw hi, id, -}
     KeyedOut o;
 };
+constexpr uint32_t WC_RARE_CAP = 8192;       // per CTA and chunk; beyond that a rare sample is resolved on the spot
 
 __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int target) {
     __syncthreads();
@@ -631,35 +658,17 @@ __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int tar
     __syncthreads();
 }
 
-// a record that could not be queued: add it to the hot window directly (exact, one L2 atomic)
-__device__ __forceinline__ void wc_spill(uint32_t rec, uint32_t owner, uint32_t P, const Prec &pc, const KeyedOut &o, uint64_t pol) {
-    const uint32_t lid = rec / pc.win, slot = rec - lid * pc.win;
-    red_add_u32_keep(&o.hot[(size_t)(lid * P + owner) * (2u * pc.win) + slot], 1u, pol);
+// a record that could not be queued: add it to its bucket directly (exact, one L2 atomic; positive rows: slot == key)
+__device__ __forceinline__ void wc_spill(uint32_t rec, uint32_t owner, uint32_t P, const Prec &pc, const KeyedOut &o) {
+    const uint32_t lid = rec / pc.win, slot = rec - lid * pc.win, id = lid * P + owner;
+    add_bucket_global(o.buckets + (size_t)id * 65536u, o.flags + id, slot, 1ull, pc.win);
 }
 
-// ids of one 4-sample group, kept PACKED while they wait in registers (unpacking right after the load would make the
-// prefetch wait for its own data)
-template <typename IdT> struct IdPack;
-template <> struct IdPack<unsigned short> {
-    unsigned int lo, hi;
-    __device__ __forceinline__ void load(const unsigned short *ids, size_t g) {
-        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "l"(reinterpret_cast<const char *>(ids) + g * 8));
-    }
-    __device__ __forceinline__ uint32_t get(int j) const { const unsigned int w = j < 2 ? lo : hi; return (j & 1) ? (w >> 16) : (w & 0xFFFFu); }
-};
-template <> struct IdPack<unsigned int> {
-    unsigned int w[4];
-    __device__ __forceinline__ void load(const unsigned int *ids, size_t g) {
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
-                     : "l"(reinterpret_cast<const char *>(ids) + g * 16));
-    }
-    __device__ __forceinline__ uint32_t get(int j) const { return w[j]; }
-};
-
 template <typename IdT, typename ValT, int SPT>
-__global__ void __launch_bounds__(WC_THREADS, 1)
+__global__ void __launch_bounds__(WcShape<SPT>::THREADS, 1)
 k_ingest_keyed_wc(WcParams prm, Prec pc) {
     using S = WcShape<SPT>;
+    constexpr int WC_THREADS = S::THREADS;
     constexpr int GROUPS = SPT / 4;
     extern __shared__ __align__(16) unsigned char wc_smem[];
     const uint32_t P = gridDim.x, p = blockIdx.x, tid = threadIdx.x;
@@ -669,11 +678,12 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
     unsigned int *s_off = s_fill + WC_MAX_PARTS;                                            // records appended to my sub-queues this chunk; phase B: record counts
     unsigned short *s_buf = reinterpret_cast<unsigned short *>(s_off + WC_MAX_PARTS);       // [P + 1][STRIDE], row P = trash
     const uint32_t fill_addr = smem_u32(s_fill), buf_addr = smem_u32(s_buf), hist_addr = smem_u32(s_hist);
+    unsigned int *s_rare = s_fill + (WC_MAX_PARTS - 1);                                     // samples set aside this chunk (slot P..158 of s_fill are free)
+    uint4 *rareq = prm.rare + (size_t)p * WC_RARE_CAP;
     const uint32_t trash_slot = P * (uint32_t)S::STRIDE + (uint32_t)S::CAP;                 // never read
 
     for (uint32_t i = tid; i < hist_words; i += WC_THREADS) s_hist[i] = 0;
     if (tid < WC_MAX_PARTS) { s_fill[tid] = 0; s_off[tid] = 0; }
-    const uint64_t pol = policy_evict_last();
     uint32_t one_bits;
     asm volatile("mov.b32 %0, 0x3F800000;" : "=r"(one_bits));
     __syncthreads();
@@ -735,41 +745,51 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
                     any |= flag[j];
                 }
                 if (__any_sync(0xFFFFFFFFu, any)) {
+                    // set the sample aside: the exact path (FP64 log, ~1K cycles) is run for all of them together at the end of
+                    // the chunk, every lane busy, instead of stalling this warp lane by lane in the middle of the stream
 #pragma unroll
                     for (int j = 0; j < 4; j++)
-                        if (flag[j]) keyed_one_slow<ValT>(cur_id[g].get(j), cur[g][j], pc, prm.o, pol);
+                        if (flag[j]) {
+                            const unsigned int at = atomicAdd(s_rare, 1u);
+                            if (at < WC_RARE_CAP) rareq[at] = make_uint4((unsigned int)cur[g][j], (unsigned int)(cur[g][j] >> 32), cur_id[g].get(j), 0u);
+                            else keyed_one_slow<ValT>(cur_id[g].get(j), cur[g][j], pc, prm.o);
+                        }
                 }
             }
-            // ---- flush every FLUSH_EVERY tiles: thread o copies owner o's full 128-byte lines to my sub-queue of owner o
-            //      with 128-bit loads / stores and moves the remainder (< 64 records) to the front.  No barrier is needed
-            //      between tiles that do not flush: appends are atomic.
+            // ---- flush every FLUSH_EVERY tiles.  A quarter warp (8 lanes x 16 B = one 128-byte line) serves one owner:
+            //      its full lines go to my sub-queue of that owner as coalesced 128-byte stores, the remainder (< 64
+            //      records) moves to the front.  No barrier is needed between tiles that do not flush: appends are atomic.
             if (++since_flush == (uint32_t)S::FLUSH_EVERY) {
                 since_flush = 0;
                 __syncthreads();
-                if (tid < P) {
-                    const uint32_t o = tid;
-                    const unsigned int n = min(s_fill[o], (unsigned int)S::CAP);
-                    const unsigned int nfull = n / WC_LINE;
-                    unsigned int off0 = s_off[o];
-                    uint4 *src = reinterpret_cast<uint4 *>(s_buf + o * S::STRIDE);
-                    uint4 *dst = reinterpret_cast<uint4 *>(qset + ((size_t)o * P + p) * cap + off0);
-                    for (unsigned int l = 0; l < nfull; l++) {
-                        if (off0 + WC_LINE <= cap) {
-#pragma unroll
-                            for (int k = 0; k < 8; k++) dst[k] = src[l * 8 + k];
-                            dst += 8;
-                            off0 += WC_LINE;
-                        } else {                                                           // sub-queue full: these records go the L2 route
-                            const unsigned short *r = s_buf + o * S::STRIDE + l * WC_LINE;
-                            for (unsigned int k = 0; k < (unsigned int)WC_LINE; k++) wc_spill(r[k], o, P, pc, prm.o, pol);
+                const uint32_t sub = (tid & 31) >> 3, k8 = tid & 7;
+                for (uint32_t base = (tid >> 5) * 4; base < P; base += (WC_THREADS / 32) * 4) {   // warp-uniform trip count
+                    const uint32_t o = base + sub;
+                    const bool act = o < P;
+                    unsigned int n = 0, nfull = 0, off0 = 0;
+                    uint4 keep = make_uint4(0, 0, 0, 0);
+                    uint4 *src = reinterpret_cast<uint4 *>(s_buf + (act ? o : 0) * S::STRIDE);
+                    if (act) {
+                        n = min(s_fill[o], (unsigned int)S::CAP);
+                        nfull = n / WC_LINE;
+                        off0 = s_off[o];
+                        unsigned short *qbase = qset + ((size_t)o * P + p) * cap;
+                        keep = src[nfull * 8 + k8];                                        // the line that holds the remainder
+                        for (unsigned int l = 0; l < nfull; l++) {
+                            if (off0 + WC_LINE <= cap) {
+                                reinterpret_cast<uint4 *>(qbase + off0)[k8] = src[l * 8 + k8];
+                                off0 += WC_LINE;
+                            } else if (k8 == 0) {                                          // sub-queue full: these records go the L2 route
+                                const unsigned short *r = s_buf + o * S::STRIDE + l * WC_LINE;
+                                for (unsigned int k = 0; k < (unsigned int)WC_LINE; k++) wc_spill(r[k], o, P, pc, prm.o);
+                            }
                         }
                     }
-                    s_off[o] = off0;
-                    if (nfull) {                                                           // remainder (a whole line is copied; only n % 64 records count)
-#pragma unroll
-                        for (int k = 0; k < 8; k++) src[k] = src[nfull * 8 + k];
+                    __syncwarp();
+                    if (act) {
+                        if (nfull) src[k8] = keep;
+                        if (k8 == 0) { s_off[o] = off0; s_fill[o] = n - nfull * WC_LINE; }
                     }
-                    s_fill[o] = n - nfull * WC_LINE;
                 }
                 __syncthreads();
             }
@@ -781,6 +801,18 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
             }
         }
         __syncthreads();    // every append of this chunk's tiles is in the buffers
+        {   // the samples set aside: exact path, all threads at once
+            const unsigned int nr = min(*s_rare, WC_RARE_CAP);
+            for (unsigned int i = tid; i < nr; i += WC_THREADS) {
+                const uint4 e = rareq[i];
+                ValT r;
+                const unsigned long long raw = ((unsigned long long)e.y << 32) | e.x;
+                memcpy(&r, &raw, 8);
+                keyed_one_direct<ValT>(e.z, r, pc, prm.o);
+            }
+            __syncthreads();
+            if (tid == 0) *s_rare = 0;
+        }
         if (last_chunk) {   // everything still waiting in the buffers goes out, the last line of each owner partially filled
             if (tid < P) {
                 const uint32_t o = tid;
@@ -796,7 +828,7 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
                         off0 += nrec;
                     } else {
                         const unsigned short *r = s_buf + o * S::STRIDE + l * WC_LINE;
-                        for (unsigned int k = 0; k < nrec; k++) wc_spill(r[k], o, P, pc, prm.o, pol);
+                        for (unsigned int k = 0; k < nrec; k++) wc_spill(r[k], o, P, pc, prm.o);
                     }
                 }
                 s_off[o] = off0;
@@ -821,20 +853,20 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
                 const unsigned int cnt = s_off[w];
                 if (i * 8u >= cnt) continue;
                 const uint4 v4 = __ldcg(qv + v);
-                const unsigned int ww[4] = {v4.x, v4.y, v4.z, v4.w};
+#define LH_WC_INC2(word)                                                                                              \
+                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + (((word) << 2) & 0x3FFFCu)) : "memory"); \
+                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + (((word) >> 14) & 0x3FFFCu)) : "memory");
                 if (i * 8u + 8u <= cnt) {                                                  // full vector: 8 unconditional increments
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + ((ww[k] << 2) & 0x3FFFCu)) : "memory");
-                        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + ((ww[k] >> 14) & 0x3FFFCu)) : "memory");
-                    }
+                    LH_WC_INC2(v4.x) LH_WC_INC2(v4.y) LH_WC_INC2(v4.z) LH_WC_INC2(v4.w)
                 } else {                                                                   // the last, partial vector of a sub-queue
                     const unsigned int nrec = cnt - i * 8u;
+                    unsigned long long lo64 = ((unsigned long long)v4.y << 32) | v4.x, hi64 = ((unsigned long long)v4.w << 32) | v4.z;
                     for (unsigned int k = 0; k < nrec; k++) {
-                        const unsigned int r = (ww[k >> 1] >> ((k & 1u) * 16u)) & 0xFFFFu;
+                        const unsigned int r = (unsigned int)((k < 4 ? lo64 >> (16u * k) : hi64 >> (16u * (k - 4u))) & 0xFFFFull);
                         asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + r * 4u) : "memory");
                     }
                 }
+#undef LH_WC_INC2
             }
         }
         __syncthreads();
@@ -843,13 +875,18 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
         // next grid barrier, which every CTA reaches after finishing this drain
     }
     __syncthreads();
-    // ---------------- flush my windows into the uint32 hot window
-    for (uint32_t i = tid; i < hist_words; i += WC_THREADS) {
-        const unsigned int cnt = s_hist[i];
-        if (!cnt) continue;
-        const uint32_t lid = i / pc.win, slot = i - lid * pc.win;
+    // ---------------- flush my windows straight into the uint64 bucket arrays (positive rows: slot == key) and raise the
+    // flags of the histograms that received counts; nothing of the common path goes through the uint32 hot window
+    for (uint32_t lid = 0; lid < prm.ids_per; lid++) {
         const uint32_t id = lid * P + p;
-        if (id < prm.o.H) atomicAdd(&prm.o.hot[(size_t)id * (2u * pc.win) + slot], cnt);
+        if (id >= prm.o.H) break;
+        int any = 0;
+        for (uint32_t slot = tid; slot < pc.win; slot += WC_THREADS) {
+            const unsigned int cnt = s_hist[lid * pc.win + slot];
+            if (cnt) { atomicAdd(&prm.o.buckets[(size_t)id * 65536u + slot], (unsigned long long)cnt); any = 1; }
+        }
+        any = __syncthreads_or(any);
+        if (any && tid == 0) mark(&prm.o.flags[id], 1u);
     }
 }
 
@@ -899,6 +936,46 @@ k_counter_add_smem(const IdT *__restrict__ ids, const unsigned long long *__rest
         unsigned int old = atomicAdd(&lo[id], a_lo);
         a_hi += (old + a_lo < old) ? 1u : 0u;        // carry out of the low half
         if (a_hi) atomicAdd(&hi[id], a_hi);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < C; i += THREADS) {
+        unsigned long long v = ((unsigned long long)hi[i] << 32) | lo[i];
+        if (v) atomicAdd(&counters[i], v);
+    }
+}
+
+// Vector body: 4 consecutive (id, amount) pairs per thread and iteration (one 256-bit amount load, one 64/128-bit id
+// load), the next group prefetched while the current one is added.  amounts 32-byte aligned, ids 4*sizeof(IdT)-aligned.
+template <typename IdT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_counter_add_smem_vec(const IdT *__restrict__ ids, const unsigned long long *__restrict__ amounts, size_t n4,
+                       unsigned long long *__restrict__ counters, uint32_t C, unsigned long long *__restrict__ dropped) {
+    extern __shared__ unsigned int s_cnt[];          // [C] low halves, [C] high halves
+    unsigned int *lo = s_cnt, *hi = s_cnt + C;
+    for (uint32_t i = threadIdx.x; i < 2 * C; i += THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * THREADS;
+    size_t g = (size_t)blockIdx.x * THREADS + threadIdx.x;
+    unsigned long long cur[4], nxt[4];
+    IdPack<IdT> cid, nid;
+    if (g < n4) { load_vals4(amounts, g, cur); cid.load(ids, g); }
+    for (; g < n4; g += stride) {
+        const size_t gn = g + stride;
+        if (gn < n4) { load_vals4(amounts, gn, nxt); nid.load(ids, gn); }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t id = cid.get(j);
+            const unsigned long long amt = cur[j];
+            if (id >= C) { atomicAdd(dropped, 1ull); continue; }
+            const unsigned int a_lo = (unsigned int)amt;
+            unsigned int a_hi = (unsigned int)(amt >> 32);
+            const unsigned int old = atomicAdd(&lo[id], a_lo);
+            a_hi += (old + a_lo < old) ? 1u : 0u;        // carry out of the low half
+            if (a_hi) atomicAdd(&hi[id], a_hi);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) cur[j] = nxt[j];
+        cid = nid;
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < C; i += THREADS) {

@@ -282,6 +282,12 @@ class Engine:
             n = h_values.size if n is None else n
         self._check(self.lib.lh_ingest_keyed_f64_u16_host(self.h, _ptr(h_ids), _ptr(h_values), n))
 
+    def ingest_keyed_i64ns_u16_host(self, h_ids, h_nanos, n: int | None = None):
+        if isinstance(h_nanos, np.ndarray):
+            assert h_nanos.dtype == np.int64 and h_ids.dtype == np.uint16
+            n = h_nanos.size if n is None else n
+        self._check(self.lib.lh_ingest_keyed_i64ns_u16_host(self.h, _ptr(h_ids), _ptr(h_nanos), n))
+
     def counter_add_u16_host(self, h_ids, h_amounts, n: int | None = None):
         if isinstance(h_amounts, np.ndarray):
             assert h_amounts.dtype == np.uint64 and h_ids.dtype == np.uint16

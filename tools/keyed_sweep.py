@@ -16,8 +16,8 @@ eng = lh.Engine(device=0, max_histograms=H, max_counters=1)
 d = eng.alloc(n, "float64")
 ids = eng.alloc(n, "uint16")
 configs = [("vec", 1, 16, 8 << 20)]
-for spt in (16, 8):
-    for chunk in ((8 << 20,) if quick else (2 << 20, 4 << 20, 8 << 20, 16 << 20, 32 << 20)):
+for spt in ((4,) if quick else (16, 8, 4)):
+    for chunk in ((32 << 20,) if quick else (16 << 20, 32 << 20, 64 << 20)):
         configs.append(("wc", 2, spt, chunk))
 for sname, kind, idkind in (("U", 0, 0), ("L", 1, 0), ("C", 3, 0), ("U/zipf-ids", 0, 1)):
     eng.gen_stream(kind, n, lh.DEFAULT_SEED, out=d)
