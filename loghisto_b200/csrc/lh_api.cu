@@ -714,6 +714,7 @@ extern "C" lh_status lh_create(const lh_config *cfg, lh_ctx **out) {
         LH_CREATE_CUDA(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
     }
 
+    LH_CREATE_CUDA(cudaFuncSetAttribute((const void *)k_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     LH_CREATE_CUDA(cudaFuncSetAttribute((const void *)k_counter_add_smem<unsigned short, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_COUNTERS * 8));
     LH_CREATE_CUDA(cudaFuncSetAttribute((const void *)k_counter_add_smem<unsigned int, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_COUNTERS * 8));
     LH_CREATE_CUDA(cudaFuncSetAttribute((const void *)k_counter_add_smem_vec<unsigned short, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_COUNTERS * 8));
@@ -1095,9 +1096,12 @@ lh_status enqueue_reduce(lh_ctx *ctx, const double *ps, uint32_t np, int slot) {
         LH_CUDA(ctx, cudaMemcpyAsync(ctx->d_ps[slot], ps, np * sizeof(double), cudaMemcpyHostToDevice, s));
     }
     char *d = ctx->d_res[slot];
-    k_reduce<<<ctx->H, K3_THREADS, 0, s>>>(v.buckets, v.flags, ctx->pc.win, ctx->d_decomp, ctx->d_ps[slot], (int)np,
+    // shared-memory window path when the 2*win-1 cells fit comfortably (two CTAs per SM); the dense path otherwise
+    const size_t cells = (size_t)2 * ctx->pc.win - 1;
+    const uint32_t smem_cells = cells * 8 <= (size_t)100 * 1024 ? (uint32_t)cells : 0u;
+    k_reduce<<<ctx->H, K3_THREADS, (size_t)smem_cells * 8, s>>>(v.buckets, v.flags, ctx->pc.win, ctx->d_decomp, ctx->d_ps[slot], (int)np,
                                            (unsigned long long *)(d + l.count), (double *)(d + l.sum), (double *)(d + l.avg),
-                                           (int *)(d + l.pkeys), (double *)(d + l.pvals), ctx->d_nnz);
+                                           (int *)(d + l.pkeys), (double *)(d + l.pvals), ctx->d_nnz, smem_cells);
     LH_CUDA(ctx, cudaGetLastError());
     LH_CUDA(ctx, cudaMemcpyAsync(ctx->h_res[slot], d, l.total, cudaMemcpyDeviceToHost, s));
     LH_CUDA(ctx, cudaEventRecord(ctx->res_done[slot], s));

@@ -681,6 +681,7 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
     unsigned int *s_rare = s_fill + (WC_MAX_PARTS - 1);                                     // samples set aside this chunk (slot P..158 of s_fill are free)
     uint4 *rareq = prm.rare + (size_t)p * WC_RARE_CAP;
     const uint32_t trash_slot = P * (uint32_t)S::STRIDE + (uint32_t)S::CAP;                 // never read
+    const uint32_t negP = 0u - P;
 
     for (uint32_t i = tid; i < hist_words; i += WC_THREADS) s_hist[i] = 0;
     if (tid < WC_MAX_PARTS) { s_fill[tid] = 0; s_off[tid] = 0; }
@@ -698,12 +699,15 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
     unsigned long long cur[GROUPS][4], nxt[GROUPS][4];
     IdPack<IdT> cur_id[GROUPS], nxt_id[GROUPS];
     uint32_t since_flush = 0;
-    auto load_tile = [&](size_t tile, unsigned long long (&raw)[GROUPS][4], IdPack<IdT> (&idp)[GROUPS]) {
+    // tile `tile` = TILE consecutive samples; thread tid takes the 4-sample groups tid, tid + THREADS, ... of it.  The
+    // pointers below walk the CTA's slice one tile at a time (no 64-bit multiplies inside the loop).
+    const char *vptr = nullptr;                  // this thread's first 32-byte value group of the current tile
+    const IdT *iptr = nullptr;                   // ... and its 4 ids
+    auto load_tile = [&](const char *vp, const IdT *ip, unsigned long long (&raw)[GROUPS][4], IdPack<IdT> (&idp)[GROUPS]) {
 #pragma unroll
         for (int g = 0; g < GROUPS; g++) {
-            const size_t g4 = tile * (S::TILE / 4) + (size_t)g * WC_THREADS + tid;          // group of 4 consecutive samples
-            load_vals4(prm.vals, g4, raw[g]);
-            idp[g].load(ids, g4);
+            load_vals4(vp, (size_t)g * WC_THREADS, raw[g]);
+            idp[g].load(ip, (size_t)g * WC_THREADS);
         }
     };
 
@@ -714,11 +718,16 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
         const bool last_chunk = c + 1 == nchunks;
         // ---------------- phase A: bin my slice of chunk c (I am writer p)
         const size_t tile0 = c * chunk_tiles + (size_t)p * prm.slice_tiles;
-        if (tile0 < tiles_total) load_tile(tile0, cur, cur_id);
-        for (uint32_t t = 0; t < prm.slice_tiles; t++) {
-            const size_t tile = tile0 + t;
-            if (tile >= tiles_total) break;                       // uniform per CTA
-            if (t + 1 < prm.slice_tiles && tile + 1 < tiles_total) load_tile(tile + 1, nxt, nxt_id);
+        const uint32_t ntile = tile0 >= tiles_total ? 0u : (uint32_t)min((size_t)prm.slice_tiles, tiles_total - tile0);   // uniform per CTA
+        if (ntile) {
+            vptr = reinterpret_cast<const char *>(prm.vals) + (tile0 * S::TILE + (size_t)tid * 4) * 8;
+            iptr = ids + tile0 * S::TILE + (size_t)tid * 4;
+            load_tile(vptr, iptr, cur, cur_id);
+        }
+        for (uint32_t t = 0; t < ntile; t++) {
+            vptr += (size_t)S::TILE * 8;
+            iptr += S::TILE;
+            if (t + 1 < ntile) load_tile(vptr, iptr, nxt, nxt_id);
 #pragma unroll
             for (int g = 0; g < GROUPS; g++) {
                 double v[4];
@@ -731,17 +740,16 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const uint32_t id = cur_id[g].get(j);
-                    const uint32_t lid = __umulhi(id, prm.inv_p), owner = id - lid * P;   // id / P, id % P
+                    const uint32_t lid = __umulhi(id, prm.inv_p), owner = lid * negP + id;   // id / P, id % P
                     const uint32_t rec = lid * pc.win + idx[j];
                     const bool rare = flag[j] | (id >= prm.o.H);
                     // branch-free append: rare samples draw from a trash counter / trash row
                     const uint32_t oe = rare ? P : owner;
                     uint32_t pos;
                     asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(fill_addr + oe * 4u) : "memory");
-                    const bool ok = pos < (uint32_t)S::CAP;
-                    const uint32_t slot = ok ? oe * (uint32_t)S::STRIDE + pos : trash_slot;
+                    flag[j] = rare | (pos >= (uint32_t)S::CAP);                            // buffer full (skewed ids): exact route as well
+                    const uint32_t slot = flag[j] ? trash_slot : oe * (uint32_t)S::STRIDE + pos;
                     asm volatile("st.shared.u16 [%0], %1;" ::"r"(buf_addr + slot * 2u), "h"((unsigned short)rec) : "memory");
-                    flag[j] = rare | !ok;                                                  // !ok: buffer full (skewed ids), exact L2 route
                     any |= flag[j];
                 }
                 if (__any_sync(0xFFFFFFFFu, any)) {
@@ -1031,8 +1039,7 @@ __device__ __forceinline__ bool warp_scans(int key0, uint32_t level, uint32_t wi
     return key0 <= (int)win - 1 && key0 + K3_WARP_KEYS - 1 >= -((int)win - 1);
 }
 
-__global__ void __launch_bounds__(K3_THREADS)
-k_reduce(const unsigned long long *__restrict__ buckets, const uint32_t *__restrict__ flags, uint32_t win,
+__device__ __forceinline__ void reduce_dense(uint32_t level, const unsigned long long *__restrict__ buckets, const uint32_t *__restrict__ flags, uint32_t win,
          const double *__restrict__ decomp,
          const double *__restrict__ ps, int np, unsigned long long *__restrict__ out_count,
          double *__restrict__ out_sum, double *__restrict__ out_avg, int *__restrict__ out_pkeys,
@@ -1044,17 +1051,6 @@ k_reduce(const unsigned long long *__restrict__ buckets, const uint32_t *__restr
     __shared__ int s_owner[LH_MAX_PCT];
     __shared__ unsigned long long s_total;
     const int h = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const uint32_t level = flags[h];
-    if (level == 0) {   // untouched this interval: the caller reports the histogram as absent
-        if (t == 0) {
-            out_count[h] = 0; out_sum[h] = 0.0; out_avg[h] = __longlong_as_double(0x7FF8000000000000ll); out_nnz[h] = 0;
-            for (int j = 0; j < np; j++) {
-                out_pkeys[(size_t)h * np + j] = (int)0x80000000;
-                out_pvals[(size_t)h * np + j] = __longlong_as_double(0x7FF8000000000000ll);
-            }
-        }
-        return;
-    }
     const unsigned long long *hb = buckets + (size_t)h * 65536u;
     const int key0 = -32768 + warp * K3_WARP_KEYS;
     const bool scans = warp_scans(key0, level, win);
@@ -1145,6 +1141,149 @@ k_reduce(const unsigned long long *__restrict__ buckets, const uint32_t *__restr
         out_sum[h] = s_sum[0];
         out_avg[h] = __ddiv_rn(s_sum[0], ftotal);    // metrics.go:356 (NaN when empty)
         out_nnz[h] = s_nnz[0];
+    }
+}
+
+// Smallest s in [0, total] with float64(s)/float64(total) >= p -- the reference's rule (metrics.go:413) turned into an
+// integer threshold on the running count: the quotient is monotone in s, so "first non-empty bucket whose running count
+// satisfies the rule" == "first non-empty bucket whose running count reaches T".  Returns false when no s satisfies
+// the rule (p > 1 or NaN: percentile() returns its error).
+__device__ __forceinline__ bool percentile_threshold(double p, unsigned long long total, unsigned long long *T) {
+    const double ft = (double)total;
+    if (!(__ddiv_rn(ft, ft) >= p)) return false;                 // even s = total fails (p > 1, NaN)
+    auto ok = [&](unsigned long long s) { return __ddiv_rn((double)s, ft) >= p; };
+    unsigned long long s = 0;
+    if (p > 0.0) {
+        const double est = ceil(p * ft);
+        s = est >= ft ? total : (unsigned long long)est;
+    }
+    int steps = 0;
+    while (s > 0 && ok(s - 1) && steps < 8) { s--; steps++; }
+    while (!ok(s) && steps < 16) { s++; steps++; }
+    if (steps >= 8 && (!ok(s) || (s > 0 && ok(s - 1)))) {        // long plateaus of float64(s) (totals beyond 2^53): bisection
+        unsigned long long lo = 0, hi = total;                  // ok(hi) holds
+        while (lo < hi) { const unsigned long long mid = lo + (hi - lo) / 2; if (ok(mid)) hi = mid; else lo = mid + 1; }
+        s = lo;
+    }
+    *T = s;
+    return true;
+}
+
+// One CTA per histogram.  Untouched histograms are answered without reading a bucket.  A histogram whose counts all
+// lie in the fast window (flag 1; the normal case) is reduced from shared memory: its 2*win-1 cells are loaded once
+// (ascending key order == ascending value order, metrics.go:409), count / sum / non-empty totals come from a block
+// reduction, an in-place block scan turns the cells into running counts, and every percentile is one binary search
+// for its integer threshold -- no per-bucket FP64 division, no serial walk.  Histograms with out-of-window keys
+// (wrapped int16 keys, NaN / Inf -> 0 ...) take the dense path over all 65 536 keys.
+__global__ void __launch_bounds__(K3_THREADS)
+k_reduce(const unsigned long long *__restrict__ buckets, const uint32_t *__restrict__ flags, uint32_t win,
+         const double *__restrict__ decomp,
+         const double *__restrict__ ps, int np, unsigned long long *__restrict__ out_count,
+         double *__restrict__ out_sum, double *__restrict__ out_avg, int *__restrict__ out_pkeys,
+         double *__restrict__ out_pvals, uint32_t *__restrict__ out_nnz, uint32_t smem_cells) {
+    extern __shared__ __align__(16) unsigned long long k3_cells[];      // [2*win-1] when the window path is enabled
+    const int h = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t level = flags[h];
+    if (level == 0) {   // untouched this interval: the caller reports the histogram as absent
+        if (t == 0) {
+            out_count[h] = 0; out_sum[h] = 0.0; out_avg[h] = __longlong_as_double(0x7FF8000000000000ll); out_nnz[h] = 0;
+            for (int j = 0; j < np; j++) {
+                out_pkeys[(size_t)h * np + j] = (int)0x80000000;
+                out_pvals[(size_t)h * np + j] = __longlong_as_double(0x7FF8000000000000ll);
+            }
+        }
+        return;
+    }
+    const uint32_t n = 2u * win - 1u;
+    if ((level & 2u) || smem_cells < n) {
+        reduce_dense(level, buckets, flags, win, decomp, ps, np, out_count, out_sum, out_avg, out_pkeys, out_pvals, out_nnz);
+        return;
+    }
+    __shared__ unsigned long long s_c[32];
+    __shared__ double s_s[32];
+    __shared__ unsigned int s_n[32];
+    __shared__ unsigned long long s_total;
+    const unsigned long long *hb = buckets + (size_t)h * 65536u;
+    // cell i of the window holds key i - (win-1)
+    constexpr int PER = 32;                                       // contiguous cells per thread in the scan (PER * 1024 >= n up to win = 16384)
+    unsigned long long mine = 0;
+    double msum = 0.0;
+    unsigned int nnz = 0;
+    for (uint32_t i = t; i < n; i += K3_THREADS) {
+        const unsigned int slot = (unsigned int)((int)i - (int)(win - 1u)) & 0xFFFFu;
+        const unsigned long long c = hb[slot];
+        k3_cells[i] = c;
+        if (c) { mine += c; msum += decomp[slot] * (double)c; nnz++; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
+        msum += __shfl_xor_sync(0xFFFFFFFFu, msum, o);
+        nnz += __shfl_xor_sync(0xFFFFFFFFu, nnz, o);
+    }
+    if (lane == 0) { s_c[warp] = mine; s_s[warp] = msum; s_n[warp] = nnz; }
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long c = s_c[lane];
+        double sm = s_s[lane];
+        unsigned int nz = s_n[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+            sm += __shfl_xor_sync(0xFFFFFFFFu, sm, o);
+            nz += __shfl_xor_sync(0xFFFFFFFFu, nz, o);
+        }
+        if (lane == 0) {
+            s_total = c;
+            out_count[h] = c;
+            out_sum[h] = sm;
+            out_avg[h] = __ddiv_rn(sm, (double)c);                // metrics.go:356
+            out_nnz[h] = nz;
+        }
+    }
+    // in-place inclusive scan of the cells: thread t owns cells [t*per, (t+1)*per)
+    const uint32_t per = (n + K3_THREADS - 1) / K3_THREADS;
+    const uint32_t first = t * per, last = min(first + per, n);
+    unsigned long long local = 0;
+    for (uint32_t i = first; i < last; i++) local += k3_cells[i];
+    unsigned long long incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    __syncthreads();                                              // s_c was read by warp 0 above
+    if (lane == 31) s_c[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = s_c[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+            if (lane >= o) wi += y;
+        }
+        s_c[lane] = wi - w;                                       // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    unsigned long long run = s_c[warp] + incl - local;
+    for (uint32_t i = first; i < last; i++) { run += k3_cells[i]; k3_cells[i] = run; }
+    __syncthreads();
+    (void)PER;
+    // one thread per percentile: integer threshold, then the first cell whose running count reaches it
+    if (t < np) {
+        const unsigned long long total = s_total;
+        unsigned long long T;
+        int key = (int)0x80000000;
+        double val = __longlong_as_double(0x7FF8000000000000ll);
+        if (total && percentile_threshold(ps[t], total, &T)) {
+            if (T == 0) T = 1;                                    // p <= 0: the smallest non-empty bucket
+            uint32_t lo = 0, hi = n - 1;                          // k3_cells[n-1] == total >= T
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (k3_cells[mid] >= T) hi = mid; else lo = mid + 1; }
+            key = (int)lo - (int)(win - 1u);
+            val = decomp[(unsigned int)key & 0xFFFFu];
+        }
+        out_pkeys[(size_t)h * np + t] = key;
+        out_pvals[(size_t)h * np + t] = val;
     }
 }
 

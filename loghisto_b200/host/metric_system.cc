@@ -72,23 +72,38 @@ inline uint64_t hash_bytes(const char *p, size_t n) {
 }
 
 struct NameCache {
-    static constexpr size_t kEntries = 2048;     // direct-mapped; >= the default max_histograms
+    // open addressing, linear probing, load factor <= 1/2: a name that was interned once is found without ever going
+    // back to the shared table (a direct-mapped cache thrashes as soon as two hot names collide)
     struct Entry { uint64_t hash = 0; uint32_t id = 0; bool used = false; std::string name; };
     uint64_t system_id = 0;                      // which MetricSystem the entries belong to
     std::vector<Entry> e;
+    size_t count = 0;
     bool find(uint64_t h, const char *p, size_t n, uint32_t *id) const {
         if (e.empty()) return false;
-        const Entry &x = e[h & (kEntries - 1)];
-        if (!x.used || x.hash != h || x.name.size() != n || memcmp(x.name.data(), p, n) != 0) return false;
-        *id = x.id;
-        return true;
+        const size_t mask = e.size() - 1;
+        for (size_t i = h & mask;; i = (i + 1) & mask) {
+            const Entry &x = e[i];
+            if (!x.used) return false;
+            if (x.hash == h && x.name.size() == n && memcmp(x.name.data(), p, n) == 0) { *id = x.id; return true; }
+        }
+    }
+    void insert_raw(uint64_t h, std::string &&name, uint32_t id) {
+        const size_t mask = e.size() - 1;
+        size_t i = h & mask;
+        while (e[i].used) i = (i + 1) & mask;
+        e[i].hash = h; e[i].id = id; e[i].used = true; e[i].name = std::move(name);
     }
     void put(uint64_t h, const char *p, size_t n, uint32_t id) {
-        if (e.empty()) e.resize(kEntries);
-        Entry &x = e[h & (kEntries - 1)];
-        x.hash = h; x.id = id; x.used = true; x.name.assign(p, n);
+        if (e.empty()) e.resize(256);
+        if ((count + 1) * 2 > e.size()) {        // grow and rehash
+            std::vector<Entry> old(e.size() * 2);
+            old.swap(e);
+            for (Entry &x : old) if (x.used) insert_raw(x.hash, std::move(x.name), x.id);
+        }
+        insert_raw(h, std::string(p, n), id);
+        count++;
     }
-    void reset(uint64_t sys) { system_id = sys; e.clear(); }
+    void reset(uint64_t sys) { system_id = sys; e.clear(); count = 0; }
 };
 thread_local NameCache tl_hcache, tl_ccache;
 

@@ -259,6 +259,29 @@ def test_timer_samples_i64(lh, oracle):
             assert (dense_from_sparse(sp, h) == want[h]).all(), h
 
 
+def test_timer_samples_host_fed_and_misaligned_counters(lh, oracle):
+    """Host-fed timer samples (lh_ingest_keyed_i64ns_u16_host) and the vectorised counter kernel at every
+    alignment / ragged size (vector body + scalar head and tail)."""
+    H, C, n = 7, 200, 300_003
+    ns = oracle.gen_stream(oracle.STREAM_TIMER_NS, n, SEED ^ 3).view(np.int64).copy()
+    ns[::97] *= -1                                    # negative durations happen (readme.md:43)
+    ids = oracle.gen_ids(0, n, H, SEED ^ 3)
+    want = oracle.ingest_keyed_i64(ids, ns, H)
+    with lh.Engine(device=0, max_histograms=H, max_counters=C) as e:
+        e.ingest_keyed_i64ns_u16_host(ids.astype(np.uint16), ns)
+        _, sp = e.snapshot(PS)
+        for h in range(H):
+            assert (dense_from_sparse(sp, h) == want[h]).all(), h
+        rng = np.random.default_rng(5)
+        cids = rng.integers(0, C, n + 8).astype(np.uint32)
+        amts = rng.integers(0, 2 ** 63, n + 8).astype(np.uint64) * np.uint64(2) + np.uint64(1)
+        d_i, d_a = e.upload(cids.astype(np.uint16)), e.upload(amts)
+        for off, m in ((0, n), (1, n - 1), (3, 65_537), (4, 16_384), (5, 5)):
+            e.counter_add_u16(d_i.offset(off), d_a.offset(off), m)
+            _, sp = e.snapshot(PS)
+            assert (sp.counter_deltas == oracle.counter_add(cids[off:off + m], amts[off:off + m], C)).all(), (off, m)
+
+
 def test_counters(eng, oracle):
     n = 500_000
     rng = np.random.default_rng(11)
