@@ -680,7 +680,6 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
     const uint32_t fill_addr = smem_u32(s_fill), buf_addr = smem_u32(s_buf), hist_addr = smem_u32(s_hist);
     unsigned int *s_rare = s_fill + (WC_MAX_PARTS - 1);                                     // samples set aside this chunk (slot P..158 of s_fill are free)
     uint4 *rareq = prm.rare + (size_t)p * WC_RARE_CAP;
-    const uint32_t trash_slot = P * (uint32_t)S::STRIDE + (uint32_t)S::CAP;                 // never read
     const uint32_t negP = 0u - P;
 
     for (uint32_t i = tid; i < hist_words; i += WC_THREADS) s_hist[i] = 0;
@@ -694,7 +693,7 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
     const size_t nchunks = (tiles_total + chunk_tiles - 1) / chunk_tiles;
     const IdT *ids = reinterpret_cast<const IdT *>(prm.ids);
     const unsigned int cap = prm.cap;
-    const uint32_t vq = cap / 8;                                  // 16-byte vectors per sub-queue
+
 
     unsigned long long cur[GROUPS][4], nxt[GROUPS][4];
     IdPack<IdT> cur_id[GROUPS], nxt_id[GROUPS];
@@ -724,22 +723,21 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
             iptr = ids + tile0 * S::TILE + (size_t)tid * 4;
             load_tile(vptr, iptr, cur, cur_id);
         }
-        for (uint32_t t = 0; t < ntile; t++) {
-            vptr += (size_t)S::TILE * 8;
-            iptr += S::TILE;
-            if (t + 1 < ntile) load_tile(vptr, iptr, nxt, nxt_id);
+        // one tile: bin the 4-sample groups held in (raw, idp), then flush when due.  Two register sets alternate (A is
+        // being binned while B's loads are in flight and vice versa), so no register copies between tiles.
+        auto bin_tile = [&](unsigned long long (&raw)[GROUPS][4], IdPack<IdT> (&idp)[GROUPS]) {
 #pragma unroll
             for (int g = 0; g < GROUPS; g++) {
                 double v[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) { ValT r; memcpy(&r, &cur[g][j], 8); v[j] = sample_to_f64<ValT>(r); }
+                for (int j = 0; j < 4; j++) { ValT r; memcpy(&r, &raw[g][j], 8); v[j] = sample_to_f64<ValT>(r); }
                 uint32_t idx[4];
                 bool flag[4];
                 bucket_offsets_v2<4, false, 0>(v, pc, one_bits, idx, flag);      // slot indices (positive-only rows)
                 bool any = false;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const uint32_t id = cur_id[g].get(j);
+                    const uint32_t id = idp[g].get(j);
                     const uint32_t lid = __umulhi(id, prm.inv_p), owner = lid * negP + id;   // id / P, id % P
                     const uint32_t rec = lid * pc.win + idx[j];
                     const bool rare = flag[j] | (id >= prm.o.H);
@@ -748,8 +746,8 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
                     uint32_t pos;
                     asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(fill_addr + oe * 4u) : "memory");
                     flag[j] = rare | (pos >= (uint32_t)S::CAP);                            // buffer full (skewed ids): exact route as well
-                    const uint32_t slot = flag[j] ? trash_slot : oe * (uint32_t)S::STRIDE + pos;
-                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(buf_addr + slot * 2u), "h"((unsigned short)rec) : "memory");
+                    if (!flag[j])                                                          // one predicated store, no branch
+                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(buf_addr + (oe * (uint32_t)S::STRIDE + pos) * 2u), "h"((unsigned short)rec) : "memory");
                     any |= flag[j];
                 }
                 if (__any_sync(0xFFFFFFFFu, any)) {
@@ -759,8 +757,8 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
                     for (int j = 0; j < 4; j++)
                         if (flag[j]) {
                             const unsigned int at = atomicAdd(s_rare, 1u);
-                            if (at < WC_RARE_CAP) rareq[at] = make_uint4((unsigned int)cur[g][j], (unsigned int)(cur[g][j] >> 32), cur_id[g].get(j), 0u);
-                            else keyed_one_slow<ValT>(cur_id[g].get(j), cur[g][j], pc, prm.o);
+                            if (at < WC_RARE_CAP) rareq[at] = make_uint4((unsigned int)raw[g][j], (unsigned int)(raw[g][j] >> 32), idp[g].get(j), 0u);
+                            else keyed_one_slow<ValT>(idp[g].get(j), raw[g][j], pc, prm.o);
                         }
                 }
             }
@@ -801,12 +799,17 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
                 }
                 __syncthreads();
             }
-#pragma unroll
-            for (int g = 0; g < GROUPS; g++) {
-                cur_id[g] = nxt_id[g];
-#pragma unroll
-                for (int j = 0; j < 4; j++) cur[g][j] = nxt[g][j];
-            }
+        };
+        for (uint32_t t = 0; t < ntile; t += 2) {
+            vptr += (size_t)S::TILE * 8;
+            iptr += S::TILE;
+            if (t + 1 < ntile) load_tile(vptr, iptr, nxt, nxt_id);
+            bin_tile(cur, cur_id);
+            if (t + 1 >= ntile) break;
+            vptr += (size_t)S::TILE * 8;
+            iptr += S::TILE;
+            if (t + 2 < ntile) load_tile(vptr, iptr, cur, cur_id);
+            bin_tile(nxt, nxt_id);
         }
         __syncthreads();    // every append of this chunk's tiles is in the buffers
         {   // the samples set aside: exact path, all threads at once
@@ -853,29 +856,27 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
         if (tid < P) s_off[tid] = __ldcg(&cset[(size_t)p * P + tid]);
         __syncthreads();
         {
-            const uint4 *qv = reinterpret_cast<const uint4 *>(qset + (size_t)p * P * cap);
-            const uint32_t total = P * vq;
-#pragma unroll 2
-            for (uint32_t v = tid; v < total; v += WC_THREADS) {
-                const uint32_t w = __umulhi(v, prm.inv_vq), i = v - w * vq;               // writer, vector inside its sub-queue
-                const unsigned int cnt = s_off[w];
-                if (i * 8u >= cnt) continue;
-                const uint4 v4 = __ldcg(qv + v);
+            // warp w drains the sub-queues of writers w, w + NW, ...: the record counts are already in shared memory, so the
+            // 16-byte vector loads of a sub-queue are independent (a lane has several in flight) and no index is wasted
+            const unsigned short *qmine = qset + (size_t)p * P * cap;
+            const uint32_t lane = tid & 31;
 #define LH_WC_INC2(word)                                                                                              \
-                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + (((word) << 2) & 0x3FFFCu)) : "memory"); \
-                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + (((word) >> 14) & 0x3FFFCu)) : "memory");
-                if (i * 8u + 8u <= cnt) {                                                  // full vector: 8 unconditional increments
+            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + (((word) << 2) & 0x3FFFCu)) : "memory");     \
+            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + (((word) >> 14) & 0x3FFFCu)) : "memory");
+            for (uint32_t w = tid >> 5; w < P; w += WC_THREADS / 32) {
+                const unsigned int cnt = s_off[w];
+                const unsigned short *q = qmine + (size_t)w * cap;
+                const uint4 *qv = reinterpret_cast<const uint4 *>(q);
+                const unsigned int nv = cnt >> 3;
+#pragma unroll 2
+                for (unsigned int i = lane; i < nv; i += 32) {
+                    const uint4 v4 = __ldcg(qv + i);
                     LH_WC_INC2(v4.x) LH_WC_INC2(v4.y) LH_WC_INC2(v4.z) LH_WC_INC2(v4.w)
-                } else {                                                                   // the last, partial vector of a sub-queue
-                    const unsigned int nrec = cnt - i * 8u;
-                    unsigned long long lo64 = ((unsigned long long)v4.y << 32) | v4.x, hi64 = ((unsigned long long)v4.w << 32) | v4.z;
-                    for (unsigned int k = 0; k < nrec; k++) {
-                        const unsigned int r = (unsigned int)((k < 4 ? lo64 >> (16u * k) : hi64 >> (16u * (k - 4u))) & 0xFFFFull);
-                        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + r * 4u) : "memory");
-                    }
                 }
-#undef LH_WC_INC2
+                const unsigned int r0 = nv * 8u + lane;                                    // the < 8 records after the last full vector
+                if (r0 < cnt) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + (unsigned int)__ldcg(q + r0) * 4u) : "memory");
             }
+#undef LH_WC_INC2
         }
         __syncthreads();
         if (tid < P) s_off[tid] = 0;
