@@ -121,8 +121,8 @@ struct PeerWire {
     uint32_t precision, device;
     int64_t pid;
     uint64_t ctx_id;                               // distinguishes contexts of one process
-    uint64_t ptr_buckets[2], ptr_flags[2], ptr_counters[2], ptr_comm;
-    cudaIpcMemHandle_t ipc_buckets[2], ipc_flags[2], ipc_counters[2], ipc_comm;
+    uint64_t ptr_buckets[2], ptr_flags[2], ptr_counters[2], ptr_comm, ptr_red;
+    cudaIpcMemHandle_t ipc_buckets[2], ipc_flags[2], ipc_counters[2], ipc_comm, ipc_red;
 };
 static_assert(sizeof(PeerWire) <= LH_PEER_HANDLE_BYTES, "lh_peer_handle too small");
 
@@ -131,6 +131,7 @@ struct PeerMap {                                   // one remote rank as mapped 
     uint32_t *flags[2] = {nullptr, nullptr};
     unsigned long long *counters[2] = {nullptr, nullptr};
     unsigned long long *comm = nullptr;
+    unsigned long long *red = nullptr;             // the rank's REDUCED bucket array: owners of a slice push their sums into it
     bool ipc = false;                              // pointers came from cudaIpcOpenMemHandle (must be closed)
 };
 
@@ -197,6 +198,7 @@ struct lh_ctx {
     bool view_reduced = false;                    // the open snapshot's reduce/export read the reduced arrays
     bool view_counters_reduced = false;
     uint64_t comm_seq = 0;
+    bool comm_two_shot = false;                    // form of the last all-reduce (lh_comm_info's byte count)
     static constexpr int kCommRing = 8;
     cudaEvent_t comm_t0[kCommRing] = {}, comm_t1[kCommRing] = {};
     uint64_t ctx_id = 0;
@@ -577,10 +579,25 @@ void comm_unmap(lh_ctx *ctx) {
                 if (pm.counters[b]) cudaIpcCloseMemHandle(pm.counters[b]);
             }
             if (pm.comm) cudaIpcCloseMemHandle(pm.comm);
+            if (pm.red) cudaIpcCloseMemHandle(pm.red);
         }
         pm = PeerMap{};
     }
     ctx->comm_world = 0;
+}
+
+// the arrays the all-reduce writes (this rank's own kernel and, for its slices, every peer's)
+lh_status comm_alloc_reduced(lh_ctx *ctx) {
+    if (ctx->d_red_buckets) return LH_OK;
+    const size_t bucket_bytes = (size_t)ctx->H * 65536u * 8u;
+    LH_CUDA(ctx, cudaMalloc(&ctx->d_red_buckets, bucket_bytes));
+    LH_CUDA(ctx, cudaMalloc(&ctx->d_red_flags, (size_t)ctx->H * 4));
+    LH_CUDA(ctx, cudaMalloc(&ctx->d_red_counters, (size_t)ctx->C * 8));
+    LH_CUDA(ctx, cudaMemsetAsync(ctx->d_red_buckets, 0, bucket_bytes, ctx->snap_stream));
+    LH_CUDA(ctx, cudaMemsetAsync(ctx->d_red_flags, 0, (size_t)ctx->H * 4, ctx->snap_stream));
+    LH_CUDA(ctx, cudaMemsetAsync(ctx->d_red_counters, 0, (size_t)ctx->C * 8, ctx->snap_stream));
+    LH_CUDA(ctx, cudaStreamSynchronize(ctx->snap_stream));
+    return LH_OK;
 }
 
 bool is_pinned_or_managed(const void *p) {
@@ -715,6 +732,7 @@ extern "C" lh_status lh_create(const lh_config *cfg, lh_ctx **out) {
     }
 
     LH_CREATE_CUDA(cudaFuncSetAttribute((const void *)k_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    LH_CREATE_CUDA(cudaFuncSetAttribute((const void *)k_peer_allreduce, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     LH_CREATE_CUDA(cudaFuncSetAttribute((const void *)k_counter_add_smem<unsigned short, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_COUNTERS * 8));
     LH_CREATE_CUDA(cudaFuncSetAttribute((const void *)k_counter_add_smem<unsigned int, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_COUNTERS * 8));
     LH_CREATE_CUDA(cudaFuncSetAttribute((const void *)k_counter_add_smem_vec<unsigned short, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_COUNTERS * 8));
@@ -1271,6 +1289,9 @@ extern "C" lh_status lh_comm_export(lh_ctx *ctx, lh_peer_handle *out) {
     }
     w.ptr_comm = (uint64_t)(uintptr_t)ctx->d_comm;
     LH_CUDA(ctx, cudaIpcGetMemHandle(&w.ipc_comm, ctx->d_comm));
+    if (lh_status st = comm_alloc_reduced(ctx)) return st;
+    w.ptr_red = (uint64_t)(uintptr_t)ctx->d_red_buckets;
+    LH_CUDA(ctx, cudaIpcGetMemHandle(&w.ipc_red, ctx->d_red_buckets));
     memset(out, 0, sizeof *out);
     memcpy(out->bytes, &w, sizeof w);
     return LH_OK;
@@ -1293,6 +1314,8 @@ extern "C" lh_status lh_comm_import(lh_ctx *ctx, uint32_t rank, uint32_t world, 
             if (w.ctx_id != ctx->ctx_id || w.pid != my_pid) return fail(ctx, LH_ERR_INVALID, "handles[rank] is not this context's own handle");
             for (int b = 0; b < 2; b++) { pm.buckets[b] = ctx->buf[b].d_buckets; pm.flags[b] = ctx->buf[b].d_flags; pm.counters[b] = ctx->buf[b].d_counters; }
             pm.comm = ctx->d_comm;
+            if (lh_status st = comm_alloc_reduced(ctx)) return st;
+            pm.red = ctx->d_red_buckets;
             continue;
         }
         if (w.pid == my_pid) {
@@ -1311,6 +1334,7 @@ extern "C" lh_status lh_comm_import(lh_ctx *ctx, uint32_t rank, uint32_t world, 
                 pm.counters[b] = (unsigned long long *)(uintptr_t)w.ptr_counters[b];
             }
             pm.comm = (unsigned long long *)(uintptr_t)w.ptr_comm;
+            pm.red = (unsigned long long *)(uintptr_t)w.ptr_red;
         } else {
             // another process on this node: CUDA IPC mappings (NVLink peer-to-peer underneath)
             pm.ipc = true;
@@ -1320,17 +1344,8 @@ extern "C" lh_status lh_comm_import(lh_ctx *ctx, uint32_t rank, uint32_t world, 
                 LH_CUDA(ctx, cudaIpcOpenMemHandle((void **)&pm.counters[b], w.ipc_counters[b], cudaIpcMemLazyEnablePeerAccess));
             }
             LH_CUDA(ctx, cudaIpcOpenMemHandle((void **)&pm.comm, w.ipc_comm, cudaIpcMemLazyEnablePeerAccess));
+            LH_CUDA(ctx, cudaIpcOpenMemHandle((void **)&pm.red, w.ipc_red, cudaIpcMemLazyEnablePeerAccess));
         }
-    }
-    if (!ctx->d_red_buckets) {
-        const size_t bucket_bytes = (size_t)ctx->H * 65536u * 8u;
-        LH_CUDA(ctx, cudaMalloc(&ctx->d_red_buckets, bucket_bytes));
-        LH_CUDA(ctx, cudaMalloc(&ctx->d_red_flags, (size_t)ctx->H * 4));
-        LH_CUDA(ctx, cudaMalloc(&ctx->d_red_counters, (size_t)ctx->C * 8));
-        LH_CUDA(ctx, cudaMemsetAsync(ctx->d_red_buckets, 0, bucket_bytes, ctx->snap_stream));
-        LH_CUDA(ctx, cudaMemsetAsync(ctx->d_red_flags, 0, (size_t)ctx->H * 4, ctx->snap_stream));
-        LH_CUDA(ctx, cudaMemsetAsync(ctx->d_red_counters, 0, (size_t)ctx->C * 8, ctx->snap_stream));
-        LH_CUDA(ctx, cudaStreamSynchronize(ctx->snap_stream));
     }
     ctx->comm_rank = rank;
     ctx->comm_world = world;
@@ -1358,13 +1373,18 @@ extern "C" lh_status lh_snapshot_allreduce(lh_ctx *ctx, uint32_t include_counter
     p.out_buckets = ctx->d_red_buckets; p.out_flags = ctx->d_red_flags; p.out_counters = ctx->d_red_counters;
     p.block_counter = ctx->d_comm_aux; p.status = ctx->d_comm_aux + 1;
     p.cells = reinterpret_cast<unsigned long long *>(ctx->d_comm_aux + 2);
-    LH_CUDA(ctx, cudaMemsetAsync(ctx->d_comm_aux + 2, 0, 8, s));
+    for (uint32_t r = 0; r < ctx->comm_world; r++) p.out_peer[r] = ctx->peers[r].red;
+    // payload = the window cells of every histogram that can be live; above 1 MiB the reduce-scatter + push form wins
+    const size_t payload = (size_t)ctx->H * (2u * ctx->pc.win - 1u) * 8u;
+    p.two_shot = payload >= (1u << 20) ? 1u : 0u;
+    ctx->comm_two_shot = p.two_shot != 0;
     const int ring = (int)(p.seq % lh_ctx::kCommRing);
-    // a few CTAs: the kernel shares the GPU with the next interval's ingest (which leaves k1_reserve_sms SMs free)
+    // a few CTAs: the kernel shares the GPU with the next interval's ingest (which leaves k1_reserve_sms SMs free);
+    // CTAs that are not resident yet simply start later (no CTA waits for another CTA of its own grid before the end)
     const size_t items = (size_t)ctx->H * (65536u / K5_CHUNK);
-    const int grid = (int)std::min<size_t>(items, ctx->H == 1 ? 5 : 32);
+    const int grid = (int)std::min<size_t>(items, ctx->H == 1 ? 5 : (p.two_shot ? 64 : 16));
     LH_CUDA(ctx, cudaEventRecord(ctx->comm_t0[ring], s));
-    k_peer_allreduce<<<grid, K5_THREADS, 0, s>>>(p);
+    k_peer_allreduce<<<grid, K5_THREADS, ctx->H, s>>>(p);
     LH_CUDA(ctx, cudaGetLastError());
     LH_CUDA(ctx, cudaEventRecord(ctx->comm_t1[ring], s));
     ctx->stats.kernel_launches++;
@@ -1404,7 +1424,8 @@ extern "C" lh_status lh_comm_info(lh_ctx *ctx, lh_comm_stats *out) {
         // bytes this rank read from its peers in the last all-reduce: window (or dense) cells of every touched histogram
         unsigned long long cells = 0;
         LH_CUDA(ctx, cudaMemcpy(&cells, ctx->d_comm_aux + 2, 8, cudaMemcpyDeviceToHost));
-        out->last_bytes_from_peers = cells * 8u * (ctx->comm_world - 1);
+        // one-shot: every cell from every peer; two-shot: this rank's 1/world of the cells from every peer (and as much pushed back)
+        out->last_bytes_from_peers = ctx->comm_two_shot ? cells * 8u * (ctx->comm_world - 1) / ctx->comm_world : cells * 8u * (ctx->comm_world - 1);
     }
     return LH_OK;
 }

@@ -677,10 +677,14 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
     unsigned int *s_fill = s_hist + ((hist_words + 3u) & ~3u);                              // records in each owner's buffer
     unsigned int *s_off = s_fill + WC_MAX_PARTS;                                            // records appended to my sub-queues this chunk; phase B: record counts
     unsigned short *s_buf = reinterpret_cast<unsigned short *>(s_off + WC_MAX_PARTS);       // [P + 1][STRIDE], row P = trash
-    const uint32_t fill_addr = smem_u32(s_fill), buf_addr = smem_u32(s_buf), hist_addr = smem_u32(s_hist);
+    uint32_t fill_addr = smem_u32(s_fill);
+    const uint32_t hist_addr = smem_u32(s_hist);
+    asm volatile("mov.b32 %0, %0;" : "+r"(fill_addr));          // keep it in a register: recomputing it costs 7 instructions per tile
+    const uint32_t buf_addr = fill_addr + 2u * WC_MAX_PARTS * 4u;
     unsigned int *s_rare = s_fill + (WC_MAX_PARTS - 1);                                     // samples set aside this chunk (slot P..158 of s_fill are free)
     uint4 *rareq = prm.rare + (size_t)p * WC_RARE_CAP;
-    const uint32_t negP = 0u - P;
+    uint32_t negP = 0u - P;
+    asm volatile("mov.b32 %0, %0;" : "+r"(negP));
 
     for (uint32_t i = tid; i < hist_words; i += WC_THREADS) s_hist[i] = 0;
     if (tid < WC_MAX_PARTS) { s_fill[tid] = 0; s_off[tid] = 0; }
@@ -741,7 +745,7 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
                     const uint32_t lid = __umulhi(id, prm.inv_p), owner = lid * negP + id;   // id / P, id % P
                     const uint32_t rec = lid * pc.win + idx[j];
                     const bool rare = flag[j] | (id >= prm.o.H);
-                    // branch-free append: rare samples draw from a trash counter / trash row
+                    // branch-free append: rare samples draw from a trash counter (a predicated atomic makes ptxas branch and spill)
                     const uint32_t oe = rare ? P : owner;
                     uint32_t pos;
                     asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(fill_addr + oe * 4u) : "memory");
@@ -1389,6 +1393,8 @@ struct PeerParams {
     const unsigned long long *counters[LH_MAX_RANKS];
     unsigned long long *comm[LH_MAX_RANKS];               // every rank's comm block
     unsigned long long *out_buckets;                      // this rank's reduced arrays (zero outside what is written)
+    unsigned long long *out_peer[LH_MAX_RANKS];           // every rank's reduced bucket array (own rank: out_buckets)
+    uint32_t two_shot;                                    // 1: each rank sums 1/world of the cells and pushes the sums to every rank
     uint32_t *out_flags;
     unsigned long long *out_counters;
     unsigned int *block_counter;                          // local, zero between launches
@@ -1433,8 +1439,8 @@ __device__ __forceinline__ bool wait_token(const unsigned long long *slot, unsig
 
 __global__ void __launch_bounds__(K5_THREADS)
 k_peer_allreduce(PeerParams p) {
-    __shared__ uint32_t s_level;
-    __shared__ uint32_t s_lv[LH_MAX_RANKS];
+    extern __shared__ unsigned char s_level[];               // [H]: OR over ranks of the histogram's flag
+    __shared__ unsigned long long s_cells;
     const uint32_t t = threadIdx.x;
     const unsigned long long token = p.seq * 2ull + p.frozen;
     unsigned long long *mine = p.comm[p.rank];
@@ -1449,34 +1455,60 @@ k_peer_allreduce(PeerParams p) {
         if (!wait_token(mine + t, token, p.timeout_ns, &seen)) atomicMax(p.status, 1u);
         else if ((seen >> 1) == p.seq && (seen & 1ull) != p.frozen) atomicMax(p.status, 2u);
     }
+    if (t == 0) s_cells = 0;
     __syncthreads();
     const bool ok = ld_sys_u32(p.status) == 0;
     // 3. sum.  Work item = (histogram, chunk of K5_CHUNK cells); the set of cells follows the OR of all ranks' flags.
+    //    one-shot (small payload): every rank sums every item into its own array - one NVLink round trip.
+    //    two-shot (large payload): the rank that owns an item sums it and pushes the sum into every rank's array, so a
+    //    rank moves 2 * (world - 1) / world of the payload over NVLink instead of (world - 1) times the payload.
     if (ok) {
         const uint32_t wcells = 2u * p.win - 1u;
-        const uint32_t chunks_w = (wcells + K5_CHUNK - 1) / K5_CHUNK, chunks_all = 65536u / K5_CHUNK;
-        const uint32_t per_h = chunks_all;                   // items are indexed as if every histogram were dense
-        for (uint32_t item = blockIdx.x; item < p.H * per_h; item += gridDim.x) {
-            const uint32_t h = item / per_h, chunk = item - h * per_h;
-            __syncthreads();
-            if (t < p.world) s_lv[t] = ld_sys_u32(p.flags[t] + h);
-            __syncthreads();
-            if (t == 0) { uint32_t lv = 0; for (uint32_t r = 0; r < p.world; r++) lv |= s_lv[r]; s_level = lv; }
-            __syncthreads();
-            const uint32_t level = s_level;
+        constexpr uint32_t PER_H = 65536u / K5_CHUNK;         // items are indexed as if every histogram were dense
+        const uint32_t chunks_w = (wcells + K5_CHUNK - 1) / K5_CHUNK;
+        unsigned long long cells = 0;
+        for (uint32_t h = t; h < p.H; h += K5_THREADS) {
+            uint32_t lv = 0;
+            for (uint32_t r = 0; r < p.world; r++) lv |= ld_sys_u32(p.flags[r] + h);
+            s_level[h] = (unsigned char)lv;
+            if (blockIdx.x == 0 && lv) { p.out_flags[h] = lv; cells += (lv & 2u) ? 65536u : wcells; }
+        }
+        if (blockIdx.x == 0 && cells) atomicAdd(&s_cells, cells);
+        __syncthreads();
+        if (blockIdx.x == 0 && t == 0) *p.cells = s_cells;
+        const size_t nitems = (size_t)p.H * PER_H;
+        for (size_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const uint32_t h = (uint32_t)(item / PER_H), chunk = (uint32_t)(item % PER_H);
+            const uint32_t level = s_level[h];
             if (level == 0) continue;
             const bool dense = (level & 2u) != 0;
             if (!dense && chunk >= chunks_w) continue;
+            if (p.two_shot && (h + chunk) % p.world != p.rank) continue;
             const uint32_t ncell = dense ? 65536u : wcells;
-            if (chunk == 0 && t == 0) { p.out_flags[h] = level; atomicAdd(p.cells, (unsigned long long)ncell); }
+            constexpr int K = K5_CHUNK / K5_THREADS;
+            size_t cell[K];
+            unsigned long long sum[K];
 #pragma unroll
-            for (int k = 0; k < K5_CHUNK / K5_THREADS; k++) {
+            for (int k = 0; k < K; k++) {
                 const uint32_t i = chunk * K5_CHUNK + k * K5_THREADS + t;
-                if (i >= ncell) continue;
-                const size_t cell = (size_t)h * 65536u + (dense ? i : window_cell(i, p.win));
-                unsigned long long sum = 0;
-                for (uint32_t r = 0; r < p.world; r++) sum += ld_sys_u64(p.buckets[r] + cell);
-                if (sum) p.out_buckets[cell] = sum;
+                cell[k] = i < ncell ? (size_t)h * 65536u + (dense ? i : window_cell(i, p.win)) : (size_t)-1;
+                sum[k] = 0;
+            }
+#pragma unroll 4
+            for (uint32_t r = 0; r < p.world; r++) {          // K * world independent loads in flight per thread
+                const unsigned long long *src = p.buckets[r];
+#pragma unroll
+                for (int k = 0; k < K; k++)
+                    if (cell[k] != (size_t)-1) sum[k] += ld_sys_u64(src + cell[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                if (cell[k] == (size_t)-1 || sum[k] == 0) continue;
+                if (p.two_shot) {
+                    for (uint32_t r = 0; r < p.world; r++) p.out_peer[r][cell[k]] = sum[k];
+                } else {
+                    p.out_buckets[cell[k]] = sum[k];
+                }
             }
         }
         if (p.do_counters && blockIdx.x == 0) {
@@ -1487,18 +1519,19 @@ k_peer_allreduce(PeerParams p) {
             }
         }
     }
-    // 4. depart: the last CTA of this rank tells every peer it has finished reading them, then waits until
-    //    every peer has finished reading this rank
+    // 4. depart: the last CTA of this rank tells every peer it has finished reading them and that the sums it pushed
+    //    are visible (every CTA fences at system scope before it checks out), then waits for the same from every peer
     __syncthreads();
     __shared__ bool s_last;
     if (t == 0) {
-        __threadfence();
+        __threadfence_system();
         s_last = atomicAdd(p.block_counter, 1u) == gridDim.x - 1;
     }
     __syncthreads();
     if (!s_last) return;
     if (t == 0) *p.block_counter = 0;
     if (t < p.world && t != p.rank) {
+        __threadfence_system();
         st_release_sys_u64(p.comm[t] + LH_MAX_RANKS + p.rank, token);
         unsigned long long seen = 0;
         if (!wait_token(mine + LH_MAX_RANKS + t, token, p.timeout_ns, &seen)) atomicMax(p.status, 1u);

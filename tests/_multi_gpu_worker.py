@@ -1,5 +1,6 @@
 """torchrun worker for tests/test_gpu_multi.py and tests/test_gpu_comm.py: one rank per GPU; the bucket arrays are
-summed by the library's peer-memory all-reduce (argv[1] == "peer") or by an NCCL all-reduce ("nccl", default)."""
+summed by the library's peer-memory all-reduce (argv[1] == "peer") or by an NCCL all-reduce ("nccl", default);
+argv[2] = number of histograms."""
 import os
 import sys
 
@@ -22,7 +23,7 @@ def main():
     n_total = 4_000_001
     ps = list(o.DEFAULT_PERCENTILES.values())
     a, b = shard_range(rank, world, n_total)
-    H = 3
+    H = int(sys.argv[2]) if len(sys.argv) > 2 else 3      # >= 16 histograms: the all-reduce takes its two-shot (push) form
     with lh.Engine(device=local, max_histograms=H, max_counters=4) as eng:
         sh = ShardedEngine(eng, local, collective=sys.argv[1] if len(sys.argv) > 1 else "nccl")
         d = eng.gen_stream(lh.STREAM_S, b - a, lh.DEFAULT_SEED, start=a)

@@ -86,6 +86,52 @@ def test_two_contexts_one_process(oracle):
             e.close()
 
 
+def test_two_contexts_many_histograms_two_shot(oracle):
+    """H = 48 histograms: the payload is above the 1 MiB threshold, so each rank sums its share of the (histogram,
+    chunk) items and PUSHES the sums into every rank's reduced array (reduce-scatter + all-gather in one kernel).
+    Histogram 3 also gets out-of-window values on one rank only (dense flag on one side)."""
+    import torch
+    import loghisto_b200 as lh
+    from loghisto_b200.distributed import shard_range
+    world = 2
+    devs = [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
+    H, n_total = 48, 2_000_003
+    engs = [lh.Engine(device=d, max_histograms=H, max_counters=4) for d in devs]
+    try:
+        handles = b"".join(e.comm_export() for e in engs)
+        for r, e in enumerate(engs):
+            e.comm_import(r, world, handles)
+        for interval in range(2):
+            vals = oracle.gen_stream(lh.STREAM_S, n_total, SEED + 10 + interval)
+            ids = oracle.gen_ids(0, n_total, H - 2, SEED + 10 + interval)        # the last two histograms stay untouched
+            huge = np.array([1e300, -1e300, 3e200, -7e250], dtype=np.float64)    # keys far outside the window
+            want = np.zeros((H, 65536), dtype=np.uint64)
+            want[: H - 2] = oracle.ingest_keyed(ids, vals, H - 2)
+            want[3] += oracle.ingest(huge)
+            for r, e in enumerate(engs):
+                a, b = shard_range(r, world, n_total)
+                e.ingest_keyed_f64_u16(e.upload(ids[a:b].astype(np.uint16)), e.upload(vals[a:b]), b - a)
+            engs[1].ingest_f64(3, engs[1].upload(huge), len(huge))
+            for e in engs:
+                e.snapshot_begin()
+                e.snapshot_allreduce()
+            for r, e in enumerate(engs):
+                red = e.snapshot_reduce(PS)
+                sp = e.snapshot_export()
+                e.snapshot_end()
+                assert e.comm_info()["status"] == 0
+                for h in range(H):
+                    assert (dense_from_sparse(sp, h) == want[h]).all(), (interval, r, h)
+                    ref = oracle.process_histogram(want[h], PS)
+                    assert int(red.counts[h]) == ref["total"]
+                    if ref["total"]:
+                        assert (red.pkeys[h] == ref["pkeys"]).all()
+            assert engs[0].comm_last_bytes() > 0
+    finally:
+        for e in engs:
+            e.close()
+
+
 def test_allreduce_requires_import():
     import loghisto_b200 as lh
     with lh.Engine(device=0) as e:
@@ -95,7 +141,8 @@ def test_allreduce_requires_import():
         e.snapshot_end()
 
 
-def test_one_process_per_gpu_peer_collective():
+@pytest.mark.parametrize("H", [3, 40])        # one-shot and two-shot (push) forms of the all-reduce, over CUDA IPC mappings
+def test_one_process_per_gpu_peer_collective(H):
     import torch
     n = torch.cuda.device_count()
     if n < 2:
@@ -106,7 +153,7 @@ def test_one_process_per_gpu_peer_collective():
     port = s.getsockname()[1]
     s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "_multi_gpu_worker.py"), "peer"]
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "_multi_gpu_worker.py"), "peer", str(H)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0 and "MULTI_GPU_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
 
