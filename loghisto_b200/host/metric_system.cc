@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <stdexcept>
@@ -41,10 +42,9 @@ void check(lh_ctx *ctx, lh_status st, const char *what) {
     }
 }
 
-size_t this_thread_slot(size_t n) {
+size_t next_thread_slot() {
     static std::atomic<size_t> next{0};
-    thread_local size_t mine = next.fetch_add(1);
-    return mine % n;
+    return next.fetch_add(1);
 }
 
 // ---- per-thread name -> id cache --------------------------------------------------------------------------
@@ -73,39 +73,70 @@ inline uint64_t hash_bytes(const char *p, size_t n) {
 
 struct NameCache {
     // open addressing, linear probing, load factor <= 1/2: a name that was interned once is found without ever going
-    // back to the shared table (a direct-mapped cache thrashes as soon as two hot names collide)
-    struct Entry { uint64_t hash = 0; uint32_t id = 0; bool used = false; std::string name; };
-    uint64_t system_id = 0;                      // which MetricSystem the entries belong to
+    // back to the shared table (a direct-mapped cache thrashes as soon as two hot names collide).  Entries are 24
+    // bytes; the names' bytes live in an append-only arena owned by the cache.
+    struct Entry { uint64_t hash; const char *name; uint32_t len; uint32_t id_plus1; };   // id_plus1 == 0: empty
     std::vector<Entry> e;
+    std::vector<std::unique_ptr<char[]>> arena;
+    size_t arena_left = 0;
+    char *arena_next = nullptr;
     size_t count = 0;
     bool find(uint64_t h, const char *p, size_t n, uint32_t *id) const {
         if (e.empty()) return false;
         const size_t mask = e.size() - 1;
         for (size_t i = h & mask;; i = (i + 1) & mask) {
             const Entry &x = e[i];
-            if (!x.used) return false;
-            if (x.hash == h && x.name.size() == n && memcmp(x.name.data(), p, n) == 0) { *id = x.id; return true; }
+            if (!x.id_plus1) return false;
+            if (x.hash == h && x.len == n && memcmp(x.name, p, n) == 0) { *id = x.id_plus1 - 1; return true; }
         }
     }
-    void insert_raw(uint64_t h, std::string &&name, uint32_t id) {
+    void insert_raw(const Entry &en) {
         const size_t mask = e.size() - 1;
-        size_t i = h & mask;
-        while (e[i].used) i = (i + 1) & mask;
-        e[i].hash = h; e[i].id = id; e[i].used = true; e[i].name = std::move(name);
+        size_t i = en.hash & mask;
+        while (e[i].id_plus1) i = (i + 1) & mask;
+        e[i] = en;
     }
     void put(uint64_t h, const char *p, size_t n, uint32_t id) {
-        if (e.empty()) e.resize(256);
+        if (e.empty()) e.assign(256, Entry{0, nullptr, 0, 0});
         if ((count + 1) * 2 > e.size()) {        // grow and rehash
-            std::vector<Entry> old(e.size() * 2);
+            std::vector<Entry> old(e.size() * 2, Entry{0, nullptr, 0, 0});
             old.swap(e);
-            for (Entry &x : old) if (x.used) insert_raw(x.hash, std::move(x.name), x.id);
+            for (const Entry &x : old) if (x.id_plus1) insert_raw(x);
         }
-        insert_raw(h, std::string(p, n), id);
+        if (n > arena_left) {
+            const size_t block = std::max<size_t>(n, 16384);
+            arena.emplace_back(new char[block]);
+            arena_next = arena.back().get();
+            arena_left = block;
+        }
+        memcpy(arena_next, p, n);
+        insert_raw(Entry{h, arena_next, (uint32_t)n, id + 1});
+        arena_next += n; arena_left -= n;
         count++;
     }
-    void reset(uint64_t sys) { system_id = sys; e.clear(); count = 0; }
+    void reset() { e.clear(); arena.clear(); arena_left = 0; arena_next = nullptr; count = 0; }
 };
-thread_local NameCache tl_hcache, tl_ccache;
+
+// Everything a thread needs on the per-call path, reached through ONE thread-local pointer (a plain pointer has no
+// initialisation guard; the object behind it is created on the thread's first call and freed when the thread ends).
+struct ThreadState {
+    uint64_t system_id = 0;                      // which MetricSystem `shard` and the caches belong to
+    void *shard = nullptr;                       // MetricSystem::Shard * of this thread (round-robin over the shards)
+    size_t slot = 0;                             // process-wide thread number
+    NameCache h, c;
+};
+struct ThreadStateOwner {                        // destroyed at thread exit
+    ThreadState *p = nullptr;
+    ~ThreadStateOwner() { delete p; }
+};
+thread_local ThreadState *tl_state = nullptr;
+thread_local ThreadStateOwner tl_owner;
+ThreadState *make_thread_state() {
+    tl_owner.p = new ThreadState();
+    tl_owner.p->slot = next_thread_slot();
+    tl_state = tl_owner.p;
+    return tl_state;
+}
 
 std::atomic<uint64_t> g_system_ids{1};
 
@@ -163,14 +194,17 @@ MetricSystem::MetricSystem(std::chrono::nanoseconds interval, bool /*sysStats*/,
     percentiles_ = {{"%s_min", 0.0}, {"%s_50", .5}, {"%s_75", .75}, {"%s_90", .9}, {"%s_95", .95},
                     {"%s_99", .99}, {"%s_99.9", .999}, {"%s_99.99", .9999}, {"%s_max", 1.0}};   // metrics.go:145-155
     // one shard per hardware thread: goroutines of print_benchmark.go:59-67 become OS threads here, each with its own
-    uint32_t nshards = opt.shards ? opt.shards : std::min<uint32_t>(std::max(1u, std::thread::hardware_concurrency()), 256u);
+    // operational overrides (no recompile): LOGHISTO_B200_SHARDS, LOGHISTO_B200_STAGING_BYTES
+    if (const char *e = getenv("LOGHISTO_B200_SHARDS")) { long v = atol(e); if (v > 0 && v <= 4096) opt_.shards = (uint32_t)v; }
+    if (const char *e = getenv("LOGHISTO_B200_STAGING_BYTES")) { long long v = atoll(e); if (v >= 4096) opt_.staging_bytes = (uint64_t)v; }
+    uint32_t nshards = opt_.shards ? opt_.shards : std::min<uint32_t>(std::max(1u, std::thread::hardware_concurrency()), 256u);
     system_id_ = g_system_ids.fetch_add(1);
     lh_config cfg{};
     cfg.struct_size = sizeof(cfg);
     cfg.device = opt.device;
     cfg.max_histograms = opt.max_histograms;
     cfg.max_counters = opt.max_counters;
-    cfg.staging_bytes = opt.staging_bytes;
+    cfg.staging_bytes = opt_.staging_bytes;
     cfg.staging_slots = 2 * nshards + 2;   // every shard may hold one histogram and one counter slot (memory is allocated on first use)
     cfg.precision = opt.precision;
     lh_status st = lh_create(&cfg, &ctx_);
@@ -212,33 +246,45 @@ uint16_t MetricSystem::intern(std::shared_mutex &mu, std::unordered_map<std::str
 }
 
 // name -> dense id through the calling thread's cache; false when the name table is full (sample dropped, counted)
+// The calling thread's state for THIS system (a thread that moves to another MetricSystem starts over).
+static inline ThreadState *thread_state(uint64_t system_id, const std::vector<std::unique_ptr<MetricSystem::Shard>> &shards) {
+    ThreadState *ts = tl_state;
+    if (__builtin_expect(ts == nullptr, 0)) ts = make_thread_state();
+    if (__builtin_expect(ts->system_id != system_id, 0)) {
+        ts->system_id = system_id;
+        ts->shard = shards[ts->slot % shards.size()].get();
+        ts->h.reset();
+        ts->c.reset();
+    }
+    return ts;
+}
+
 bool MetricSystem::lookup_histogram(const char *p, size_t n, uint32_t *id) {
-    if (tl_hcache.system_id != system_id_) tl_hcache.reset(system_id_);
+    ThreadState *ts = thread_state(system_id_, shards_);
     const uint64_t h = hash_bytes(p, n);
-    if (tl_hcache.find(h, p, n, id)) return true;
+    if (ts->h.find(h, p, n, id)) return true;
     bool ok;
     const uint16_t v = intern(histo_mu_, histo_ids_, histo_names_, std::string(p, n), opt_.max_histograms, &ok);
     if (!ok) { dropped_over_limit_.fetch_add(1, std::memory_order_relaxed); return false; }
-    tl_hcache.put(h, p, n, v);
+    ts->h.put(h, p, n, v);
     *id = v;
     return true;
 }
 bool MetricSystem::lookup_counter(const char *p, size_t n, uint32_t *id) {
-    if (tl_ccache.system_id != system_id_) tl_ccache.reset(system_id_);
+    ThreadState *ts = thread_state(system_id_, shards_);
     const uint64_t h = hash_bytes(p, n);
-    if (tl_ccache.find(h, p, n, id)) return true;
+    if (ts->c.find(h, p, n, id)) return true;
     bool ok;
     const uint16_t v = intern(counter_mu_, counter_ids_, counter_names_, std::string(p, n), opt_.max_counters, &ok);
     if (!ok) { dropped_over_limit_.fetch_add(1, std::memory_order_relaxed); return false; }
-    tl_ccache.put(h, p, n, v);
+    ts->c.put(h, p, n, v);
     *id = v;
     return true;
 }
 
 // Ingest never fails the caller and never throws (metrics.go:570-573, 632-636: problems are logged and data is
 // dropped): a staging call that fails resets the shard, counts the samples it held as dropped and logs once.
-void MetricSystem::histogram_id(uint32_t id, double value) noexcept {
-    Shard &s = *shards_[this_thread_slot(shards_.size())];
+void MetricSystem::append_histogram(Shard &s, uint32_t id, double value) noexcept {
     ShardGuard g(s);
     if (!s.h_open) {
         lh_status st = lh_staging_acquire(ctx_, &s.hs);
@@ -252,6 +298,9 @@ void MetricSystem::histogram_id(uint32_t id, double value) noexcept {
     s.h_vals[s.h_n] = value;
     s.h_ids[s.h_n] = (uint16_t)id;
     if (++s.h_n == s.h_cap) commit_histograms(s);
+}
+void MetricSystem::histogram_id(uint32_t id, double value) noexcept {
+    append_histogram(*static_cast<Shard *>(thread_state(system_id_, shards_)->shard), id, value);
 }
 
 void MetricSystem::commit_histograms(Shard &s) noexcept {
@@ -278,21 +327,22 @@ void MetricSystem::commit_counters(Shard &s) noexcept {
     s.c_n = 0;
 }
 
-void MetricSystem::Histogram(const std::string &name, double value) noexcept {
-    uint32_t id;
-    if (!lookup_histogram(name.data(), name.size(), &id)) return;   // name table full: dropped and counted
-    histogram_id(id, value);
-}
+void MetricSystem::Histogram(const std::string &name, double value) noexcept { Histogram(name.data(), name.size(), value); }
 void MetricSystem::Histogram(const char *name, size_t len, double value) noexcept {
+    // steady state: one thread-local pointer, one hash of the name's bytes, one probe of this thread's name cache, one
+    // uncontended spinlock, two stores into pinned memory
+    ThreadState *ts = thread_state(system_id_, shards_);
     uint32_t id;
-    if (!lookup_histogram(name, len, &id)) return;
-    histogram_id(id, value);
+    if (__builtin_expect(!ts->h.find(hash_bytes(name, len), name, len, &id), 0)) {
+        if (!lookup_histogram(name, len, &id)) return;              // name table full: dropped and counted
+    }
+    append_histogram(*static_cast<Shard *>(ts->shard), id, value);
 }
 
 void MetricSystem::Counter(const std::string &name, uint64_t amount) noexcept {
     uint32_t id;
     if (!lookup_counter(name.data(), name.size(), &id)) return;
-    Shard &s = *shards_[this_thread_slot(shards_.size())];
+    Shard &s = *static_cast<Shard *>(thread_state(system_id_, shards_)->shard);
     ShardGuard g(s);
     s.c_touched[id] = 1;                    // Counter(name, 0) still makes the name appear in Rates (metrics.go:430-433)
     s.c_any_touched = true;

@@ -153,6 +153,7 @@ class MetricSystem {
                     std::vector<std::string> &names, const std::string &name, uint32_t limit, bool *ok);
     bool lookup_histogram(const char *p, size_t n, uint32_t *id);
     bool lookup_counter(const char *p, size_t n, uint32_t *id);
+    void append_histogram(Shard &s, uint32_t id, double value) noexcept;
     void commit_histograms(Shard &s) noexcept;
     void commit_counters(Shard &s) noexcept;
     void flush_shard(Shard &s, std::vector<uint8_t> *touched);

@@ -2,6 +2,7 @@
 // mirror: `concurrency` threads loop { StartTimer(name); op(); Stop() } against one MetricSystem with a 1 s (here:
 // configurable) interval, a receiver prints the interesting keys of every ProcessedMetricSet.  Unlike the reference
 // it stops after `seconds` and returns the last interval's <name>_count, so it can be used as a measurement.
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -89,30 +90,68 @@ inline uint32_t stream_id(uint64_t seed, uint64_t i, uint32_t H) {    // ids kin
 }
 }  // namespace
 
-extern "C" __attribute__((visibility("default")))
 // Feeds samples [start, start + n) of stream `kind` through ms.Histogram(names[id_i], value_i) from `threads` threads
-// (contiguous slices); returns the seconds the calls took (excluding thread start-up).  The caller then collects.
-double lhms_histogram_stream(void *msp, const char *const *names, uint32_t n_names, int kind, uint64_t seed, uint64_t start,
-                             uint64_t n, unsigned threads) {
-    auto *ms = static_cast<loghisto::MetricSystem *>(msp);
-    if (!ms || !names || !n_names || !threads) return -1.0;
+// (contiguous slices).  Every thread works in blocks of 1024 samples: it regenerates the block's (name index, value)
+// pairs, then makes the 1024 Histogram() calls.  Returns the wall seconds of the whole run (generator included,
+// thread start-up excluded); *call_seconds (optional) receives the largest per-thread time spent inside the call
+// loops alone -- the cost of the API path without the synthetic generator.  dry != 0 skips the calls (generator only).
+static double histogram_stream_impl(loghisto::MetricSystem *ms, const char *const *names, uint32_t n_names, int kind, uint64_t seed,
+                                    uint64_t start, uint64_t n, unsigned threads, int dry, double *call_seconds) {
+    using clk = std::chrono::steady_clock;
     std::vector<std::string> nm(names, names + n_names);
     std::atomic<unsigned> ready{0};
     std::atomic<bool> go{false};
     std::vector<std::thread> workers;
+    std::vector<double> in_calls(threads, 0.0);
+    std::atomic<uint64_t> sink{0};
     const uint64_t per = n / threads;
     for (unsigned t = 0; t < threads; t++)
         workers.emplace_back([&, t] {
+            constexpr int B = 1024;
+            double vals[B];
+            uint32_t ids[B];
             const uint64_t a = start + per * t, b = (t + 1 == threads) ? start + n : a + per;
+            double spent = 0;
+            uint64_t acc = 0;
             ready.fetch_add(1);
             while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
-            for (uint64_t i = a; i < b; i++) ms->Histogram(nm[n_names == 1 ? 0 : stream_id(seed, i, n_names)], stream_value(kind, seed, i));
+            for (uint64_t i0 = a; i0 < b; i0 += B) {
+                const int m = (int)std::min<uint64_t>(B, b - i0);
+                for (int k = 0; k < m; k++) {
+                    vals[k] = stream_value(kind, seed, i0 + k);
+                    ids[k] = n_names == 1 ? 0u : stream_id(seed, i0 + k, n_names);
+                }
+                if (dry) { for (int k = 0; k < m; k++) acc += ids[k] + (uint64_t)vals[k]; continue; }
+                const auto t0 = clk::now();
+                for (int k = 0; k < m; k++) ms->Histogram(nm[ids[k]], vals[k]);
+                spent += std::chrono::duration<double>(clk::now() - t0).count();
+            }
+            in_calls[t] = spent;
+            sink.fetch_add(acc);
         });
     while (ready.load() < threads) std::this_thread::yield();
-    const auto t0 = std::chrono::steady_clock::now();
+    const auto t0 = clk::now();
     go.store(true, std::memory_order_release);
     for (auto &w : workers) w.join();
-    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const double wall = std::chrono::duration<double>(clk::now() - t0).count();
+    if (call_seconds) { double mx = 0; for (double x : in_calls) mx = std::max(mx, x); *call_seconds = mx; }
+    return wall;
+}
+
+extern "C" __attribute__((visibility("default")))
+double lhms_histogram_stream(void *msp, const char *const *names, uint32_t n_names, int kind, uint64_t seed, uint64_t start,
+                             uint64_t n, unsigned threads) {
+    auto *ms = static_cast<loghisto::MetricSystem *>(msp);
+    if (!ms || !names || !n_names || !threads) return -1.0;
+    return histogram_stream_impl(ms, names, n_names, kind, seed, start, n, threads, 0, nullptr);
+}
+
+extern "C" __attribute__((visibility("default")))
+double lhms_histogram_stream2(void *msp, const char *const *names, uint32_t n_names, int kind, uint64_t seed, uint64_t start,
+                              uint64_t n, unsigned threads, int dry, double *call_seconds) {
+    auto *ms = static_cast<loghisto::MetricSystem *>(msp);
+    if (!ms || !names || !n_names || !threads) return -1.0;
+    return histogram_stream_impl(ms, names, n_names, kind, seed, start, n, threads, dry, call_seconds);
 }
 
 extern "C" __attribute__((visibility("default")))

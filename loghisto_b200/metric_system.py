@@ -47,6 +47,9 @@ def _bind(L):
     L.lhms_timer_free.argtypes = [vp]
     L.lhms_histogram_stream.restype = C.c_double
     L.lhms_histogram_stream.argtypes = [vp, C.POINTER(C.c_char_p), C.c_uint32, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint]
+    L.lhms_histogram_stream2.restype = C.c_double
+    L.lhms_histogram_stream2.argtypes = [vp, C.POINTER(C.c_char_p), C.c_uint32, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint,
+                                         C.c_int, C.POINTER(C.c_double)]
     L.lhms_timer_loop.restype = C.c_double
     L.lhms_timer_loop.argtypes = [C.c_char_p, C.c_uint, C.c_double, C.c_int64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
     L.lhms_print_benchmark.restype = C.c_double
@@ -212,6 +215,14 @@ class MetricSystem:
         samples [start, start + n) of synthetic stream `kind`; returns the seconds the calls took."""
         arr = (C.c_char_p * len(names))(*[x.encode() for x in names])
         return float(self._lib.lhms_histogram_stream(self._h, arr, len(names), kind, seed, start, n, threads))
+
+    def histogram_stream_timed(self, names, kind: int, seed: int, start: int, n: int, threads: int, dry: bool = False):
+        """As histogram_stream; returns (wall seconds incl. the synthetic generator, largest per-thread seconds spent
+        inside the Histogram() call loops alone).  dry=True runs the generator only."""
+        arr = (C.c_char_p * len(names))(*[x.encode() for x in names])
+        calls = C.c_double()
+        wall = self._lib.lhms_histogram_stream2(self._h, arr, len(names), kind, seed, start, n, threads, 1 if dry else 0, C.byref(calls))
+        return float(wall), float(calls.value)
 
 
 def timer_loop(name: str, threads: int, seconds: float, interval_s: float = 0.1, device: int = 0):

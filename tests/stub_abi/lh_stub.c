@@ -89,10 +89,14 @@ static lh_status lh_staging_commit_keyed_f64_u16_impl(lh_ctx *c, const lh_stagin
     const double *v = (const double *)c->slot_mem[s->slot];
     const uint16_t *ids = (const uint16_t *)((const char *)c->slot_mem[s->slot] + ids_offset);
     uint64_t *b = c->buckets[c->active];
+#ifndef LH_STUB_DISCARD                 /* -DLH_STUB_DISCARD: host-path profiling only (tools/host_path_profile.sh) */
     for (size_t i = 0; i < n; i++) {
         if (ids[i] >= c->cfg.max_histograms) { c->dropped++; continue; }
         b[(size_t)ids[i] * 65536u + (uint16_t)lho_compress(v[i])]++;
     }
+#else
+    (void)v; (void)ids; (void)b;
+#endif
     c->samples += n;
     c->slot_busy[s->slot] = 0;
     return LH_OK;
