@@ -179,6 +179,7 @@ struct lh_ctx {
     uint32_t hot_replicas = 1;          // copies of the hot window (all L2-resident); only the vector RED kernel spreads over them
     int keyed_mode = 0;                 // 0 auto, 1 force L2-atomic kernel, 2 force the write-combining owner kernel
     int64_t kp_chunk = 32 << 20;        // samples per chunk of the owner-partitioned kernel
+    uint32_t wc_flush_samples = 24576;  // samples a CTA bins between two flushes of its owner buffers
     int wc_spt = 4;                     // samples per thread per tile of that kernel (4: 1024 threads; 8, 16: 512 threads)
     // owner-partitioned keyed kernel scratch (allocated on first use)
     unsigned short *d_kp_queues = nullptr;
@@ -363,7 +364,9 @@ lh_status launch_keyed_wc_spt(lh_ctx *ctx, int b, const IdT *ids, const ValT *va
     WcParams prm{};
     prm.ids = ids; prm.vals = vals; prm.n = n4x4; prm.ids_per = ids_per; prm.cap = (uint32_t)cap;
     prm.inv_p = (uint32_t)(((uint64_t)1 << 32) / (uint64_t)P) + 1u;
-    prm.inv_vq = (uint32_t)(((uint64_t)1 << 32) / (uint64_t)(cap / 8)) + 1u;
+    // samples between two flushes of the shared-memory owner buffers: the flush costs about the same whatever it moves,
+    // so as many as the buffers hold at 4 sigma (wc_flush_samples; default 24576)
+    prm.flush_tiles = std::max<uint32_t>(1u, (uint32_t)(ctx->wc_flush_samples / S::TILE));
     prm.slice_tiles = (uint32_t)slice_tiles; prm.queues = ctx->d_kp_queues; prm.q_cnt = ctx->d_kp_cnt;
     prm.barrier = d_barrier; prm.rare = ctx->d_kp_rare; prm.o = keyed_out(ctx, b);
     Prec pc = ctx->pc;
@@ -1584,6 +1587,11 @@ extern "C" lh_status lh_tune(lh_ctx *ctx, const char *key, int64_t value) {
     if (!strcmp(key, "keyed_mode")) {
         if (value < 0 || value > 2) return fail(ctx, LH_ERR_RANGE, "keyed_mode is 0 (auto), 1 (L2 atomics) or 2 (owner-partitioned, write-combining)");
         ctx->keyed_mode = (int)value;
+        return LH_OK;
+    }
+    if (!strcmp(key, "wc_flush")) {
+        if (value < 4096 || value > 65536) return fail(ctx, LH_ERR_RANGE, "wc_flush is 4096 ... 65536 samples");
+        ctx->wc_flush_samples = (uint32_t)value;
         return LH_OK;
     }
     if (!strcmp(key, "wc_spt")) {

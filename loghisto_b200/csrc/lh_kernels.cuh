@@ -619,9 +619,9 @@ constexpr int WC_LINE = 64;                   // records per line (128 B)
 template <int SPT> struct WcShape {           // SPT = samples per thread per tile
     static constexpr int THREADS = SPT == 4 ? 1024 : 512;      // SPT 4 fits 64 registers per thread: twice the warps per SM
     static constexpr int TILE = THREADS * SPT;
-    static constexpr int FLUSH_EVERY = 16384 / TILE;            // tiles binned between two flushes (16384 samples)
-    // records one owner's buffer must hold: < WC_LINE carried over + the share of 16384 samples (~111 at P = 148)
-    // + 6 sigma of the binomial (63); beyond that the sample takes the L2 route
+    // records one owner's buffer must hold: < WC_LINE carried over + its share of the samples binned between two
+    // flushes (WcParams::flush_tiles; ~166 for 24576 samples at P = 148) + 4 sigma of the binomial; a record that
+    // does not fit takes the exact route
     static constexpr int CAP = 256;
     // storage per owner: CAP + one spill line (the remainder copy reads a whole line) + 8 records of padding so that
     // the 128-bit accesses of the per-owner flush (thread o <-> owner o) are bank-conflict free
@@ -636,7 +636,7 @@ struct WcParams {
     uint32_t cap;                    // records per (owner, writer) sub-queue per parity, multiple of WC_LINE
     uint32_t slice_tiles;            // tiles per CTA per chunk
     uint32_t inv_p;                  // floor(2^32 / P) + 1: id / P == __umulhi(id, inv_p) for id < 65536
-    uint32_t inv_vq;                 // floor(2^32 / (cap / 8)) + 1: v / (cap / 8) == __umulhi(v, inv_vq) for v < P * cap / 8
+    uint32_t flush_tiles;            // tiles binned between two flushes of the owner buffers
     unsigned short *queues;          // [2][P owners][P writers][cap]
     unsigned int *q_cnt;             // [2][P owners][P writers]
     unsigned int *barrier;           // grid barrier counter, zeroed by the host before the launch
@@ -766,10 +766,10 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
                         }
                 }
             }
-            // ---- flush every FLUSH_EVERY tiles.  A quarter warp (8 lanes x 16 B = one 128-byte line) serves one owner:
+            // ---- flush every prm.flush_tiles tiles.  A quarter warp (8 lanes x 16 B = one 128-byte line) serves one owner:
             //      its full lines go to my sub-queue of that owner as coalesced 128-byte stores, the remainder (< 64
             //      records) moves to the front.  No barrier is needed between tiles that do not flush: appends are atomic.
-            if (++since_flush == (uint32_t)S::FLUSH_EVERY) {
+            if (++since_flush == prm.flush_tiles) {
                 since_flush = 0;
                 __syncthreads();
                 const uint32_t sub = (tid & 31) >> 3, k8 = tid & 7;

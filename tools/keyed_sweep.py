@@ -15,16 +15,17 @@ quick = len(sys.argv) > 3
 eng = lh.Engine(device=0, max_histograms=H, max_counters=1)
 d = eng.alloc(n, "float64")
 ids = eng.alloc(n, "uint16")
-configs = [("vec", 1, 16, 8 << 20)]
+configs = [("vec", 1, 16, 8 << 20, 24576)]
 for spt in ((4,) if quick else (16, 8, 4)):
     for chunk in ((32 << 20,) if quick else (16 << 20, 32 << 20, 64 << 20)):
-        configs.append(("wc", 2, spt, chunk))
+        for flush in ((16384, 24576, 28672) if spt == 4 else (24576,)):
+            configs.append(("wc", 2, spt, chunk, flush))
 for sname, kind, idkind in (("U", 0, 0), ("L", 1, 0), ("C", 3, 0), ("U/zipf-ids", 0, 1)):
     eng.gen_stream(kind, n, lh.DEFAULT_SEED, out=d)
     eng.gen_ids_u16(idkind, n, H, lh.DEFAULT_SEED, out=ids)
     ref = None
-    for name, mode, spt, chunk in configs:
-        eng.tune("keyed_mode", mode); eng.tune("wc_spt", spt); eng.tune("kp_chunk", chunk)
+    for name, mode, spt, chunk, flush in configs:
+        eng.tune("keyed_mode", mode); eng.tune("wc_spt", spt); eng.tune("kp_chunk", chunk); eng.tune("wc_flush", flush)
         t = []
         for _ in range(4):
             eng.ingest_keyed_f64_u16(ids, d, n)
@@ -34,7 +35,7 @@ for sname, kind, idkind in (("U", 0, 0), ("L", 1, 0), ("C", 3, 0), ("U/zipf-ids"
         if ref is None:
             ref = sig
         ms = sorted(t)[1]
-        print("H=%-4d stream %-10s %-4s spt=%-2d chunk=%-9d %8.3f ms %7.1f G samples/s %5.2f TB/s  kernel=%s  count_ok=%s same_buckets=%s"
-              % (H, sname, name, spt, chunk, ms, n / ms / 1e6, n * 10 / ms / 1e9, eng.keyed_kernel_name(),
+        print("H=%-4d stream %-10s %-4s spt=%-2d chunk=%-9d flush=%-5d %8.3f ms %7.1f G samples/s %5.2f TB/s  kernel=%s  count_ok=%s same_buckets=%s"
+              % (H, sname, name, spt, chunk, flush, ms, n / ms / 1e6, n * 10 / ms / 1e9, eng.keyed_kernel_name(),
                  int(red.counts.sum()) == 4 * n, sig == ref), flush=True)
 eng.close()
