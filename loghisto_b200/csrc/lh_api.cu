@@ -180,7 +180,7 @@ struct lh_ctx {
     int keyed_mode = 0;                 // 0 auto, 1 force L2-atomic kernel, 2 force the write-combining owner kernel
     int64_t kp_chunk = 32 << 20;        // samples per chunk of the owner-partitioned kernel
     uint32_t wc_flush_samples = 24576;  // samples a CTA bins between two flushes of its owner buffers
-    int wc_spt = 4;                     // samples per thread per tile of that kernel (4: 1024 threads; 8, 16: 512 threads)
+    int wc_spt = 4;                     // tile shape of that kernel (4: 1024 threads x 4 samples; 3: 768 x 4; 8: 512 x 8)
     // owner-partitioned keyed kernel scratch (allocated on first use)
     unsigned short *d_kp_queues = nullptr;
     unsigned int *d_kp_cnt = nullptr;     // per-(owner, writer) record counts, then the grid-barrier word
@@ -380,8 +380,8 @@ lh_status launch_keyed_wc_spt(lh_ctx *ctx, int b, const IdT *ids, const ValT *va
 template <typename IdT, typename ValT>
 lh_status launch_keyed_wc(lh_ctx *ctx, int b, const IdT *ids, const ValT *vals, size_t n4x4, cudaStream_t s, bool *used, size_t *taken) {
     return ctx->wc_spt == 4 ? launch_keyed_wc_spt<IdT, ValT, 4>(ctx, b, ids, vals, n4x4, s, used, taken)
-         : ctx->wc_spt == 8 ? launch_keyed_wc_spt<IdT, ValT, 8>(ctx, b, ids, vals, n4x4, s, used, taken)
-                            : launch_keyed_wc_spt<IdT, ValT, 16>(ctx, b, ids, vals, n4x4, s, used, taken);
+         : ctx->wc_spt == 3 ? launch_keyed_wc_spt<IdT, ValT, 3>(ctx, b, ids, vals, n4x4, s, used, taken)
+                            : launch_keyed_wc_spt<IdT, ValT, 8>(ctx, b, ids, vals, n4x4, s, used, taken);
 }
 
 template <typename IdT, typename ValT>
@@ -1595,7 +1595,7 @@ extern "C" lh_status lh_tune(lh_ctx *ctx, const char *key, int64_t value) {
         return LH_OK;
     }
     if (!strcmp(key, "wc_spt")) {
-        if (value != 4 && value != 8 && value != 16) return fail(ctx, LH_ERR_RANGE, "wc_spt is 4, 8 or 16");
+        if (value != 4 && value != 3 && value != 8) return fail(ctx, LH_ERR_RANGE, "wc_spt is 4 (1024 threads x 4), 3 (768 x 4) or 8 (512 x 8)");
         ctx->wc_spt = (int)value;
         return LH_OK;
     }

@@ -616,9 +616,11 @@ k_ingest_keyed_small(const IdT *__restrict__ ids, const ValT *__restrict__ vals,
 constexpr int WC_MAX_PARTS = 160;             // owners = CTAs (one per SM)
 constexpr int WC_LINE = 64;                   // records per line (128 B)
 
-template <int SPT> struct WcShape {           // SPT = samples per thread per tile
-    static constexpr int THREADS = SPT == 4 ? 1024 : 512;      // SPT 4 fits 64 registers per thread: twice the warps per SM
-    static constexpr int TILE = THREADS * SPT;
+template <int SPT> struct WcShape {           // shape code: 4 = 1024 threads x 4 samples per tile (64 registers per thread),
+                                              // 3 = 768 threads x 4 samples (80 registers), 8 = 512 threads x 8 samples (128)
+    static constexpr int THREADS = SPT == 4 ? 1024 : SPT == 3 ? 768 : 512;
+    static constexpr int PER = SPT == 3 ? 4 : SPT;             // samples per thread per tile
+    static constexpr int TILE = THREADS * PER;
     // records one owner's buffer must hold: < WC_LINE carried over + its share of the samples binned between two
     // flushes (WcParams::flush_tiles; ~166 for 24576 samples at P = 148) + 4 sigma of the binomial; a record that
     // does not fit takes the exact route
@@ -669,7 +671,7 @@ __global__ void __launch_bounds__(WcShape<SPT>::THREADS, 1)
 k_ingest_keyed_wc(WcParams prm, Prec pc) {
     using S = WcShape<SPT>;
     constexpr int WC_THREADS = S::THREADS;
-    constexpr int GROUPS = SPT / 4;
+    constexpr int GROUPS = S::PER / 4;
     extern __shared__ __align__(16) unsigned char wc_smem[];
     const uint32_t P = gridDim.x, p = blockIdx.x, tid = threadIdx.x;
     unsigned int *s_hist = reinterpret_cast<unsigned int *>(wc_smem);                       // [ids_per][win]

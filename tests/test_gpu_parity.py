@@ -484,8 +484,8 @@ def test_mixed_ops_interval_pipeline(lh, oracle):
             assert (dense_from_sparse(sp, h) == want[h]).all()
 
 
-@pytest.mark.parametrize("chunk,spt", [(65536, 16), (1 << 20, 16), (65536, 8), (1 << 20, 8)])
-def test_keyed_owner_partitioned_kernel(lh, oracle, chunk, spt):
+@pytest.mark.parametrize("chunk,spt,flush", [(65536, 4, 24576), (1 << 20, 4, 4096), (1 << 20, 4, 65536), (65536, 3, 24576), (1 << 20, 8, 16384)])
+def test_keyed_owner_partitioned_kernel(lh, oracle, chunk, spt, flush):
     """The owner-partitioned write-combining keyed kernel (bin -> per-owner buffers -> per-(owner, writer) queues ->
     shared-memory windows) against the oracle: several chunks (grid barriers, queue parity), signed/edge values,
     skewed ids, out-of-range ids, and a single-id stream that overflows one owner's buffer and queue and must fall
@@ -495,6 +495,7 @@ def test_keyed_owner_partitioned_kernel(lh, oracle, chunk, spt):
         e.tune("keyed_mode", 2)
         e.tune("wc_spt", spt)
         e.tune("kp_chunk", chunk)
+        e.tune("wc_flush", flush)       # 65536 samples between flushes overflows the owner buffers: the exact route must absorb it
         for stream, idkind in ((lh.STREAM_S, 0), (lh.STREAM_U, 1), (lh.STREAM_L, 0)):
             vals = oracle.gen_stream(stream, n, SEED ^ 0x31)
             ids = oracle.gen_ids(idkind, n, H, SEED ^ 0x31)

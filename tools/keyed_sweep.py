@@ -16,7 +16,7 @@ eng = lh.Engine(device=0, max_histograms=H, max_counters=1)
 d = eng.alloc(n, "float64")
 ids = eng.alloc(n, "uint16")
 configs = [("vec", 1, 16, 8 << 20, 24576)]
-for spt in ((4,) if quick else (16, 8, 4)):
+for spt in ((4, 3) if quick else (8, 3, 4)):
     for chunk in ((32 << 20,) if quick else (16 << 20, 32 << 20, 64 << 20)):
         for flush in ((16384, 24576, 28672) if spt == 4 else (24576,)):
             configs.append(("wc", 2, spt, chunk, flush))
