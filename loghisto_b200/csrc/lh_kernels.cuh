@@ -768,30 +768,36 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
                         }
                 }
             }
-            // ---- flush every prm.flush_tiles tiles.  A quarter warp (8 lanes x 16 B = one 128-byte line) serves one owner:
-            //      its full lines go to my sub-queue of that owner as coalesced 128-byte stores, the remainder (< 64
-            //      records) moves to the front.  No barrier is needed between tiles that do not flush: appends are atomic.
+            // ---- flush every prm.flush_tiles tiles.  Four lanes (4 x 32 B = one 128-byte line) serve one owner, so the
+            //      8 x 32 = 256 lane groups of the CTA cover all owners in ONE pass: an owner's full lines go to my sub-queue
+            //      of that owner as coalesced 128-byte stores, the remainder (< 64 records) moves to the front.  No barrier
+            //      is needed between tiles that do not flush: appends are atomic.
             if (++since_flush == prm.flush_tiles) {
                 since_flush = 0;
                 __syncthreads();
-                const uint32_t sub = (tid & 31) >> 3, k8 = tid & 7;
-                for (uint32_t base = (tid >> 5) * 4; base < P; base += (WC_THREADS / 32) * 4) {   // warp-uniform trip count
+                constexpr uint32_t GROUPS_PER_WARP = 8;
+                const uint32_t sub = (tid & 31) >> 2, k4 = (tid & 3) * 2;
+                for (uint32_t base = (tid >> 5) * GROUPS_PER_WARP; base < P; base += (WC_THREADS / 32) * GROUPS_PER_WARP) {   // warp-uniform trip count
                     const uint32_t o = base + sub;
                     const bool act = o < P;
                     unsigned int n = 0, nfull = 0, off0 = 0;
-                    uint4 keep = make_uint4(0, 0, 0, 0);
+                    uint4 keep0 = make_uint4(0, 0, 0, 0), keep1 = keep0;
                     uint4 *src = reinterpret_cast<uint4 *>(s_buf + (act ? o : 0) * S::STRIDE);
                     if (act) {
                         n = min(s_fill[o], (unsigned int)S::CAP);
                         nfull = n / WC_LINE;
                         off0 = s_off[o];
                         unsigned short *qbase = qset + ((size_t)o * P + p) * cap;
-                        keep = src[nfull * 8 + k8];                                        // the line that holds the remainder
+                        keep0 = src[nfull * 8 + k4];                                       // the line that holds the remainder
+                        keep1 = src[nfull * 8 + k4 + 1];
                         for (unsigned int l = 0; l < nfull; l++) {
                             if (off0 + WC_LINE <= cap) {
-                                reinterpret_cast<uint4 *>(qbase + off0)[k8] = src[l * 8 + k8];
+                                uint4 *dst = reinterpret_cast<uint4 *>(qbase + off0);
+                                const uint4 a0 = src[l * 8 + k4], a1 = src[l * 8 + k4 + 1];
+                                dst[k4] = a0;
+                                dst[k4 + 1] = a1;
                                 off0 += WC_LINE;
-                            } else if (k8 == 0) {                                          // sub-queue full: these records go the L2 route
+                            } else if (k4 == 0) {                                          // sub-queue full: these records go the L2 route
                                 const unsigned short *r = s_buf + o * S::STRIDE + l * WC_LINE;
                                 for (unsigned int k = 0; k < (unsigned int)WC_LINE; k++) wc_spill(r[k], o, P, pc, prm.o);
                             }
@@ -799,8 +805,8 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
                     }
                     __syncwarp();
                     if (act) {
-                        if (nfull) src[k8] = keep;
-                        if (k8 == 0) { s_off[o] = off0; s_fill[o] = n - nfull * WC_LINE; }
+                        if (nfull) { src[k4] = keep0; src[k4 + 1] = keep1; }
+                        if (k4 == 0) { s_off[o] = off0; s_fill[o] = n - nfull * WC_LINE; }
                     }
                 }
                 __syncthreads();

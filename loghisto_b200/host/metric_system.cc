@@ -7,6 +7,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include <cstring>
 #include <limits>
 #include <stdexcept>
@@ -41,6 +43,37 @@ void check(lh_ctx *ctx, lh_status st, const char *what) {
         throw std::runtime_error(msg);
     }
 }
+
+// ---- asymmetric owner / reaper exclusion ------------------------------------------------------------------
+// A staging shard that belongs to ONE thread is entered by that thread with plain stores (no locked instruction on
+// the per-call path: on x86 a locked RMW waits for every store in flight, i.e. for the cache misses of the pinned
+// buffer it just wrote).  The reaper, which needs the shard once per interval, raises `reaper_wants`, forces a full
+// barrier on every thread of the process with membarrier(PRIVATE_EXPEDITED), and then waits for `owner_busy` to
+// drop: the Dekker handshake with the expensive half moved to the side that runs once per interval.  Where the
+// syscall is unavailable (or LOGHISTO_B200_SHARD_LOCK=1) every shard falls back to its spinlock.
+constexpr int kMembarrierQuery = 0, kMembarrierPrivateExpedited = 1 << 3, kMembarrierRegisterPrivateExpedited = 1 << 4;
+bool asym_available() {
+    if (const char *e = getenv("LOGHISTO_B200_SHARD_LOCK")) if (e[0] == '1') return false;   // read per system: A/B runs in one process
+    static const bool ok = [] {
+#ifdef __NR_membarrier
+        const long q = syscall(__NR_membarrier, kMembarrierQuery, 0);
+        if (q < 0 || !(q & kMembarrierPrivateExpedited)) return false;
+        return syscall(__NR_membarrier, kMembarrierRegisterPrivateExpedited, 0) == 0;
+#else
+        return false;
+#endif
+    }();
+    return ok;
+}
+void asym_barrier() {
+#ifdef __NR_membarrier
+    syscall(__NR_membarrier, kMembarrierPrivateExpedited, 0);
+#endif
+}
+
+// live systems by id: a thread that ends (or moves to another system) hands its exclusive shard back through this
+std::mutex g_reg_mu;
+std::unordered_map<uint64_t, MetricSystem *> g_systems;
 
 size_t next_thread_slot() {
     static std::atomic<size_t> next{0};
@@ -81,13 +114,19 @@ struct NameCache {
     size_t arena_left = 0;
     char *arena_next = nullptr;
     size_t count = 0;
-    bool find(uint64_t h, const char *p, size_t n, uint32_t *id) const {
+    const Entry *last = nullptr;                 // most recently found entry: a thread that repeats one name skips the hash
+    bool find_last(const char *p, size_t n, uint32_t *id) const {
+        const Entry *x = last;
+        if (x && x->len == n && memcmp(x->name, p, n) == 0) { *id = x->id_plus1 - 1; return true; }
+        return false;
+    }
+    bool find(uint64_t h, const char *p, size_t n, uint32_t *id) {
         if (e.empty()) return false;
         const size_t mask = e.size() - 1;
         for (size_t i = h & mask;; i = (i + 1) & mask) {
             const Entry &x = e[i];
             if (!x.id_plus1) return false;
-            if (x.hash == h && x.len == n && memcmp(x.name, p, n) == 0) { *id = x.id_plus1 - 1; return true; }
+            if (x.hash == h && x.len == n && memcmp(x.name, p, n) == 0) { *id = x.id_plus1 - 1; last = &x; return true; }
         }
     }
     void insert_raw(const Entry &en) {
@@ -98,6 +137,7 @@ struct NameCache {
     }
     void put(uint64_t h, const char *p, size_t n, uint32_t id) {
         if (e.empty()) e.assign(256, Entry{0, nullptr, 0, 0});
+        last = nullptr;
         if ((count + 1) * 2 > e.size()) {        // grow and rehash
             std::vector<Entry> old(e.size() * 2, Entry{0, nullptr, 0, 0});
             old.swap(e);
@@ -114,20 +154,32 @@ struct NameCache {
         arena_next += n; arena_left -= n;
         count++;
     }
-    void reset() { e.clear(); arena.clear(); arena_left = 0; arena_next = nullptr; count = 0; }
+    void reset() { last = nullptr; e.clear(); arena.clear(); arena_left = 0; arena_next = nullptr; count = 0; }
 };
 
 // Everything a thread needs on the per-call path, reached through ONE thread-local pointer (a plain pointer has no
 // initialisation guard; the object behind it is created on the thread's first call and freed when the thread ends).
 struct ThreadState {
     uint64_t system_id = 0;                      // which MetricSystem `shard` and the caches belong to
-    void *shard = nullptr;                       // MetricSystem::Shard * of this thread (round-robin over the shards)
+    void *shard = nullptr;                       // MetricSystem::Shard * of this thread
+    bool exclusive = false;                      // the shard is this thread's alone (handed back when the thread ends)
     size_t slot = 0;                             // process-wide thread number
     NameCache h, c;
 };
+void release_thread_shard(ThreadState *ts) {
+    if (!ts->shard || !ts->exclusive) return;
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    auto it = g_systems.find(ts->system_id);
+    if (it != g_systems.end()) it->second->release_shard(ts->shard);
+    ts->shard = nullptr;
+    ts->exclusive = false;
+}
 struct ThreadStateOwner {                        // destroyed at thread exit
     ThreadState *p = nullptr;
-    ~ThreadStateOwner() { delete p; }
+    ~ThreadStateOwner() {
+        if (p) release_thread_shard(p);
+        delete p;
+    }
 };
 thread_local ThreadState *tl_state = nullptr;
 thread_local ThreadStateOwner tl_owner;
@@ -147,6 +199,11 @@ std::atomic<uint64_t> g_system_ids{1};
 // steady state a shard has ONE writer and its spinlock is uncontended (an exchange and a store, ~10 ns); the reaper
 // takes it once per interval to commit whatever is open.
 struct MetricSystem::Shard {
+    // exclusive shards (one owner thread): asymmetric handshake, see asym_available()
+    std::atomic<uint32_t> owner_busy{0};     // written by the owner with plain stores
+    std::atomic<uint32_t> reaper_wants{0};   // raised by a collecting thread
+    bool exclusive = false;
+    // shared shards (more threads than shards, or no membarrier): a spinlock
     std::atomic_flag busy = ATOMIC_FLAG_INIT;
     void lock() { while (busy.test_and_set(std::memory_order_acquire)) { __builtin_ia32_pause(); } }
     void unlock() { busy.clear(std::memory_order_release); }
@@ -164,15 +221,38 @@ struct MetricSystem::Shard {
     uint16_t *c_ids = nullptr;
     std::vector<uint8_t> c_touched;      // [max_counters] Counter(name, x) was called this interval, even with x == 0
     bool c_any_touched = false;
-    uint64_t dropped = 0;                // samples lost to a failed staging call (never silent: dropped_samples())
-    char pad[64];                        // keep neighbouring shards off this one's cache lines
+    std::atomic<uint64_t> dropped{0};    // samples lost to a failed staging call (never silent: dropped_samples())
+    char pad[128];                       // keep neighbouring shards (and the adjacent-line prefetcher) off this one's cache lines
 };
 
 namespace {
-struct ShardGuard {
+struct ShardGuard {                      // the calling thread's OWN shard (or a shared one)
     MetricSystem::Shard &s;
-    explicit ShardGuard(MetricSystem::Shard &sh) : s(sh) { s.lock(); }
-    ~ShardGuard() { s.unlock(); }
+    explicit ShardGuard(MetricSystem::Shard &sh) : s(sh) {
+        if (!s.exclusive) { s.lock(); return; }
+        for (;;) {
+            s.owner_busy.store(1, std::memory_order_relaxed);
+            std::atomic_signal_fence(std::memory_order_seq_cst);             // compiler only; the reaper's membarrier supplies the fence
+            if (__builtin_expect(s.reaper_wants.load(std::memory_order_acquire) == 0, 1)) return;
+            s.owner_busy.store(0, std::memory_order_release);                // a collect is flushing this shard (microseconds)
+            while (s.reaper_wants.load(std::memory_order_acquire)) __builtin_ia32_pause();
+        }
+    }
+    ~ShardGuard() {
+        if (s.exclusive) s.owner_busy.store(0, std::memory_order_release);
+        else s.unlock();
+    }
+};
+struct ForeignGuard {                    // another thread's shard, after reaper_wants was raised and asym_barrier() ran
+    MetricSystem::Shard &s;
+    explicit ForeignGuard(MetricSystem::Shard &sh) : s(sh) {
+        if (!s.exclusive) { s.lock(); return; }
+        while (s.owner_busy.load(std::memory_order_acquire)) __builtin_ia32_pause();
+    }
+    ~ForeignGuard() {
+        if (s.exclusive) s.reaper_wants.store(0, std::memory_order_release);
+        else s.unlock();
+    }
 };
 void log_once(std::atomic<bool> &flag, lh_ctx *ctx, lh_status st, const char *what) {
     if (!flag.exchange(true))
@@ -205,17 +285,51 @@ MetricSystem::MetricSystem(std::chrono::nanoseconds interval, bool /*sysStats*/,
     cfg.max_histograms = opt.max_histograms;
     cfg.max_counters = opt.max_counters;
     cfg.staging_bytes = opt_.staging_bytes;
-    cfg.staging_slots = 2 * nshards + 2;   // every shard may hold one histogram and one counter slot (memory is allocated on first use)
+    // exclusive shards for the first `nshards` live threads; a few shared, spin-locked ones for the threads beyond that
+    asym_ = asym_available();
+    const uint32_t nshared = asym_ ? 8u : 0u;
+    cfg.staging_slots = 2 * (nshards + nshared) + 2;   // every shard may hold one histogram and one counter slot (memory is allocated on first use)
     cfg.precision = opt.precision;
     lh_status st = lh_create(&cfg, &ctx_);
     if (st != LH_OK) throw std::runtime_error(std::string("lh_create: ") + lh_strerror(st));
-    for (uint32_t i = 0; i < nshards; i++) {
+    for (uint32_t i = 0; i < nshards + nshared; i++) {
         shards_.emplace_back(new Shard());
         shards_.back()->c_touched.assign(opt.max_counters, 0);
+        if (asym_ && i < nshards) {
+            shards_.back()->exclusive = true;
+            free_exclusive_.push_back(shards_.back().get());
+        } else {
+            shared_.push_back(shards_.back().get());
+        }
     }
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    g_systems[system_id_] = this;
+}
+
+// the calling thread's shard: an exclusive one while any is free, otherwise one of the shared ones (round-robin)
+void *MetricSystem::assign_shard(size_t thread_slot, bool *exclusive) {
+    {
+        std::lock_guard<std::mutex> lk(assign_mu_);
+        if (!free_exclusive_.empty()) {
+            Shard *s = free_exclusive_.back();
+            free_exclusive_.pop_back();
+            *exclusive = true;
+            return s;
+        }
+    }
+    *exclusive = false;
+    return shared_[thread_slot % shared_.size()];
+}
+void MetricSystem::release_shard(void *shard) {
+    std::lock_guard<std::mutex> lk(assign_mu_);
+    free_exclusive_.push_back(static_cast<Shard *>(shard));   // whatever it still holds is committed by the next collect
 }
 
 MetricSystem::~MetricSystem() {
+    {
+        std::lock_guard<std::mutex> lk(g_reg_mu);
+        g_systems.erase(system_id_);
+    }
     try { Stop(); } catch (...) {}
     if (reaper_thread_.joinable()) reaper_thread_.join();
     lh_destroy(ctx_);
@@ -247,12 +361,13 @@ uint16_t MetricSystem::intern(std::shared_mutex &mu, std::unordered_map<std::str
 
 // name -> dense id through the calling thread's cache; false when the name table is full (sample dropped, counted)
 // The calling thread's state for THIS system (a thread that moves to another MetricSystem starts over).
-static inline ThreadState *thread_state(uint64_t system_id, const std::vector<std::unique_ptr<MetricSystem::Shard>> &shards) {
+static inline ThreadState *thread_state(MetricSystem &ms, uint64_t system_id) {
     ThreadState *ts = tl_state;
     if (__builtin_expect(ts == nullptr, 0)) ts = make_thread_state();
     if (__builtin_expect(ts->system_id != system_id, 0)) {
+        release_thread_shard(ts);                // a shard of the system this thread used before
         ts->system_id = system_id;
-        ts->shard = shards[ts->slot % shards.size()].get();
+        ts->shard = ms.assign_shard(ts->slot, &ts->exclusive);
         ts->h.reset();
         ts->c.reset();
     }
@@ -260,7 +375,7 @@ static inline ThreadState *thread_state(uint64_t system_id, const std::vector<st
 }
 
 bool MetricSystem::lookup_histogram(const char *p, size_t n, uint32_t *id) {
-    ThreadState *ts = thread_state(system_id_, shards_);
+    ThreadState *ts = thread_state(*this, system_id_);
     const uint64_t h = hash_bytes(p, n);
     if (ts->h.find(h, p, n, id)) return true;
     bool ok;
@@ -271,7 +386,7 @@ bool MetricSystem::lookup_histogram(const char *p, size_t n, uint32_t *id) {
     return true;
 }
 bool MetricSystem::lookup_counter(const char *p, size_t n, uint32_t *id) {
-    ThreadState *ts = thread_state(system_id_, shards_);
+    ThreadState *ts = thread_state(*this, system_id_);
     const uint64_t h = hash_bytes(p, n);
     if (ts->c.find(h, p, n, id)) return true;
     bool ok;
@@ -288,7 +403,7 @@ void MetricSystem::append_histogram(Shard &s, uint32_t id, double value) noexcep
     ShardGuard g(s);
     if (!s.h_open) {
         lh_status st = lh_staging_acquire(ctx_, &s.hs);
-        if (st != LH_OK) { s.dropped++; log_once(g_logged_staging, ctx_, st, "lh_staging_acquire"); return; }
+        if (st != LH_OK) { s.dropped.fetch_add(1, std::memory_order_relaxed); log_once(g_logged_staging, ctx_, st, "lh_staging_acquire"); return; }
         s.h_cap = ((size_t)s.hs.bytes / 10) & ~(size_t)15;
         s.h_vals = reinterpret_cast<double *>(s.hs.host);
         s.h_ids = reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(s.hs.host) + s.h_cap * 8);
@@ -300,14 +415,14 @@ void MetricSystem::append_histogram(Shard &s, uint32_t id, double value) noexcep
     if (++s.h_n == s.h_cap) commit_histograms(s);
 }
 void MetricSystem::histogram_id(uint32_t id, double value) noexcept {
-    append_histogram(*static_cast<Shard *>(thread_state(system_id_, shards_)->shard), id, value);
+    append_histogram(*static_cast<Shard *>(thread_state(*this, system_id_)->shard), id, value);
 }
 
 void MetricSystem::commit_histograms(Shard &s) noexcept {
     if (!s.h_open) return;
     lh_status st = lh_staging_commit_keyed_f64_u16(ctx_, &s.hs, s.h_n, s.h_cap * 8);
     if (st != LH_OK) {
-        s.dropped += s.h_n;
+        s.dropped.fetch_add(s.h_n, std::memory_order_relaxed);
         log_once(g_logged_staging, ctx_, st, "lh_staging_commit_keyed_f64_u16");
         lh_staging_abandon(ctx_, &s.hs);      // harmless if the commit already recycled the slot
     }
@@ -319,7 +434,7 @@ void MetricSystem::commit_counters(Shard &s) noexcept {
     if (!s.c_open) return;
     lh_status st = lh_staging_commit_counter_u16(ctx_, &s.cs, s.c_n, s.c_cap * 8);
     if (st != LH_OK) {
-        s.dropped += s.c_n;
+        s.dropped.fetch_add(s.c_n, std::memory_order_relaxed);
         log_once(g_logged_staging, ctx_, st, "lh_staging_commit_counter_u16");
         lh_staging_abandon(ctx_, &s.cs);
     }
@@ -331,9 +446,9 @@ void MetricSystem::Histogram(const std::string &name, double value) noexcept { H
 void MetricSystem::Histogram(const char *name, size_t len, double value) noexcept {
     // steady state: one thread-local pointer, one hash of the name's bytes, one probe of this thread's name cache, one
     // uncontended spinlock, two stores into pinned memory
-    ThreadState *ts = thread_state(system_id_, shards_);
+    ThreadState *ts = thread_state(*this, system_id_);
     uint32_t id;
-    if (__builtin_expect(!ts->h.find(hash_bytes(name, len), name, len, &id), 0)) {
+    if (!ts->h.find_last(name, len, &id) && __builtin_expect(!ts->h.find(hash_bytes(name, len), name, len, &id), 0)) {
         if (!lookup_histogram(name, len, &id)) return;              // name table full: dropped and counted
     }
     append_histogram(*static_cast<Shard *>(ts->shard), id, value);
@@ -342,14 +457,14 @@ void MetricSystem::Histogram(const char *name, size_t len, double value) noexcep
 void MetricSystem::Counter(const std::string &name, uint64_t amount) noexcept {
     uint32_t id;
     if (!lookup_counter(name.data(), name.size(), &id)) return;
-    Shard &s = *static_cast<Shard *>(thread_state(system_id_, shards_)->shard);
+    Shard &s = *static_cast<Shard *>(thread_state(*this, system_id_)->shard);
     ShardGuard g(s);
     s.c_touched[id] = 1;                    // Counter(name, 0) still makes the name appear in Rates (metrics.go:430-433)
     s.c_any_touched = true;
     if (amount == 0) return;                // nothing to add on the device
     if (!s.c_open) {
         lh_status st = lh_staging_acquire(ctx_, &s.cs);
-        if (st != LH_OK) { s.dropped++; log_once(g_logged_staging, ctx_, st, "lh_staging_acquire"); return; }
+        if (st != LH_OK) { s.dropped.fetch_add(1, std::memory_order_relaxed); log_once(g_logged_staging, ctx_, st, "lh_staging_acquire"); return; }
         s.c_cap = ((size_t)s.cs.bytes / 10) & ~(size_t)15;
         s.c_amounts = reinterpret_cast<uint64_t *>(s.cs.host);
         s.c_ids = reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(s.cs.host) + s.c_cap * 8);
@@ -381,7 +496,7 @@ void MetricSystem::DeregisterGaugeFunc(const std::string &name) {
 
 // commit whatever the shard holds and hand over (and clear) its touched-counter marks
 void MetricSystem::flush_shard(Shard &s, std::vector<uint8_t> *touched) {
-    ShardGuard g(s);
+    ForeignGuard g(s);
     commit_histograms(s);
     commit_counters(s);
     if (s.c_any_touched) {
@@ -395,7 +510,7 @@ uint64_t MetricSystem::dropped_samples() {
     lh_stats st{};
     lh_get_stats(ctx_, &st);
     uint64_t d = st.dropped + dropped_over_limit_.load();
-    for (auto &s : shards_) { ShardGuard g(*s); d += s->dropped; }
+    for (auto &s : shards_) d += s->dropped.load(std::memory_order_relaxed);
     return d;
 }
 
@@ -414,6 +529,11 @@ std::shared_ptr<RawMetricSet> MetricSystem::collectRawMetrics() {
     }
 
     std::vector<uint8_t> touched(opt_.max_counters, 0);
+    // exclusive shards: announce, one process-wide barrier, then every shard is entered as soon as its owner is out
+    if (asym_) {
+        for (auto &s : shards_) if (s->exclusive) s->reaper_wants.store(1, std::memory_order_seq_cst);
+        asym_barrier();
+    }
     for (auto &s : shards_) flush_shard(*s, &touched);
     check(ctx_, lh_snapshot_begin(ctx_), "lh_snapshot_begin");   // the cache swaps of :425-428 and :460-463
 

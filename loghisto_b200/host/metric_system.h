@@ -132,6 +132,8 @@ class MetricSystem {
     void Counter(const std::string &name, uint64_t amount) noexcept;      // :251
     void Histogram(const std::string &name, double value) noexcept;       // :273
     void Histogram(const char *name, size_t len, double value) noexcept;  // same, without building a std::string
+    void *assign_shard(size_t thread_slot, bool *exclusive);             // internal: a thread's staging shard (exclusive while any is free)
+    void release_shard(void *shard);                                      // internal: a finished thread hands its exclusive shard back
     void histogram_id(uint32_t id, double value) noexcept;                // body of Histogram once the name is interned
     void RegisterGaugeFunc(const std::string &name, std::function<double()> f);   // :299
     void DeregisterGaugeFunc(const std::string &name);                    // :306
@@ -172,6 +174,9 @@ class MetricSystem {
     std::vector<std::string> histo_names_, counter_names_;
 
     std::vector<std::unique_ptr<Shard>> shards_;
+    std::mutex assign_mu_;
+    std::vector<Shard *> free_exclusive_, shared_;
+    bool asym_ = false;             // exclusive shards use the membarrier handshake instead of a lock
 
     std::mutex counter_store_mu_;
     std::map<std::string, uint64_t> counter_store_;            // metrics.go:111-113

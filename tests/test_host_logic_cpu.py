@@ -120,3 +120,42 @@ def test_per_call_api_small(MS):
         for k, c in raw["Histograms"].get(names[h], {}).items():
             got[k & 0xFFFF] = c
         assert (got == want[h]).all(), h
+
+
+@pytest.mark.parametrize("shard_lock", ["0", "1"])
+def test_collects_race_with_per_call_ingest(MS, monkeypatch, shard_lock):
+    """12 threads call Histogram() while the main thread collects in a loop: with 4 exclusive shards (membarrier
+    handshake between owner and collector; shard_lock=1: the spin-locked fallback) plus the shared overflow shards,
+    no sample may be lost or counted twice, and the union of all intervals must be the oracle's histogram."""
+    import threading
+    import numpy as np
+    from oracle import oracle as o
+    monkeypatch.setenv("LOGHISTO_B200_SHARDS", "4")
+    monkeypatch.setenv("LOGHISTO_B200_STAGING_BYTES", "65536")
+    monkeypatch.setenv("LOGHISTO_B200_SHARD_LOCK", shard_lock)
+    H, n = 8, 1_200_000
+    names = ["name%d" % i for i in range(H)]
+    ms = MS(interval_s=3600.0, max_histograms=H)
+    total = np.zeros((H, 65536), dtype=np.uint64)
+
+    def add(raw):
+        for h in range(H):
+            for k, c in raw["Histograms"].get(names[h], {}).items():
+                total[h, k & 0xFFFF] += c
+
+    for rnd in range(2):          # the second round's threads take over the shards the first round's threads handed back
+        t = threading.Thread(target=ms.histogram_stream, args=(names, o.STREAM_U, o.DEFAULT_SEED, rnd * n, n, 12))
+        t.start()
+        collects = 0
+        while t.is_alive():
+            raw, _ = ms.collect_and_process()
+            add(raw)
+            collects += 1
+        t.join()
+        raw, _ = ms.collect_and_process()
+        add(raw)
+        assert collects >= 1
+    want = o.stream_ingest_keyed(o.STREAM_U, 2 * n, H, o.DEFAULT_SEED)
+    assert ms.dropped() == 0
+    assert int(total.sum()) == 2 * n
+    assert (total == want).all()

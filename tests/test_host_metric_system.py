@@ -231,3 +231,42 @@ def test_counter_zero_amount_appears_in_rates(MS):
     assert metrics["quiet_rate"] == 0.0 and metrics["quiet"] == 0.0
     raw, _ = ms.collect_and_process()
     assert raw["Rates"] == {} and raw["Counters"] == {"quiet": 0, "busy": 5}
+
+
+@pytest.mark.parametrize("shard_lock", ["0", "1"])
+def test_collects_race_with_per_call_ingest(MS, monkeypatch, shard_lock):
+    """The same race as tests/test_host_logic_cpu.py, against the real library: 24 threads call Histogram() while the
+    main thread collects in a loop; 8 exclusive shards (membarrier handshake; shard_lock=1: spin-locked fallback) plus
+    the shared overflow shards.  The union of all intervals must be the oracle's histogram, nothing dropped."""
+    import threading
+    import numpy as np
+    from oracle import oracle as o
+    o.build()
+    monkeypatch.setenv("LOGHISTO_B200_SHARDS", "8")
+    monkeypatch.setenv("LOGHISTO_B200_STAGING_BYTES", "262144")
+    monkeypatch.setenv("LOGHISTO_B200_SHARD_LOCK", shard_lock)
+    H, n = 16, 12_000_000
+    names = ["name%d" % i for i in range(H)]
+    ms = MS(interval_s=3600.0, max_histograms=H)
+    total = np.zeros((H, 65536), dtype=np.uint64)
+
+    def add(raw):
+        for h in range(H):
+            for k, c in raw["Histograms"].get(names[h], {}).items():
+                total[h, k & 0xFFFF] += c
+
+    collects = 0
+    for rnd in range(2):
+        t = threading.Thread(target=ms.histogram_stream, args=(names, o.STREAM_U, o.DEFAULT_SEED, rnd * n, n, 24))
+        t.start()
+        while t.is_alive():
+            raw, _ = ms.collect_and_process()
+            add(raw)
+            collects += 1
+        t.join()
+        raw, _ = ms.collect_and_process()
+        add(raw)
+    want = o.stream_ingest_keyed(o.STREAM_U, 2 * n, H, o.DEFAULT_SEED)
+    assert collects >= 2 and ms.dropped() == 0
+    assert int(total.sum()) == 2 * n
+    assert (total == want).all()

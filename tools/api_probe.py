@@ -9,10 +9,13 @@ ladder = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else sort
 slots = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [4 << 20]
 names_list = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [1, 1024]
 print("cpus", ncpu, "cpu.max", open("/sys/fs/cgroup/cpu.max").read().strip() if os.path.exists("/sys/fs/cgroup/cpu.max") else "?", flush=True)
+lock_modes = ["0", "1"] if os.environ.get("PROBE_LOCK_AB") else ["0"]
 for names_n in names_list:
     names = ["histogram%d" % i for i in range(names_n)]
-    for sb in slots:
+    for sb, unl in [(a, b) for a in slots for b in lock_modes]:
         os.environ["LOGHISTO_B200_STAGING_BYTES"] = str(sb)
+        os.environ["LOGHISTO_B200_SHARD_LOCK"] = unl
+        print("  shards: %s" % ("spin-locked (LOGHISTO_B200_SHARD_LOCK=1)" if unl == "1" else "exclusive per thread, membarrier handshake"), flush=True)
         for threads in ladder:
             if threads > ncpu:
                 continue

@@ -6,7 +6,7 @@ timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_r02h.txt 2
 tail -6 gpurun_out/pytest_gpu_r02h.txt
 timeout 400 python tools/keyed_sweep.py 1000000000 1024 quick > gpurun_out/keyed_sweep_r02j.txt 2>&1
 cut -c1-170 gpurun_out/keyed_sweep_r02j.txt
-timeout 500 python tools/api_probe.py 1,16,32,64,128 4194304,262144 1 > gpurun_out/api_probe_r02h.txt 2>&1
+PROBE_LOCK_AB=1 timeout 700 python tools/api_probe.py 1,16,32,64,128 4194304,262144 1 > gpurun_out/api_probe_r02h.txt 2>&1
 cat gpurun_out/api_probe_r02h.txt
 timeout 200 python tools/api_probe.py 32,128 262144 1024 >> gpurun_out/api_probe_r02h.txt 2>&1
 tail -2 gpurun_out/api_probe_r02h.txt
