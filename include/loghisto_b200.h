@@ -99,6 +99,13 @@ LH_API lh_status lh_ingest_keyed_f64_u32(lh_ctx *ctx, const uint32_t *d_ids, con
 /* Timer samples: value = float64(duration.Nanoseconds()), metrics.go:242-246. */
 LH_API lh_status lh_ingest_keyed_i64ns_u16(lh_ctx *ctx, const uint16_t *d_ids, const int64_t *d_nanos,
                                     size_t n, void *stream);
+
+/* A batch of Histogram samples AND a batch of Timer samples (metrics.go:242-246 then :273-295) in one call: above a few
+ * million pairs both are binned by ONE launch of the write-combining kernel, so its fixed costs are paid once per batch
+ * (configs[4]: 50 % Histogram / 25 % Timer ops).  Same semantics as lh_ingest_keyed_f64_u16 followed by
+ * lh_ingest_keyed_i64ns_u16; either count may be 0. */
+LH_API lh_status lh_ingest_keyed_pair_u16(lh_ctx *ctx, const uint16_t *d_ids_f64, const double *d_values, size_t n_f64,
+                                          const uint16_t *d_ids_ns, const int64_t *d_nanos, size_t n_ns, void *stream);
 /* Counter(name, amount), metrics.go:251-269: wrapping uint64 adds. */
 LH_API lh_status lh_counter_add_u16(lh_ctx *ctx, const uint16_t *d_ids, const uint64_t *d_amounts,
                              size_t n, void *stream);

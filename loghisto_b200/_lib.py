@@ -83,6 +83,7 @@ SIGNATURES = {
     "lh_ingest_keyed_f64_u16": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "lh_ingest_keyed_f64_u32": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "lh_ingest_keyed_i64ns_u16": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "lh_ingest_keyed_pair_u16": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp]),
     "lh_counter_add_u16": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "lh_counter_add_u32": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "lh_ingest_f64_host": (_i32, [_vp, _u32, _vp, _sz]),

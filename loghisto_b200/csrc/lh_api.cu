@@ -330,20 +330,24 @@ uint32_t ks_ids_per_pass(const lh_ctx *ctx) { return std::max<uint32_t>(1, (uint
 // cooperative launch.
 constexpr size_t kSmemBudget = 227 * 1024;
 // Processes the first *taken samples (whole tiles only); the caller sends the rest to the scalar kernel.
+// Optional second segment (ids2, vals2, n2): int64 nanosecond samples binned by the SAME launch (ValT = double only).
 template <typename IdT, typename ValT, int SPT>
-lh_status launch_keyed_wc_spt(lh_ctx *ctx, int b, const IdT *ids, const ValT *vals, size_t n4x4, cudaStream_t s, bool *used, size_t *taken) {
+lh_status launch_keyed_wc_spt(lh_ctx *ctx, int b, const IdT *ids, const ValT *vals, size_t n4x4, cudaStream_t s, bool *used, size_t *taken,
+                              const IdT *ids2 = nullptr, const long long *vals2 = nullptr, size_t n2 = 0, size_t *taken2 = nullptr) {
     *used = false;
     *taken = 0;
+    if (taken2) *taken2 = 0;
     const int P = std::min(ctx->sm_count - ctx->k1_reserve_sms, (int)WC_MAX_PARTS);
-    if (P < 8 || n4x4 == 0) return LH_OK;
+    if (P < 8 || n4x4 + n2 == 0) return LH_OK;
     const uint32_t ids_per = (ctx->H + P - 1) / P;
     using S = WcShape<SPT>;
     const size_t hist_bytes = (((size_t)ids_per * ctx->pc.win + 3) & ~(size_t)3) * 4;
     const size_t smem = hist_bytes + 2 * WC_MAX_PARTS * 4 + (size_t)(P + 1) * S::STRIDE * 2;
     if (smem > kSmemBudget || (size_t)ids_per * ctx->pc.win > 65535) return LH_OK;     // records are 16-bit (lid*win + slot)
-    if (ctx->keyed_mode != 2 && n4x4 < ((size_t)1 << 22)) return LH_OK;                // small batches: the L2-atomic kernel
+    if (ctx->keyed_mode != 2 && n4x4 + n2 < ((size_t)1 << 22)) return LH_OK;           // small batches: the L2-atomic kernel
     n4x4 = n4x4 / S::TILE * S::TILE;
-    if (n4x4 == 0) return LH_OK;
+    n2 = n2 / S::TILE * S::TILE;
+    if (n4x4 + n2 == 0) return LH_OK;
     const size_t slice_tiles = std::max<size_t>(1, ((size_t)ctx->kp_chunk + (size_t)P * S::TILE - 1) / ((size_t)P * S::TILE));
     // every (owner, writer) pair has its own sub-queue: 1.25x the expected records per pair per chunk, plus slack
     // (records that do not fit take the exact L2 route, so this only trades speed on heavily skewed ids)
@@ -357,12 +361,16 @@ lh_status launch_keyed_wc_spt(lh_ctx *ctx, int b, const IdT *ids, const ValT *va
         LH_CUDA(ctx, cudaMalloc(&ctx->d_kp_cnt, ((size_t)2 * P * P + 1) * sizeof(unsigned int)));
         ctx->kp_cap = cap; ctx->kp_parts = P;
     }
-    const void *fn = (const void *)k_ingest_keyed_wc<IdT, ValT, SPT>;
+    const void *fn = (const void *)k_ingest_keyed_wc<IdT, ValT, SPT, false>;
+    if constexpr (std::is_same<ValT, double>::value) {
+        if (n2) fn = (const void *)k_ingest_keyed_wc<IdT, double, SPT, true>;
+    }
     LH_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned int *d_barrier = ctx->d_kp_cnt + (size_t)2 * P * P;
     LH_CUDA(ctx, cudaMemsetAsync(d_barrier, 0, sizeof(unsigned int), s));
     WcParams prm{};
     prm.ids = ids; prm.vals = vals; prm.n = n4x4; prm.ids_per = ids_per; prm.cap = (uint32_t)cap;
+    prm.ids2 = ids2; prm.vals2 = vals2; prm.n2 = n2;
     prm.inv_p = (uint32_t)(((uint64_t)1 << 32) / (uint64_t)P) + 1u;
     // samples between two flushes of the shared-memory owner buffers: the flush costs about the same whatever it moves,
     // so as many as the buffers hold at 4 sigma (wc_flush_samples; default 24576)
@@ -375,13 +383,15 @@ lh_status launch_keyed_wc_spt(lh_ctx *ctx, int b, const IdT *ids, const ValT *va
     ctx->stats.kernel_launches++;
     *used = true;
     *taken = n4x4;
+    if (taken2) *taken2 = n2;
     return LH_OK;
 }
 template <typename IdT, typename ValT>
-lh_status launch_keyed_wc(lh_ctx *ctx, int b, const IdT *ids, const ValT *vals, size_t n4x4, cudaStream_t s, bool *used, size_t *taken) {
-    return ctx->wc_spt == 4 ? launch_keyed_wc_spt<IdT, ValT, 4>(ctx, b, ids, vals, n4x4, s, used, taken)
-         : ctx->wc_spt == 3 ? launch_keyed_wc_spt<IdT, ValT, 3>(ctx, b, ids, vals, n4x4, s, used, taken)
-                            : launch_keyed_wc_spt<IdT, ValT, 8>(ctx, b, ids, vals, n4x4, s, used, taken);
+lh_status launch_keyed_wc(lh_ctx *ctx, int b, const IdT *ids, const ValT *vals, size_t n4x4, cudaStream_t s, bool *used, size_t *taken,
+                          const IdT *ids2 = nullptr, const long long *vals2 = nullptr, size_t n2 = 0, size_t *taken2 = nullptr) {
+    return ctx->wc_spt == 4 ? launch_keyed_wc_spt<IdT, ValT, 4>(ctx, b, ids, vals, n4x4, s, used, taken, ids2, vals2, n2, taken2)
+         : ctx->wc_spt == 3 ? launch_keyed_wc_spt<IdT, ValT, 3>(ctx, b, ids, vals, n4x4, s, used, taken, ids2, vals2, n2, taken2)
+                            : launch_keyed_wc_spt<IdT, ValT, 8>(ctx, b, ids, vals, n4x4, s, used, taken, ids2, vals2, n2, taken2);
 }
 
 template <typename IdT, typename ValT>
@@ -470,6 +480,56 @@ lh_status launch_keyed(lh_ctx *ctx, const IdT *d_ids, const ValT *d_vals, size_t
     ctx->timing_valid = true;
     ctx->stats.samples += n;
     return after_write(ctx, b, s);
+}
+
+// Histogram samples (float64) and Timer samples (int64 ns, metrics.go:242-246) of one batch in ONE launch of the
+// write-combining kernel: its fixed costs (zeroing and flushing the owners' windows, the last partly filled chunk) are
+// paid once.  Needs both arrays vector-aligned and the write-combining kernel eligible; otherwise two keyed ingests.
+template <typename IdT>
+lh_status launch_keyed_pair(lh_ctx *ctx, const IdT *ids_f, const double *vals_f, size_t n_f, const IdT *ids_ns, const long long *vals_ns,
+                            size_t n_ns, cudaStream_t s) {
+    auto aligned = [](const void *v, const void *i) { return (((uintptr_t)v & 31u) == 0) && (((uintptr_t)i & (4 * sizeof(IdT) - 1)) == 0); };
+    // few histograms: the shared-memory privatised kernel of launch_keyed() is the better one, per array
+    const uint32_t small_passes = (ctx->H + ks_ids_per_pass(ctx) - 1) / ks_ids_per_pass(ctx);
+    const bool small = small_passes <= 4 && ctx->keyed_mode == 0;
+    const bool fuse = n_f && n_ns && ctx->keyed_mode != 1 && !small && aligned(vals_f, ids_f) && aligned(vals_ns, ids_ns);
+    if (fuse) {
+        const int b = ctx->active;
+        lh_status st = before_write(ctx, b, s);
+        if (st != LH_OK) return st;
+        next_timing_slot(ctx);
+        LH_CUDA(ctx, cudaEventRecord(ctx->ev_t0, s));
+        bool used = false;
+        size_t took_f = 0, took_ns = 0;
+        st = launch_keyed_wc<IdT, double>(ctx, b, ids_f, vals_f, n_f, s, &used, &took_f, ids_ns, vals_ns, n_ns, &took_ns);
+        if (st != LH_OK) return st;
+        if (used) {
+            constexpr int T = 256;
+            const KeyedOut ko = keyed_out(ctx, b);
+            ctx->keyed_kernel = "k_ingest_keyed_wc";
+            if (took_f < n_f) {          // the ragged ends go through the scalar kernel
+                k_ingest_keyed<IdT, double, T><<<grid_1d(ctx, n_f - took_f, T, 1, ctx->keyed_blocks_per_sm), T, 0, s>>>(
+                    ids_f + took_f, vals_f + took_f, n_f - took_f, ko, ctx->pc);
+                ctx->stats.kernel_launches++;
+            }
+            if (took_ns < n_ns) {
+                k_ingest_keyed<IdT, long long, T><<<grid_1d(ctx, n_ns - took_ns, T, 1, ctx->keyed_blocks_per_sm), T, 0, s>>>(
+                    ids_ns + took_ns, vals_ns + took_ns, n_ns - took_ns, ko, ctx->pc);
+                ctx->stats.kernel_launches++;
+            }
+            LH_CUDA(ctx, cudaGetLastError());
+            LH_CUDA(ctx, cudaEventRecord(ctx->ev_t1, s));
+            ctx->timing_valid = true;
+            ctx->stats.samples += n_f + n_ns;
+            return after_write(ctx, b, s);
+        }
+        // not eligible after all (few histograms, small batch): the events recorded above are simply overwritten below
+        st = after_write(ctx, b, s);
+        if (st != LH_OK) return st;
+    }
+    lh_status st = n_f ? launch_keyed<IdT, double>(ctx, ids_f, vals_f, n_f, s) : LH_OK;
+    if (st != LH_OK) return st;
+    return n_ns ? launch_keyed<IdT, long long>(ctx, ids_ns, vals_ns, n_ns, s) : LH_OK;
 }
 
 template <typename IdT>
@@ -843,6 +903,15 @@ extern "C" lh_status lh_ingest_keyed_i64ns_u16(lh_ctx *ctx, const uint16_t *d_id
     LH_ENTER(ctx);
     if (n && (!d_ids || !d_nanos)) return fail(ctx, LH_ERR_INVALID, "NULL input");
     return launch_keyed<unsigned short, long long>(ctx, d_ids, reinterpret_cast<const long long *>(d_nanos), n, pick_stream(ctx, stream));
+}
+extern "C" lh_status lh_ingest_keyed_pair_u16(lh_ctx *ctx, const uint16_t *d_ids_f64, const double *d_values, size_t n_f64,
+                                              const uint16_t *d_ids_ns, const int64_t *d_nanos, size_t n_ns, void *stream) {
+    LH_ENTER(ctx);
+    if ((n_f64 && (!d_ids_f64 || !d_values)) || (n_ns && (!d_ids_ns || !d_nanos))) return fail(ctx, LH_ERR_INVALID, "NULL input");
+    if (((uintptr_t)d_values & 7u) || ((uintptr_t)d_nanos & 7u) || ((uintptr_t)d_ids_f64 & 1u) || ((uintptr_t)d_ids_ns & 1u))
+        return fail(ctx, LH_ERR_INVALID, "ids / values are not naturally aligned");
+    return launch_keyed_pair<unsigned short>(ctx, d_ids_f64, d_values, n_f64, d_ids_ns, reinterpret_cast<const long long *>(d_nanos), n_ns,
+                                             pick_stream(ctx, stream));
 }
 extern "C" lh_status lh_counter_add_u16(lh_ctx *ctx, const uint16_t *d_ids, const uint64_t *d_amounts, size_t n, void *stream) {
     LH_ENTER(ctx);

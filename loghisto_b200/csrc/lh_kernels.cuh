@@ -26,6 +26,7 @@
 // arrays raises them; the snapshot kernels (reduce, export, clear, all-reduce) scan only what they cover.
 #pragma once
 #include "../../include/loghisto_b200.h"
+#include <type_traits>
 #include "lh_device.cuh"
 
 namespace lh {
@@ -634,6 +635,9 @@ struct WcParams {
     const void *ids;                 // IdT[n], 4*sizeof(IdT)-aligned
     const void *vals;                // ValT[n], 32-byte aligned
     size_t n;                        // multiple of the tile size (the host sends the ragged tail to k_ingest_keyed)
+    const void *ids2;                // optional second segment of the same launch (ValT = double only): int64 nanosecond
+    const void *vals2;               //   values (TimerToken.Stop(), metrics.go:242-246), converted with (double) like Go's
+    size_t n2;                       //   float64(duration.Nanoseconds()); multiple of the tile size, 0 = none
     uint32_t ids_per;                // ceil(H / P)
     uint32_t cap;                    // records per (owner, writer) sub-queue per parity, multiple of WC_LINE
     uint32_t slice_tiles;            // tiles per CTA per chunk
@@ -666,9 +670,10 @@ __device__ __forceinline__ void wc_spill(uint32_t rec, uint32_t owner, uint32_t 
     add_bucket_global(o.buckets + (size_t)id * 65536u, o.flags + id, slot, 1ull, pc.win);
 }
 
-template <typename IdT, typename ValT, int SPT>
+template <typename IdT, typename ValT, int SPT, bool PAIR = false>      // PAIR: a second, int64 segment follows the float64 one
 __global__ void __launch_bounds__(WcShape<SPT>::THREADS, 1)
 k_ingest_keyed_wc(WcParams prm, Prec pc) {
+    static_assert(!PAIR || std::is_same<ValT, double>::value, "the int64 segment rides on the float64 instantiation");
     using S = WcShape<SPT>;
     constexpr int WC_THREADS = S::THREADS;
     constexpr int GROUPS = S::PER / 4;
@@ -694,7 +699,8 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
     asm volatile("mov.b32 %0, 0x3F800000;" : "=r"(one_bits));
     __syncthreads();
 
-    const size_t tiles_total = prm.n / S::TILE;                  // the host passes whole tiles only
+    const size_t tiles_seg0 = prm.n / S::TILE;                   // the host passes whole tiles only
+    const size_t tiles_total = tiles_seg0 + (PAIR ? prm.n2 / S::TILE : 0);    // tiles [tiles_seg0, tiles_total) are the int64 segment
     const size_t chunk_tiles = (size_t)prm.slice_tiles * P;
     const size_t nchunks = (tiles_total + chunk_tiles - 1) / chunk_tiles;
     const IdT *ids = reinterpret_cast<const IdT *>(prm.ids);
@@ -723,15 +729,18 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
         const bool last_chunk = c + 1 == nchunks;
         // ---------------- phase A: bin my slice of chunk c (I am writer p)
         const size_t tile0 = c * chunk_tiles + (size_t)p * prm.slice_tiles;
-        const uint32_t ntile = tile0 >= tiles_total ? 0u : (uint32_t)min((size_t)prm.slice_tiles, tiles_total - tile0);   // uniform per CTA
-        if (ntile) {
-            vptr = reinterpret_cast<const char *>(prm.vals) + (tile0 * S::TILE + (size_t)tid * 4) * 8;
-            iptr = ids + tile0 * S::TILE + (size_t)tid * 4;
-            load_tile(vptr, iptr, cur, cur_id);
-        }
+        const uint32_t ntile_all = tile0 >= tiles_total ? 0u : (uint32_t)min((size_t)prm.slice_tiles, tiles_total - tile0);   // uniform per CTA
         // one tile: bin the 4-sample groups held in (raw, idp), then flush when due.  Two register sets alternate (A is
         // being binned while B's loads are in flight and vice versa), so no register copies between tiles.
-        auto bin_tile = [&](unsigned long long (&raw)[GROUPS][4], IdPack<IdT> (&idp)[GROUPS]) {
+        auto bin_tile = [&](unsigned long long (&raw)[GROUPS][4], IdPack<IdT> (&idp)[GROUPS], const bool as_i64) {
+            if constexpr (PAIR) {
+                if (as_i64) {                    // tile of the int64 segment (warp-uniform): from here on the bits are a float64
+#pragma unroll
+                    for (int g = 0; g < GROUPS; g++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) raw[g][j] = (unsigned long long)__double_as_longlong(__ll2double_rn((long long)raw[g][j]));
+                }
+            }
 #pragma unroll
             for (int g = 0; g < GROUPS; g++) {
                 double v[4];
@@ -812,16 +821,28 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
                 __syncthreads();
             }
         };
-        for (uint32_t t = 0; t < ntile; t += 2) {
-            vptr += (size_t)S::TILE * 8;
-            iptr += S::TILE;
-            if (t + 1 < ntile) load_tile(vptr, iptr, nxt, nxt_id);
-            bin_tile(cur, cur_id);
-            if (t + 1 >= ntile) break;
-            vptr += (size_t)S::TILE * 8;
-            iptr += S::TILE;
-            if (t + 2 < ntile) load_tile(vptr, iptr, cur, cur_id);
-            bin_tile(nxt, nxt_id);
+        // the slice may straddle the two segments: part 0 = its float64 tiles, part 1 = its int64 tiles
+        for (int part = 0; part < (PAIR ? 2 : 1); part++) {
+            const size_t lo = part == 0 ? tile0 : max(tile0, tiles_seg0);
+            const size_t hi = part == 0 ? min(tile0 + ntile_all, tiles_seg0) : tile0 + ntile_all;
+            if (hi <= lo) continue;
+            const uint32_t ntile = (uint32_t)(hi - lo);
+            const bool as_i64 = part == 1;
+            const size_t first = (part == 0 ? lo : lo - tiles_seg0) * S::TILE + (size_t)tid * 4;     // sample index inside the segment
+            vptr = reinterpret_cast<const char *>(part == 0 ? prm.vals : prm.vals2) + first * 8;
+            iptr = (part == 0 ? ids : reinterpret_cast<const IdT *>(prm.ids2)) + first;
+            load_tile(vptr, iptr, cur, cur_id);
+            for (uint32_t t = 0; t < ntile; t += 2) {
+                vptr += (size_t)S::TILE * 8;
+                iptr += S::TILE;
+                if (t + 1 < ntile) load_tile(vptr, iptr, nxt, nxt_id);
+                bin_tile(cur, cur_id, as_i64);
+                if (t + 1 >= ntile) break;
+                vptr += (size_t)S::TILE * 8;
+                iptr += S::TILE;
+                if (t + 2 < ntile) load_tile(vptr, iptr, cur, cur_id);
+                bin_tile(nxt, nxt_id, as_i64);
+            }
         }
         __syncthreads();    // every append of this chunk's tiles is in the buffers
         {   // the samples set aside: exact path, all threads at once

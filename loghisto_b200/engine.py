@@ -263,6 +263,11 @@ class Engine:
     def ingest_keyed_i64ns_u16(self, d_ids, d_nanos, n: int, stream=None):
         self._check(self.lib.lh_ingest_keyed_i64ns_u16(self.h, _ptr(d_ids), _ptr(d_nanos), n, _stream(stream)))
 
+    def ingest_keyed_pair_u16(self, d_ids_f64, d_values, n_f64: int, d_ids_ns, d_nanos, n_ns: int, stream=None):
+        """Histogram samples and Timer samples of one batch in one call (one launch of the write-combining kernel)."""
+        self._check(self.lib.lh_ingest_keyed_pair_u16(self.h, _ptr(d_ids_f64), _ptr(d_values), n_f64, _ptr(d_ids_ns), _ptr(d_nanos), n_ns,
+                                                      _stream(stream)))
+
     def counter_add_u16(self, d_ids, d_amounts, n: int, stream=None):
         self._check(self.lib.lh_counter_add_u16(self.h, _ptr(d_ids), _ptr(d_amounts), n, _stream(stream)))
 

@@ -520,6 +520,23 @@ def test_keyed_owner_partitioned_kernel(lh, oracle, chunk, spt, flush):
         e.ingest_keyed_i64ns_u16(d_i, d_n, n)
         red, _ = e.snapshot(PS)
         assert (red.counts == want.sum(axis=1)).all()
+        # Histogram samples and Timer samples of one batch in ONE launch (lh_ingest_keyed_pair_u16): the chunk slices
+        # straddle the float64 / int64 boundary; lengths chosen so that both segments leave ragged ends
+        nf, nn = n - 12_345, n - 777
+        vals = oracle.gen_stream(lh.STREAM_S, nf, SEED ^ 9)
+        ids_f = oracle.gen_ids(0, nf, H, SEED ^ 9)
+        want = oracle.ingest_keyed(ids_f, vals, H) + oracle.ingest_keyed_i64(ids[:nn], ns[:nn], H)
+        d_vf, d_if = e.upload(vals), e.upload(ids_f.astype(np.uint16))
+        e.ingest_keyed_pair_u16(d_if, d_vf, nf, d_i, d_n, nn)
+        assert e.keyed_kernel_name() == "k_ingest_keyed_wc"
+        red, sp = e.snapshot(PS)
+        assert (red.counts == want.sum(axis=1)).all()
+        for h in (0, 3, 146, 147, 640, 1023):
+            assert (dense_from_sparse(sp, h) == want[h]).all(), h
+        e.ingest_keyed_pair_u16(d_if, d_vf, nf, d_i, d_n, 0)          # either side may be empty
+        e.ingest_keyed_pair_u16(d_if, d_vf, 0, d_i, d_n, nn)
+        red2, sp2 = e.snapshot(PS)
+        assert (sp2.counts == sp.counts).all() and (sp2.keys == sp.keys).all()
         # one id only: its owner's queue overflows, the surplus takes the L2 route; ids >= H are dropped
         vals = oracle.gen_stream(lh.STREAM_U, n, SEED ^ 5)
         ids = np.full(n, 777, dtype=np.uint32)

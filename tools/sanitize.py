@@ -24,6 +24,7 @@ with lh.Engine(device=0, max_histograms=64, max_counters=64) as e:
     for spt in (4, 3, 8):
         e.tune("wc_spt", spt)
         e.ingest_keyed_f64_u16(ids, d, n); total += n
+    e.ingest_keyed_pair_u16(ids, d, n, ids, ns, n); total += 2 * n   # float64 + int64 segments in one launch
     e.tune("keyed_mode", 0)
     e.counter_add_u16(ids, amt, n)                      # vector + scalar counter kernels
     e.counter_add_u16(ids.offset(1), amt.offset(1), n - 1)
