@@ -108,7 +108,21 @@ struct NameCache {
     // open addressing, linear probing, load factor <= 1/2: a name that was interned once is found without ever going
     // back to the shared table (a direct-mapped cache thrashes as soon as two hot names collide).  Entries are 24
     // bytes; the names' bytes live in an append-only arena owned by the cache.
-    struct Entry { uint64_t hash; const char *name; uint32_t len; uint32_t id_plus1; };   // id_plus1 == 0: empty
+    struct Entry {                               // id_plus1 == 0: empty
+        uint64_t hash; const char *name; uint32_t len; uint32_t id_plus1;
+        char head[16];                           // the first 16 bytes of the name, zero padded: short names never touch the arena
+        bool matches(uint64_t h, const char *p, size_t n) const {
+            if (hash != h || len != n) return false;
+            if (n <= 16) {
+                uint64_t a[2] = {0, 0};
+                memcpy(a, p, n);
+                uint64_t b[2];
+                memcpy(b, head, 16);
+                return a[0] == b[0] && a[1] == b[1];
+            }
+            return memcmp(name, p, n) == 0;
+        }
+    };
     std::vector<Entry> e;
     std::vector<std::unique_ptr<char[]>> arena;
     size_t arena_left = 0;
@@ -126,7 +140,7 @@ struct NameCache {
         for (size_t i = h & mask;; i = (i + 1) & mask) {
             const Entry &x = e[i];
             if (!x.id_plus1) return false;
-            if (x.hash == h && x.len == n && memcmp(x.name, p, n) == 0) { *id = x.id_plus1 - 1; last = &x; return true; }
+            if (x.matches(h, p, n)) { *id = x.id_plus1 - 1; last = &x; return true; }
         }
     }
     void insert_raw(const Entry &en) {
@@ -136,10 +150,10 @@ struct NameCache {
         e[i] = en;
     }
     void put(uint64_t h, const char *p, size_t n, uint32_t id) {
-        if (e.empty()) e.assign(256, Entry{0, nullptr, 0, 0});
+        if (e.empty()) e.assign(256, Entry{});
         last = nullptr;
         if ((count + 1) * 2 > e.size()) {        // grow and rehash
-            std::vector<Entry> old(e.size() * 2, Entry{0, nullptr, 0, 0});
+            std::vector<Entry> old(e.size() * 2, Entry{});
             old.swap(e);
             for (const Entry &x : old) if (x.id_plus1) insert_raw(x);
         }
@@ -150,7 +164,10 @@ struct NameCache {
             arena_left = block;
         }
         memcpy(arena_next, p, n);
-        insert_raw(Entry{h, arena_next, (uint32_t)n, id + 1});
+        Entry en{};
+        en.hash = h; en.name = arena_next; en.len = (uint32_t)n; en.id_plus1 = id + 1;
+        memcpy(en.head, p, std::min<size_t>(n, 16));
+        insert_raw(en);
         arena_next += n; arena_left -= n;
         count++;
     }
