@@ -1547,6 +1547,7 @@ k_peer_allreduce(PeerParams p) {
                 p.out_counters[i] = sum;
             }
         }
+        if (p.two_shot) __threadfence_system();              // my pushes are performed before this CTA checks out
     }
     // 4. depart: the last CTA of this rank tells every peer it has finished reading them and that the sums it pushed
     //    are visible (every CTA fences at system scope before it checks out), then waits for the same from every peer
