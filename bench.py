@@ -154,9 +154,23 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------- CPU arm
+def cpu_quota_cores():
+    """CPU time this container may use, in cores (cgroup v2 cpu.max; the pool's boxes show 128 CPUs under a 16-core
+    quota), or the CPU count when there is no quota."""
+    ncpu = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            return max(1, min(ncpu, int(round(int(quota) / int(period)))))
+    except Exception:
+        pass
+    return ncpu
+
+
 def _thread_ladder():
     ncpu = os.cpu_count() or 1
-    return sorted({1, min(2, ncpu), min(4, ncpu), min(16, ncpu), ncpu})
+    q = cpu_quota_cores()
+    return sorted({1, min(2, ncpu), min(4, ncpu), min(16, ncpu), min(q, ncpu), min(2 * q, ncpu), ncpu})
 
 
 def _calibrate_cpu_port(o, kind, n_hist, names):
@@ -241,7 +255,7 @@ def run_reference(a):
         "config": workload_config(a, a.n or default_n(a.workload, a.gpus), a.gpus),
         "rate_normalised": True, "sample": "bounded sample of %d samples per step (about 1 s of CPU work)" % n,
         "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port",
-                         "host_cpus": os.cpu_count(), "thread_ladder_samples_per_s": ladder,
+                         "host_cpus": os.cpu_count(), "cpu_quota_cores": cpu_quota_cores(), "thread_ladder_samples_per_s": ladder,
                          "sample": "%d samples/step x %d steps, stream %s, %d name(s); C port of "
                                    "metrics.go:273-295 incl. Go's RWMutex algorithm (Go toolchain absent), run at "
                                    "the fastest thread count of the ladder" % (n, a.steps, a.stream, n_hist)},
@@ -353,6 +367,10 @@ def api_leg(device, kind):
     out["timer_loop"] = {"value": rate, "unit": "calls/s", "threads": 100, "op": "StartTimer + Stop (print_benchmark.go:59-67, empty op)",
                          "calls": calls, "reported_count": reported, "count_ok": float(calls) == reported, "host_cpus": ncpu}
     n_api = 1_000_000_000
+    # twice the CPU quota: enough runnable threads to use every core the container is allowed, not so many that the
+    # quota throttles them in bursts (measured: profiles/r02/api_probe_r02h.txt)
+    ncpu = min(ncpu, 2 * cpu_quota_cores())
+    out["cpu_quota_cores"] = cpu_quota_cores()
     ms = MetricSystem(3600.0, False, device=device, max_histograms=16, max_counters=16)
     k = kind if kind in (0, 1) else 0
     # pass 0 warms the staging ring up (every shard pins its slots on first use: cudaMallocHost is slow); pass 1 is reported
@@ -701,7 +719,7 @@ def run_b200(a):
                           "Go-exact compress) at the fastest rung of a thread ladder (= `cores`; more threads are slower, "
                           "the shared reader count ping-pongs as in the reference); the Go toolchain is absent so the "
                           "reference itself cannot run" % ns,
-                "host_cpus": os.cpu_count(), "thread_ladder_samples_per_s": ladder,
+                "host_cpus": os.cpu_count(), "cpu_quota_cores": cpu_quota_cores(), "thread_ladder_samples_per_s": ladder,
                 "dense_private_arrays_all_cores_value": dense}
         print(json.dumps(line))
         sys.stdout.flush()

@@ -179,6 +179,7 @@ struct lh_ctx {
     uint32_t hot_replicas = 1;          // copies of the hot window (all L2-resident); only the vector RED kernel spreads over them
     int keyed_mode = 0;                 // 0 auto, 1 force L2-atomic kernel, 2 force the write-combining owner kernel
     int64_t kp_chunk = 32 << 20;        // samples per chunk of the owner-partitioned kernel
+    uint32_t wc_pf_flush = 4, wc_pf_chunk = 8;   // input tiles asked of L2 when a flush / the drain starts (DRAM streams meanwhile)
     uint32_t wc_flush_samples = 24576;  // samples a CTA bins between two flushes of its owner buffers
     int wc_spt = 4;                     // tile shape of that kernel (4: 1024 threads x 4 samples; 3: 768 x 4; 8: 512 x 8)
     // owner-partitioned keyed kernel scratch (allocated on first use)
@@ -375,6 +376,8 @@ lh_status launch_keyed_wc_spt(lh_ctx *ctx, int b, const IdT *ids, const ValT *va
     // samples between two flushes of the shared-memory owner buffers: the flush costs about the same whatever it moves,
     // so as many as the buffers hold at 4 sigma (wc_flush_samples; default 24576)
     prm.flush_tiles = std::max<uint32_t>(1u, (uint32_t)(ctx->wc_flush_samples / S::TILE));
+    prm.pf_flush = ctx->wc_pf_flush;
+    prm.pf_chunk = ctx->wc_pf_chunk;
     prm.slice_tiles = (uint32_t)slice_tiles; prm.queues = ctx->d_kp_queues; prm.q_cnt = ctx->d_kp_cnt;
     prm.barrier = d_barrier; prm.rare = ctx->d_kp_rare; prm.o = keyed_out(ctx, b);
     Prec pc = ctx->pc;
@@ -1656,6 +1659,11 @@ extern "C" lh_status lh_tune(lh_ctx *ctx, const char *key, int64_t value) {
     if (!strcmp(key, "keyed_mode")) {
         if (value < 0 || value > 2) return fail(ctx, LH_ERR_RANGE, "keyed_mode is 0 (auto), 1 (L2 atomics) or 2 (owner-partitioned, write-combining)");
         ctx->keyed_mode = (int)value;
+        return LH_OK;
+    }
+    if (!strcmp(key, "wc_pf_flush") || !strcmp(key, "wc_pf_chunk")) {
+        if (value < 0 || value > 64) return fail(ctx, LH_ERR_RANGE, "prefetch distance is 0 ... 64 tiles");
+        (key[6] == 'f' ? ctx->wc_pf_flush : ctx->wc_pf_chunk) = (uint32_t)value;
         return LH_OK;
     }
     if (!strcmp(key, "wc_flush")) {
