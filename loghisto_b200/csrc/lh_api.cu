@@ -179,7 +179,6 @@ struct lh_ctx {
     uint32_t hot_replicas = 1;          // copies of the hot window (all L2-resident); only the vector RED kernel spreads over them
     int keyed_mode = 0;                 // 0 auto, 1 force L2-atomic kernel, 2 force the write-combining owner kernel
     int64_t kp_chunk = 32 << 20;        // samples per chunk of the owner-partitioned kernel
-    uint32_t wc_pf_flush = 4, wc_pf_chunk = 8;   // input tiles asked of L2 when a flush / the drain starts (DRAM streams meanwhile)
     uint32_t wc_flush_samples = 24576;  // samples a CTA bins between two flushes of its owner buffers
     int wc_spt = 4;                     // tile shape of that kernel (4: 1024 threads x 4 samples; 3: 768 x 4; 8: 512 x 8)
     // owner-partitioned keyed kernel scratch (allocated on first use)
@@ -376,8 +375,6 @@ lh_status launch_keyed_wc_spt(lh_ctx *ctx, int b, const IdT *ids, const ValT *va
     // samples between two flushes of the shared-memory owner buffers: the flush costs about the same whatever it moves,
     // so as many as the buffers hold at 4 sigma (wc_flush_samples; default 24576)
     prm.flush_tiles = std::max<uint32_t>(1u, (uint32_t)(ctx->wc_flush_samples / S::TILE));
-    prm.pf_flush = ctx->wc_pf_flush;
-    prm.pf_chunk = ctx->wc_pf_chunk;
     prm.slice_tiles = (uint32_t)slice_tiles; prm.queues = ctx->d_kp_queues; prm.q_cnt = ctx->d_kp_cnt;
     prm.barrier = d_barrier; prm.rare = ctx->d_kp_rare; prm.o = keyed_out(ctx, b);
     Prec pc = ctx->pc;
@@ -392,9 +389,12 @@ lh_status launch_keyed_wc_spt(lh_ctx *ctx, int b, const IdT *ids, const ValT *va
 template <typename IdT, typename ValT>
 lh_status launch_keyed_wc(lh_ctx *ctx, int b, const IdT *ids, const ValT *vals, size_t n4x4, cudaStream_t s, bool *used, size_t *taken,
                           const IdT *ids2 = nullptr, const long long *vals2 = nullptr, size_t n2 = 0, size_t *taken2 = nullptr) {
-    return ctx->wc_spt == 4 ? launch_keyed_wc_spt<IdT, ValT, 4>(ctx, b, ids, vals, n4x4, s, used, taken, ids2, vals2, n2, taken2)
-         : ctx->wc_spt == 3 ? launch_keyed_wc_spt<IdT, ValT, 3>(ctx, b, ids, vals, n4x4, s, used, taken, ids2, vals2, n2, taken2)
-                            : launch_keyed_wc_spt<IdT, ValT, 8>(ctx, b, ids, vals, n4x4, s, used, taken, ids2, vals2, n2, taken2);
+#define LH_WC_SHAPE(code) case code: return launch_keyed_wc_spt<IdT, ValT, code>(ctx, b, ids, vals, n4x4, s, used, taken, ids2, vals2, n2, taken2);
+    switch (ctx->wc_spt) {
+        LH_WC_SHAPE(4) LH_WC_SHAPE(6) LH_WC_SHAPE(3) LH_WC_SHAPE(5) LH_WC_SHAPE(2)
+        default: return launch_keyed_wc_spt<IdT, ValT, 8>(ctx, b, ids, vals, n4x4, s, used, taken, ids2, vals2, n2, taken2);
+    }
+#undef LH_WC_SHAPE
 }
 
 template <typename IdT, typename ValT>
@@ -1661,18 +1661,14 @@ extern "C" lh_status lh_tune(lh_ctx *ctx, const char *key, int64_t value) {
         ctx->keyed_mode = (int)value;
         return LH_OK;
     }
-    if (!strcmp(key, "wc_pf_flush") || !strcmp(key, "wc_pf_chunk")) {
-        if (value < 0 || value > 64) return fail(ctx, LH_ERR_RANGE, "prefetch distance is 0 ... 64 tiles");
-        (key[6] == 'f' ? ctx->wc_pf_flush : ctx->wc_pf_chunk) = (uint32_t)value;
-        return LH_OK;
-    }
     if (!strcmp(key, "wc_flush")) {
         if (value < 4096 || value > 65536) return fail(ctx, LH_ERR_RANGE, "wc_flush is 4096 ... 65536 samples");
         ctx->wc_flush_samples = (uint32_t)value;
         return LH_OK;
     }
     if (!strcmp(key, "wc_spt")) {
-        if (value != 4 && value != 3 && value != 8) return fail(ctx, LH_ERR_RANGE, "wc_spt is 4 (1024 threads x 4), 3 (768 x 4) or 8 (512 x 8)");
+        if (value != 4 && value != 6 && value != 3 && value != 5 && value != 2 && value != 8)
+            return fail(ctx, LH_ERR_RANGE, "wc_spt is a shape code: 4 (1024 threads x 4), 6 (896 x 4), 3 (768 x 4), 5 (640 x 4), 2 (512 x 4) or 8 (512 x 8)");
         ctx->wc_spt = (int)value;
         return LH_OK;
     }

@@ -617,10 +617,10 @@ k_ingest_keyed_small(const IdT *__restrict__ ids, const ValT *__restrict__ vals,
 constexpr int WC_MAX_PARTS = 160;             // owners = CTAs (one per SM)
 constexpr int WC_LINE = 64;                   // records per line (128 B)
 
-template <int SPT> struct WcShape {           // shape code: 4 = 1024 threads x 4 samples per tile (64 registers per thread),
-                                              // 3 = 768 threads x 4 samples (80 registers), 8 = 512 threads x 8 samples (128)
-    static constexpr int THREADS = SPT == 4 ? 1024 : SPT == 3 ? 768 : 512;
-    static constexpr int PER = SPT == 3 ? 4 : SPT;             // samples per thread per tile
+template <int SPT> struct WcShape {           // shape code -> threads x samples per thread and tile (registers per thread):
+                                              // 4: 1024 x 4 (64), 6: 896 x 4 (72), 3: 768 x 4 (80), 5: 640 x 4 (96), 2: 512 x 4 (128), 8: 512 x 8 (128)
+    static constexpr int THREADS = SPT == 4 ? 1024 : SPT == 6 ? 896 : SPT == 3 ? 768 : SPT == 5 ? 640 : 512;
+    static constexpr int PER = SPT == 8 ? 8 : 4;               // samples per thread per tile
     static constexpr int TILE = THREADS * PER;
     // records one owner's buffer must hold: < WC_LINE carried over + its share of the samples binned between two
     // flushes (WcParams::flush_tiles; ~166 for 24576 samples at P = 148) + 4 sigma of the binomial; a record that
@@ -643,8 +643,6 @@ struct WcParams {
     uint32_t slice_tiles;            // tiles per CTA per chunk
     uint32_t inv_p;                  // floor(2^32 / P) + 1: id / P == __umulhi(id, inv_p) for id < 65536
     uint32_t flush_tiles;            // tiles binned between two flushes of the owner buffers
-    uint32_t pf_flush;               // tiles prefetched into L2 when a flush starts (DRAM keeps streaming while the SM copies lines)
-    uint32_t pf_chunk;               // tiles of my NEXT slice prefetched into L2 when the drain (phase B) starts
     unsigned short *queues;          // [2][P owners][P writers][cap]
     unsigned int *q_cnt;             // [2][P owners][P writers]
     unsigned int *barrier;           // grid barrier counter, zeroed by the host before the launch
@@ -716,16 +714,6 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
     // pointers below walk the CTA's slice one tile at a time (no 64-bit multiplies inside the loop).
     const char *vptr = nullptr;                  // this thread's first 32-byte value group of the current tile
     const IdT *iptr = nullptr;                   // ... and its 4 ids
-    // Phase A is DRAM-bound while the flushes and the drain do not touch DRAM at all: both start by asking L2 for the
-    // input tiles that come next, so the HBM keeps streaming while the SM is busy with shared memory and L2.
-    auto prefetch_tile = [&](const char *vp, const IdT *ip) {       // vp / ip: this thread's group of the tile
-#pragma unroll
-        for (int g = 0; g < GROUPS; g++) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(vp + (size_t)g * WC_THREADS * 32));
-            if ((tid & 3) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(ip + (size_t)g * WC_THREADS * 4));
-        }
-    };
-    uint32_t tiles_after_vptr = 0;               // tiles of the current part that lie beyond the one vptr points to
     auto load_tile = [&](const char *vp, const IdT *ip, unsigned long long (&raw)[GROUPS][4], IdPack<IdT> (&idp)[GROUPS]) {
 #pragma unroll
         for (int g = 0; g < GROUPS; g++) {
@@ -795,7 +783,6 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
             //      is needed between tiles that do not flush: appends are atomic.
             if (++since_flush == prm.flush_tiles) {
                 since_flush = 0;
-                for (uint32_t k = 1; k <= min(prm.pf_flush, tiles_after_vptr); k++) prefetch_tile(vptr + (size_t)k * S::TILE * 8, iptr + (size_t)k * S::TILE);
                 __syncthreads();
                 constexpr uint32_t GROUPS_PER_WARP = 8;
                 const uint32_t sub = (tid & 31) >> 2, k4 = (tid & 3) * 2;
@@ -849,13 +836,11 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
                 vptr += (size_t)S::TILE * 8;                 // -> tile t + 1
                 iptr += S::TILE;
                 if (t + 1 < ntile) load_tile(vptr, iptr, nxt, nxt_id);
-                tiles_after_vptr = ntile > t + 2 ? ntile - (t + 2) : 0u;
                 bin_tile(cur, cur_id, as_i64);
                 if (t + 1 >= ntile) break;
                 vptr += (size_t)S::TILE * 8;                 // -> tile t + 2
                 iptr += S::TILE;
                 if (t + 2 < ntile) load_tile(vptr, iptr, cur, cur_id);
-                tiles_after_vptr = ntile > t + 3 ? ntile - (t + 3) : 0u;
                 bin_tile(nxt, nxt_id, as_i64);
             }
         }
@@ -902,16 +887,6 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
         // P * vq 16-byte vectors of my region are dealt to the threads as ONE flat index space (vector v belongs to
         // writer v / vq), so every thread has several independent L2 loads in flight instead of a count -> data chain.
         if (tid < P) s_off[tid] = __ldcg(&cset[(size_t)p * P + tid]);
-        if (!last_chunk) {   // the head of my slice of chunk c + 1 (tile by tile: the slice may straddle the two segments)
-            const size_t nt0 = (c + 1) * chunk_tiles + (size_t)p * prm.slice_tiles;
-            for (uint32_t k = 0; k < prm.pf_chunk && k < prm.slice_tiles && nt0 + k < tiles_total; k++) {
-                const size_t tl = nt0 + k;
-                const bool seg2 = PAIR && tl >= tiles_seg0;
-                const size_t first = (seg2 ? tl - tiles_seg0 : tl) * S::TILE + (size_t)tid * 4;
-                prefetch_tile(reinterpret_cast<const char *>(seg2 ? prm.vals2 : prm.vals) + first * 8,
-                              (seg2 ? reinterpret_cast<const IdT *>(prm.ids2) : ids) + first);
-            }
-        }
         __syncthreads();
         {
             // warp w drains the sub-queues of writers w, w + NW, ...: the record counts are already in shared memory, so the

@@ -15,24 +15,22 @@ quick = len(sys.argv) > 3
 eng = lh.Engine(device=0, max_histograms=H, max_counters=1)
 d = eng.alloc(n, "float64")
 ids = eng.alloc(n, "uint16")
-# (label, keyed_mode, tile shape, chunk samples, samples between flushes, L2 prefetch tiles at flush / at drain)
-configs = [("vec", 1, 4, 8 << 20, 24576, 4, 8)]
+# (label, keyed_mode, tile shape code, chunk samples, samples between flushes)
+configs = [("vec", 1, 4, 8 << 20, 24576)]
 if quick:
-    for spt, chunk, flush, pff, pfc in ((4, 32 << 20, 24576, 0, 0), (4, 32 << 20, 24576, 4, 8), (4, 32 << 20, 24576, 8, 16),
-                                        (4, 16 << 20, 24576, 4, 8), (4, 32 << 20, 16384, 4, 8), (3, 32 << 20, 24576, 4, 8)):
-        configs.append(("wc", 2, spt, chunk, flush, pff, pfc))
+    for spt in (4, 6, 3, 5, 2, 8):
+        configs.append(("wc", 2, spt, 32 << 20, 24576))
 else:
-    for spt in (8, 3, 4):
+    for spt in (4, 3, 2):
         for chunk in (16 << 20, 32 << 20, 64 << 20):
-            for flush in ((16384, 24576, 28672) if spt == 4 else (24576,)):
-                configs.append(("wc", 2, spt, chunk, flush, 4, 8))
+            for flush in (16384, 24576, 28672):
+                configs.append(("wc", 2, spt, chunk, flush))
 for sname, kind, idkind in (("U", 0, 0), ("L", 1, 0), ("C", 3, 0), ("U/zipf-ids", 0, 1)):
     eng.gen_stream(kind, n, lh.DEFAULT_SEED, out=d)
     eng.gen_ids_u16(idkind, n, H, lh.DEFAULT_SEED, out=ids)
     ref = None
-    for name, mode, spt, chunk, flush, pff, pfc in configs:
+    for name, mode, spt, chunk, flush in configs:
         eng.tune("keyed_mode", mode); eng.tune("wc_spt", spt); eng.tune("kp_chunk", chunk); eng.tune("wc_flush", flush)
-        eng.tune("wc_pf_flush", pff); eng.tune("wc_pf_chunk", pfc)
         t = []
         for _ in range(4):
             eng.ingest_keyed_f64_u16(ids, d, n)
@@ -42,7 +40,7 @@ for sname, kind, idkind in (("U", 0, 0), ("L", 1, 0), ("C", 3, 0), ("U/zipf-ids"
         if ref is None:
             ref = sig
         ms = sorted(t)[1]
-        print("H=%-4d stream %-10s %-4s spt=%-2d chunk=%-9d flush=%-5d pf=%d/%-2d %8.3f ms %7.1f G samples/s %5.2f TB/s  kernel=%s  count_ok=%s same_buckets=%s"
-              % (H, sname, name, spt, chunk, flush, pff, pfc, ms, n / ms / 1e6, n * 10 / ms / 1e9, eng.keyed_kernel_name(),
+        print("H=%-4d stream %-10s %-4s shape=%-2d chunk=%-9d flush=%-5d %8.3f ms %7.1f G samples/s %5.2f TB/s  kernel=%s  count_ok=%s same_buckets=%s"
+              % (H, sname, name, spt, chunk, flush, ms, n / ms / 1e6, n * 10 / ms / 1e9, eng.keyed_kernel_name(),
                  int(red.counts.sum()) == 4 * n, sig == ref), flush=True)
 eng.close()
