@@ -180,7 +180,7 @@ struct lh_ctx {
     int keyed_mode = 0;                 // 0 auto, 1 force L2-atomic kernel, 2 force the write-combining owner kernel
     int64_t kp_chunk = 32 << 20;        // samples per chunk of the owner-partitioned kernel
     uint32_t wc_flush_samples = 24576;  // samples a CTA bins between two flushes of its owner buffers
-    int wc_spt = 4;                     // tile shape of that kernel (4: 1024 threads x 4 samples; 3: 768 x 4; 8: 512 x 8)
+    int wc_spt = 6;                     // tile shape of that kernel (6: 896 threads x 4 samples; 4: 1024 x 4; 3: 768 x 4; 8: 512 x 8)
     // owner-partitioned keyed kernel scratch (allocated on first use)
     unsigned short *d_kp_queues = nullptr;
     unsigned int *d_kp_cnt = nullptr;     // per-(owner, writer) record counts, then the grid-barrier word
@@ -348,10 +348,16 @@ lh_status launch_keyed_wc_spt(lh_ctx *ctx, int b, const IdT *ids, const ValT *va
     n4x4 = n4x4 / S::TILE * S::TILE;
     n2 = n2 / S::TILE * S::TILE;
     if (n4x4 + n2 == 0) return LH_OK;
-    const size_t slice_tiles = std::max<size_t>(1, ((size_t)ctx->kp_chunk + (size_t)P * S::TILE - 1) / ((size_t)P * S::TILE));
+    // chunks of about kp_chunk samples, EQUAL in size: with the nominal slice a short last chunk would be binned by a
+    // few CTAs at full slice length while the others idle (it cost a whole chunk time per launch: 50 M pairs ran at 211
+    // instead of 260 G samples/s, profiles/r02/keyed_batch_probe_r02l.txt)
+    const size_t slice_max = std::max<size_t>(1, ((size_t)ctx->kp_chunk + (size_t)P * S::TILE - 1) / ((size_t)P * S::TILE));
+    const size_t tiles_all = n4x4 / S::TILE + n2 / S::TILE;
+    const size_t nchunks = (tiles_all + slice_max * P - 1) / (slice_max * P);
+    const size_t slice_tiles = std::max<size_t>(1, (tiles_all + nchunks * P - 1) / (nchunks * P));
     // every (owner, writer) pair has its own sub-queue: 1.25x the expected records per pair per chunk, plus slack
     // (records that do not fit take the exact L2 route, so this only trades speed on heavily skewed ids)
-    const size_t expect = slice_tiles * S::TILE / P;
+    const size_t expect = slice_max * S::TILE / P;       // sized for the nominal slice: the allocation does not follow the batch size
     const size_t cap = ((expect * 5 / 4 + 3 * WC_LINE + WC_LINE - 1) / WC_LINE) * WC_LINE;
     if (!ctx->d_kp_queues || ctx->kp_cap != cap || ctx->kp_parts != P) {
         cudaFree(ctx->d_kp_queues); cudaFree(ctx->d_kp_cnt); cudaFree(ctx->d_kp_rare);
@@ -391,7 +397,7 @@ lh_status launch_keyed_wc(lh_ctx *ctx, int b, const IdT *ids, const ValT *vals, 
                           const IdT *ids2 = nullptr, const long long *vals2 = nullptr, size_t n2 = 0, size_t *taken2 = nullptr) {
 #define LH_WC_SHAPE(code) case code: return launch_keyed_wc_spt<IdT, ValT, code>(ctx, b, ids, vals, n4x4, s, used, taken, ids2, vals2, n2, taken2);
     switch (ctx->wc_spt) {
-        LH_WC_SHAPE(4) LH_WC_SHAPE(6) LH_WC_SHAPE(3) LH_WC_SHAPE(5) LH_WC_SHAPE(2)
+        LH_WC_SHAPE(6) LH_WC_SHAPE(4) LH_WC_SHAPE(3)
         default: return launch_keyed_wc_spt<IdT, ValT, 8>(ctx, b, ids, vals, n4x4, s, used, taken, ids2, vals2, n2, taken2);
     }
 #undef LH_WC_SHAPE
@@ -1667,8 +1673,8 @@ extern "C" lh_status lh_tune(lh_ctx *ctx, const char *key, int64_t value) {
         return LH_OK;
     }
     if (!strcmp(key, "wc_spt")) {
-        if (value != 4 && value != 6 && value != 3 && value != 5 && value != 2 && value != 8)
-            return fail(ctx, LH_ERR_RANGE, "wc_spt is a shape code: 4 (1024 threads x 4), 6 (896 x 4), 3 (768 x 4), 5 (640 x 4), 2 (512 x 4) or 8 (512 x 8)");
+        if (value != 4 && value != 6 && value != 3 && value != 8)
+            return fail(ctx, LH_ERR_RANGE, "wc_spt is a shape code: 6 (896 threads x 4 samples), 4 (1024 x 4), 3 (768 x 4) or 8 (512 x 8)");
         ctx->wc_spt = (int)value;
         return LH_OK;
     }

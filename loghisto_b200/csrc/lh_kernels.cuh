@@ -618,8 +618,9 @@ constexpr int WC_MAX_PARTS = 160;             // owners = CTAs (one per SM)
 constexpr int WC_LINE = 64;                   // records per line (128 B)
 
 template <int SPT> struct WcShape {           // shape code -> threads x samples per thread and tile (registers per thread):
-                                              // 4: 1024 x 4 (64), 6: 896 x 4 (72), 3: 768 x 4 (80), 5: 640 x 4 (96), 2: 512 x 4 (128), 8: 512 x 8 (128)
-    static constexpr int THREADS = SPT == 4 ? 1024 : SPT == 6 ? 896 : SPT == 3 ? 768 : SPT == 5 ? 640 : 512;
+                                              // 6: 896 x 4 (72, default), 4: 1024 x 4 (64), 3: 768 x 4 (80), 8: 512 x 8 (128);
+                                              // measured within 3 % of each other, 640 x 4 and 512 x 4 were 3 - 10 % slower
+    static constexpr int THREADS = SPT == 4 ? 1024 : SPT == 6 ? 896 : SPT == 3 ? 768 : 512;
     static constexpr int PER = SPT == 8 ? 8 : 4;               // samples per thread per tile
     static constexpr int TILE = THREADS * PER;
     // records one owner's buffer must hold: < WC_LINE carried over + its share of the samples binned between two

@@ -484,7 +484,7 @@ def test_mixed_ops_interval_pipeline(lh, oracle):
             assert (dense_from_sparse(sp, h) == want[h]).all()
 
 
-@pytest.mark.parametrize("chunk,spt,flush", [(65536, 4, 24576), (1 << 20, 4, 4096), (1 << 20, 4, 65536), (65536, 3, 24576), (1 << 20, 8, 16384)])
+@pytest.mark.parametrize("chunk,spt,flush", [(65536, 6, 24576), (1 << 20, 6, 4096), (1 << 20, 4, 65536), (65536, 3, 24576), (1 << 20, 8, 16384)])
 def test_keyed_owner_partitioned_kernel(lh, oracle, chunk, spt, flush):
     """The owner-partitioned write-combining keyed kernel (bin -> per-owner buffers -> per-(owner, writer) queues ->
     shared-memory windows) against the oracle: several chunks (grid barriers, queue parity), signed/edge values,

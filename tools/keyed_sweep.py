@@ -18,10 +18,10 @@ ids = eng.alloc(n, "uint16")
 # (label, keyed_mode, tile shape code, chunk samples, samples between flushes)
 configs = [("vec", 1, 4, 8 << 20, 24576)]
 if quick:
-    for spt in (4, 6, 3, 5, 2, 8):
+    for spt in (6, 4, 3, 8):
         configs.append(("wc", 2, spt, 32 << 20, 24576))
 else:
-    for spt in (4, 3, 2):
+    for spt in (6, 4, 3):
         for chunk in (16 << 20, 32 << 20, 64 << 20):
             for flush in (16384, 24576, 28672):
                 configs.append(("wc", 2, spt, chunk, flush))

@@ -21,7 +21,7 @@ with lh.Engine(device=0, max_histograms=64, max_counters=64) as e:
     e.ingest_keyed_f64_u16(ids, d, n); total += n
     e.ingest_keyed_i64ns_u16(ids, ns, n); total += n
     e.tune("keyed_mode", 2); e.tune("kp_chunk", 65536)  # write-combining owner kernel, every tile shape, several chunks
-    for spt in (4, 3, 8):
+    for spt in (6, 4, 3, 8):
         e.tune("wc_spt", spt)
         e.ingest_keyed_f64_u16(ids, d, n); total += n
     e.ingest_keyed_pair_u16(ids, d, n, ids, ns, n); total += 2 * n   # float64 + int64 segments in one launch
