@@ -1463,7 +1463,13 @@ extern "C" lh_status lh_snapshot_allreduce(lh_ctx *ctx, uint32_t include_counter
     // a few CTAs: the kernel shares the GPU with the next interval's ingest (which leaves k1_reserve_sms SMs free);
     // CTAs that are not resident yet simply start later (no CTA waits for another CTA of its own grid before the end)
     const size_t items = (size_t)ctx->H * (65536u / K5_CHUNK);
-    const int grid = (int)std::min<size_t>(items, ctx->H == 1 ? 5 : (p.two_shot ? 64 : 16));
+    int grid = (int)std::min<size_t>(items, ctx->H == 1 ? 5 : 16);
+    if (p.two_shot) {
+        // as many CTAs (2 x 1024 threads per SM) as fit on the SMs the ingest kernels leave free: the write-combining
+        // kernel is cooperative, a wider all-reduce would hold its CTAs back and serialise the two (measured at N = 2)
+        const int room = ctx->k1_reserve_sms > 0 ? 2 * ctx->k1_reserve_sms : 16;
+        grid = (int)std::min<size_t>((ctx->H + ctx->comm_world - 1) / ctx->comm_world, (size_t)room);
+    }
     LH_CUDA(ctx, cudaEventRecord(ctx->comm_t0[ring], s));
     k_peer_allreduce<<<grid, K5_THREADS, ctx->H, s>>>(p);
     LH_CUDA(ctx, cudaGetLastError());

@@ -1412,7 +1412,8 @@ k_clear_touched(unsigned long long *__restrict__ buckets, uint32_t *__restrict__
 // token = seq*2 + frozen buffer index: ranks must take their snapshots in lock-step (same count, same order).
 static_assert(LH_MAX_RANKS == 16, "comm block layout assumes 16 ranks");
 constexpr int K5_THREADS = 1024;
-constexpr int K5_CHUNK = 2 * K5_THREADS;     // cells per work item
+constexpr int K5_CHUNK = 2 * K5_THREADS;     // cells per work item (one-shot form)
+constexpr int K5_DEEP = 9;                   // cells per thread and pass of the two-shot form: 9 x 1024 covers the 8 735-cell window of precision 100
 
 struct PeerParams {
     uint32_t rank, world, H, C, win, do_counters, frozen, pad;
@@ -1506,38 +1507,55 @@ k_peer_allreduce(PeerParams p) {
         if (blockIdx.x == 0 && cells) atomicAdd(&s_cells, cells);
         __syncthreads();
         if (blockIdx.x == 0 && t == 0) *p.cells = s_cells;
-        const size_t nitems = (size_t)p.H * PER_H;
-        for (size_t item = blockIdx.x; item < nitems; item += gridDim.x) {
-            const uint32_t h = (uint32_t)(item / PER_H), chunk = (uint32_t)(item % PER_H);
-            const uint32_t level = s_level[h];
-            if (level == 0) continue;
-            const bool dense = (level & 2u) != 0;
-            if (!dense && chunk >= chunks_w) continue;
-            if (p.two_shot && (h + chunk) % p.world != p.rank) continue;
-            const uint32_t ncell = dense ? 65536u : wcells;
-            constexpr int K = K5_CHUNK / K5_THREADS;
-            size_t cell[K];
-            unsigned long long sum[K];
+        if (!p.two_shot) {
+            const size_t nitems = (size_t)p.H * PER_H;
+            for (size_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const uint32_t h = (uint32_t)(item / PER_H), chunk = (uint32_t)(item % PER_H);
+                const uint32_t level = s_level[h];
+                if (level == 0) continue;
+                const bool dense = (level & 2u) != 0;
+                if (!dense && chunk >= chunks_w) continue;
+                const uint32_t ncell = dense ? 65536u : wcells;
+                constexpr int K = K5_CHUNK / K5_THREADS;
 #pragma unroll
-            for (int k = 0; k < K; k++) {
-                const uint32_t i = chunk * K5_CHUNK + k * K5_THREADS + t;
-                cell[k] = i < ncell ? (size_t)h * 65536u + (dense ? i : window_cell(i, p.win)) : (size_t)-1;
-                sum[k] = 0;
+                for (int k = 0; k < K; k++) {
+                    const uint32_t i = chunk * K5_CHUNK + k * K5_THREADS + t;
+                    if (i >= ncell) continue;
+                    const size_t cell = (size_t)h * 65536u + (dense ? i : window_cell(i, p.win));
+                    unsigned long long sum = 0;
+                    for (uint32_t r = 0; r < p.world; r++) sum += ld_sys_u64(p.buckets[r] + cell);
+                    if (sum) p.out_buckets[cell] = sum;
+                }
             }
-#pragma unroll 4
-            for (uint32_t r = 0; r < p.world; r++) {          // K * world independent loads in flight per thread
-                const unsigned long long *src = p.buckets[r];
+        } else {
+            // two-shot: a rank owns the histograms h = rank (mod world); a CTA takes one owned histogram at a time and every
+            // thread keeps K5_DEEP cells x world loads in flight (a few CTAs on the SMs the ingest kernel leaves free must
+            // cover the NVLink latency-bandwidth product on their own)
+            for (uint32_t h = p.rank + blockIdx.x * p.world; h < p.H; h += gridDim.x * p.world) {
+                const uint32_t level = s_level[h];
+                if (level == 0) continue;
+                const bool dense = (level & 2u) != 0;
+                const uint32_t ncell = dense ? 65536u : wcells;
+                for (uint32_t base = 0; base < ncell; base += K5_DEEP * K5_THREADS) {
+                    size_t cell[K5_DEEP];
+                    unsigned long long sum[K5_DEEP];
 #pragma unroll
-                for (int k = 0; k < K; k++)
-                    if (cell[k] != (size_t)-1) sum[k] += ld_sys_u64(src + cell[k]);
-            }
+                    for (int k = 0; k < K5_DEEP; k++) {
+                        const uint32_t i = base + k * K5_THREADS + t;
+                        cell[k] = i < ncell ? (size_t)h * 65536u + (dense ? i : window_cell(i, p.win)) : (size_t)-1;
+                        sum[k] = 0;
+                    }
+                    for (uint32_t r = 0; r < p.world; r++) {
+                        const unsigned long long *src = p.buckets[r];
 #pragma unroll
-            for (int k = 0; k < K; k++) {
-                if (cell[k] == (size_t)-1 || sum[k] == 0) continue;
-                if (p.two_shot) {
-                    for (uint32_t r = 0; r < p.world; r++) p.out_peer[r][cell[k]] = sum[k];
-                } else {
-                    p.out_buckets[cell[k]] = sum[k];
+                        for (int k = 0; k < K5_DEEP; k++)
+                            if (cell[k] != (size_t)-1) sum[k] += ld_sys_u64(src + cell[k]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < K5_DEEP; k++) {
+                        if (cell[k] == (size_t)-1 || sum[k] == 0) continue;
+                        for (uint32_t r = 0; r < p.world; r++) p.out_peer[r][cell[k]] = sum[k];
+                    }
                 }
             }
         }
