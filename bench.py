@@ -44,7 +44,7 @@ def parse_args():
                     help="c2 = configs[1] (default), c3 = configs[2] (1024 keyed), c5 = configs[4] (mixed ops), "
                          "c4x1 = the north-star target: the 1e10-sample stream of configs[3] resident on ONE GPU (80 GB)")
     ap.add_argument("--stream", default="U", choices=["U", "L", "S", "C", "Z"])
-    ap.add_argument("--n", type=int, default=0, help="samples per GPU per step (default: BASELINE config)")
+    ap.add_argument("--n", "--samples-per-gpu", dest="n", type=int, default=0, help="samples per GPU per step (default: BASELINE config)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps for the host-fed leg (default min(steps, 5))")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

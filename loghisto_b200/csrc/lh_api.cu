@@ -342,8 +342,15 @@ lh_status launch_keyed_wc_spt(lh_ctx *ctx, int b, const IdT *ids, const ValT *va
     const uint32_t ids_per = (ctx->H + P - 1) / P;
     using S = WcShape<SPT>;
     const size_t hist_bytes = (((size_t)ids_per * ctx->pc.win + 3) & ~(size_t)3) * 4;
-    const size_t smem = hist_bytes + 2 * WC_MAX_PARTS * 4 + (size_t)(P + 1) * S::STRIDE * 2;
-    if (smem > kSmemBudget || (size_t)ids_per * ctx->pc.win > 65535) return LH_OK;     // records are 16-bit (lid*win + slot)
+    // the owners' windows first, then the largest per-owner buffers that still fit (fewer SMs for ingest = more ids per
+    // owner = less room: 256 records at P = 147, 192 at P = 140 for H = 1024)
+    uint32_t row_cap = 0;
+    size_t smem = 0;
+    for (uint32_t cap_try : {256u, 192u, 128u}) {
+        smem = hist_bytes + 2 * WC_MAX_PARTS * 4 + (size_t)(P + 1) * (cap_try + WC_ROW_EXTRA) * 2;
+        if (smem <= kSmemBudget) { row_cap = cap_try; break; }
+    }
+    if (!row_cap || (size_t)ids_per * ctx->pc.win > 65535) return LH_OK;               // records are 16-bit (lid*win + slot)
     if (ctx->keyed_mode != 2 && n4x4 + n2 < ((size_t)1 << 22)) return LH_OK;           // small batches: the L2-atomic kernel
     n4x4 = n4x4 / S::TILE * S::TILE;
     n2 = n2 / S::TILE * S::TILE;
@@ -380,7 +387,14 @@ lh_status launch_keyed_wc_spt(lh_ctx *ctx, int b, const IdT *ids, const ValT *va
     prm.inv_p = (uint32_t)(((uint64_t)1 << 32) / (uint64_t)P) + 1u;
     // samples between two flushes of the shared-memory owner buffers: the flush costs about the same whatever it moves,
     // so as many as the buffers hold at 4 sigma (wc_flush_samples; default 24576)
-    prm.flush_tiles = std::max<uint32_t>(1u, (uint32_t)(ctx->wc_flush_samples / S::TILE));
+    // ... and an owner's expected share m of one interval must leave room for the carried-over remainder (< 64) and the
+    // binomial spread: m + 3.5 sqrt(m) + 63 <= row_cap
+    const double room = (double)row_cap - 63.0;
+    const double m_max = std::pow((-3.5 + std::sqrt(3.5 * 3.5 + 4.0 * room)) / 2.0, 2.0);
+    const uint32_t flush_samples = std::min<uint32_t>(ctx->wc_flush_samples, (uint32_t)(m_max * P));
+    prm.flush_tiles = std::max<uint32_t>(1u, flush_samples / S::TILE);
+    prm.row_cap = row_cap;
+    prm.row_stride = row_cap + WC_ROW_EXTRA;
     prm.slice_tiles = (uint32_t)slice_tiles; prm.queues = ctx->d_kp_queues; prm.q_cnt = ctx->d_kp_cnt;
     prm.barrier = d_barrier; prm.rare = ctx->d_kp_rare; prm.o = keyed_out(ctx, b);
     Prec pc = ctx->pc;

@@ -623,14 +623,12 @@ template <int SPT> struct WcShape {           // shape code -> threads x samples
     static constexpr int THREADS = SPT == 4 ? 1024 : SPT == 6 ? 896 : SPT == 3 ? 768 : 512;
     static constexpr int PER = SPT == 8 ? 8 : 4;               // samples per thread per tile
     static constexpr int TILE = THREADS * PER;
-    // records one owner's buffer must hold: < WC_LINE carried over + its share of the samples binned between two
-    // flushes (WcParams::flush_tiles; ~166 for 24576 samples at P = 148) + 4 sigma of the binomial; a record that
-    // does not fit takes the exact route
-    static constexpr int CAP = 256;
-    // storage per owner: CAP + one spill line (the remainder copy reads a whole line) + 8 records of padding so that
-    // the 128-bit accesses of the per-owner flush (thread o <-> owner o) are bank-conflict free
-    static constexpr int STRIDE = CAP + WC_LINE + 8;
 };
+// An owner's shared-memory buffer holds row_cap records (WcParams; 256 when it fits, else 192 or 128): < WC_LINE carried
+// over from the last flush + its share of the samples binned between two flushes + ~3.5 sigma of the binomial; a record
+// that does not fit takes the exact route.  Storage per owner = row_cap + one spill line (the remainder copy reads a
+// whole line) + 8 records of padding so that the 128-bit accesses of the flush are bank-conflict free.
+constexpr int WC_ROW_EXTRA = WC_LINE + 8;
 
 struct WcParams {
     const void *ids;                 // IdT[n], 4*sizeof(IdT)-aligned
@@ -644,6 +642,8 @@ struct WcParams {
     uint32_t slice_tiles;            // tiles per CTA per chunk
     uint32_t inv_p;                  // floor(2^32 / P) + 1: id / P == __umulhi(id, inv_p) for id < 65536
     uint32_t flush_tiles;            // tiles binned between two flushes of the owner buffers
+    uint32_t row_cap;                // records an owner's shared-memory buffer holds (multiple of 64; the host takes what fits)
+    uint32_t row_stride;             // row_cap + one spill line + 8 records of padding (bank-conflict-free 128-bit flush)
     unsigned short *queues;          // [2][P owners][P writers][cap]
     unsigned int *q_cnt;             // [2][P owners][P writers]
     unsigned int *barrier;           // grid barrier counter, zeroed by the host before the launch
@@ -706,6 +706,7 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
     const size_t nchunks = (tiles_total + chunk_tiles - 1) / chunk_tiles;
     const IdT *ids = reinterpret_cast<const IdT *>(prm.ids);
     const unsigned int cap = prm.cap;
+    const uint32_t row_cap = prm.row_cap, row_stride = prm.row_stride;
 
 
     unsigned long long cur[GROUPS][4], nxt[GROUPS][4];
@@ -761,9 +762,9 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
                     const uint32_t oe = rare ? P : owner;
                     uint32_t pos;
                     asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(fill_addr + oe * 4u) : "memory");
-                    flag[j] = rare | (pos >= (uint32_t)S::CAP);                            // buffer full (skewed ids): exact route as well
+                    flag[j] = rare | (pos >= row_cap);                            // buffer full (skewed ids): exact route as well
                     if (!flag[j])                                                          // one predicated store, no branch
-                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(buf_addr + (oe * (uint32_t)S::STRIDE + pos) * 2u), "h"((unsigned short)rec) : "memory");
+                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(buf_addr + (oe * row_stride + pos) * 2u), "h"((unsigned short)rec) : "memory");
                     any |= flag[j];
                 }
                 if (__any_sync(0xFFFFFFFFu, any)) {
@@ -792,9 +793,9 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
                     const bool act = o < P;
                     unsigned int n = 0, nfull = 0, off0 = 0;
                     uint4 keep0 = make_uint4(0, 0, 0, 0), keep1 = keep0;
-                    uint4 *src = reinterpret_cast<uint4 *>(s_buf + (act ? o : 0) * S::STRIDE);
+                    uint4 *src = reinterpret_cast<uint4 *>(s_buf + (act ? o : 0) * row_stride);
                     if (act) {
-                        n = min(s_fill[o], (unsigned int)S::CAP);
+                        n = min(s_fill[o], row_cap);
                         nfull = n / WC_LINE;
                         off0 = s_off[o];
                         unsigned short *qbase = qset + ((size_t)o * P + p) * cap;
@@ -808,7 +809,7 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
                                 dst[k4 + 1] = a1;
                                 off0 += WC_LINE;
                             } else if (k4 == 0) {                                          // sub-queue full: these records go the L2 route
-                                const unsigned short *r = s_buf + o * S::STRIDE + l * WC_LINE;
+                                const unsigned short *r = s_buf + o * row_stride + l * WC_LINE;
                                 for (unsigned int k = 0; k < (unsigned int)WC_LINE; k++) wc_spill(r[k], o, P, pc, prm.o);
                             }
                         }
@@ -861,9 +862,9 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
         if (last_chunk) {   // everything still waiting in the buffers goes out, the last line of each owner partially filled
             if (tid < P) {
                 const uint32_t o = tid;
-                const unsigned int n = min(s_fill[o], (unsigned int)S::CAP);
+                const unsigned int n = min(s_fill[o], row_cap);
                 unsigned int off0 = s_off[o];
-                const uint4 *src = reinterpret_cast<const uint4 *>(s_buf + o * S::STRIDE);
+                const uint4 *src = reinterpret_cast<const uint4 *>(s_buf + o * row_stride);
                 for (unsigned int l = 0; l * WC_LINE < n; l++) {
                     const unsigned int nrec = min((unsigned int)WC_LINE, n - l * WC_LINE);
                     if (off0 + WC_LINE <= cap) {
@@ -872,7 +873,7 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
                         for (int k = 0; k < 8; k++) dst[k] = src[l * 8 + k];
                         off0 += nrec;
                     } else {
-                        const unsigned short *r = s_buf + o * S::STRIDE + l * WC_LINE;
+                        const unsigned short *r = s_buf + o * row_stride + l * WC_LINE;
                         for (unsigned int k = 0; k < nrec; k++) wc_spill(r[k], o, P, pc, prm.o);
                     }
                 }
@@ -1438,6 +1439,11 @@ __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long lon
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+// Bulk reads of a peer's frozen arrays: ordinary L2-only loads (ld.global.cg), which a warp coalesces into 128-byte
+// requests - strong system-scope loads went out as one small NVLink request per lane (35 MB took 0.7 - 3 ms).  They are
+// ordered after the acquire of the peer's arrival token, and L1 (which could hold the same addresses from two
+// snapshots ago) is bypassed; peer memory is not cached in the local L2.
+__device__ __forceinline__ unsigned long long ld_peer_u64(const unsigned long long *p) { return __ldcg(p); }
 __device__ __forceinline__ uint32_t ld_sys_u32(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -1523,7 +1529,7 @@ k_peer_allreduce(PeerParams p) {
                     if (i >= ncell) continue;
                     const size_t cell = (size_t)h * 65536u + (dense ? i : window_cell(i, p.win));
                     unsigned long long sum = 0;
-                    for (uint32_t r = 0; r < p.world; r++) sum += ld_sys_u64(p.buckets[r] + cell);
+                    for (uint32_t r = 0; r < p.world; r++) sum += ld_peer_u64(p.buckets[r] + cell);
                     if (sum) p.out_buckets[cell] = sum;
                 }
             }
@@ -1549,7 +1555,7 @@ k_peer_allreduce(PeerParams p) {
                         const unsigned long long *src = p.buckets[r];
 #pragma unroll
                         for (int k = 0; k < K5_DEEP; k++)
-                            if (cell[k] != (size_t)-1) sum[k] += ld_sys_u64(src + cell[k]);
+                            if (cell[k] != (size_t)-1) sum[k] += ld_peer_u64(src + cell[k]);
                     }
 #pragma unroll
                     for (int k = 0; k < K5_DEEP; k++) {
