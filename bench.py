@@ -448,7 +448,19 @@ def run_b200(a):
         eng.tune("keyed_mode", a.keyed_mode)
     depth = a.pipeline_depth if a.pipeline_depth >= 0 else 2
     peer = world > 1 and a.collective == "peer"
-    reserve = a.reserve_sms if a.reserve_sms >= 0 else (0 if depth == 0 else 1 if (world == 1 or peer) else 2 if world <= 4 else 8)
+    # SMs the ingest kernels leave to the snapshot stream.  Peer collective: 1 is enough for one histogram (70 KB per peer);
+    # with 1 024 histograms the two-shot all-reduce moves 2 x 36 MB per rank and needs 4 SMs to finish inside a step
+    # (measured at N = 2: 432 G samples/s with 1 SM, 556 G with 4).  NCCL needs 2 (N <= 4) or 8 SMs.
+    if a.reserve_sms >= 0:
+        reserve = a.reserve_sms
+    elif depth == 0:
+        reserve = 0
+    elif world == 1:
+        reserve = 1
+    elif peer:
+        reserve = 1 if single else 4
+    else:
+        reserve = 2 if world <= 4 else 8
     if reserve:
         eng.tune("k1_reserve_sms", reserve)
     # launch on the context's own non-blocking ingest stream (torch's legacy default stream serialises against
