@@ -57,9 +57,10 @@ def parse_args():
     ap.add_argument("--k1-variant", type=int, default=-1)
     ap.add_argument("--pipeline-depth", type=int, default=-1,
                     help="snapshots in flight behind the next ingest: 0 = blocking snapshot after every batch, 1, 2 (default 2)")
-    ap.add_argument("--collective", default="nccl", choices=["nccl", "peer"],
-                    help="N>1: nccl = torch.distributed all-reduce of the frozen arrays; peer = the library's own "
-                         "peer-memory all-reduce kernel behind the C ABI (lh_comm_*)")
+    ap.add_argument("--collective", default="peer", choices=["nccl", "peer"],
+                    help="N>1: peer (default) = the library's own peer-memory all-reduce kernel behind the C ABI "
+                         "(lh_comm_*); nccl = torch.distributed all-reduce of the frozen arrays, kept for comparison "
+                         "(and the automatic fallback if the peer mappings cannot be made)")
     ap.add_argument("--keyed-mode", type=int, default=-1)
     ap.add_argument("--debug-steps", action="store_true", help="print every timed step's kernel time to stderr")
     ap.add_argument("--nccl-defaults", action="store_true", help="do not set NCCL_MAX_NCHANNELS / NCCL_CGA_CLUSTER_SIZE")
@@ -704,6 +705,8 @@ def run_b200(a):
                                   "timed": "CUDA events around the collective on the snapshot stream, one pair per step, "
                                            "warm-up pairs discarded",
                                   "bytes": sharded.allreduce_bytes()}
+            if getattr(sharded, "fallback_reason", None):
+                line["collective"]["fallback_from_peer"] = sharded.fallback_reason
             line["allreduce_ms"] = ar_ms
         if sus:
             v_s = n * world / (sus["ms_per_step"] / 1e3)

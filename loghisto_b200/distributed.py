@@ -63,6 +63,7 @@ class ShardedEngine:
         self._views = {}     # device pointer -> cached zero-copy tensor
         self._ext = None
         self._bytes = 0
+        self.fallback_reason = None
         if self.collective == "peer":
             self._init_peer(dist)
 
@@ -75,8 +76,18 @@ class ShardedEngine:
         t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to("cuda:%d" % self.device_index)
         out = [torch.empty_like(t) for _ in range(self.world)]
         dist.all_gather(out, t, group=self.group)
-        eng.comm_import(rank, self.world, b"".join(bytes(o.cpu().numpy().tobytes()) for o in out))
-        dist.barrier(group=self.group)                             # every rank has mapped every peer
+        err = ""
+        try:
+            eng.comm_import(rank, self.world, b"".join(bytes(o.cpu().numpy().tobytes()) for o in out))
+        except Exception as e:                                     # e.g. no peer access / CUDA IPC between two of the devices
+            err = str(e)
+        # every rank has mapped every peer -- or ALL ranks fall back to NCCL together (a rank must never wait in the
+        # peer kernel for a rank that is not going to launch it)
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device="cuda:%d" % self.device_index)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            self.collective = "nccl"
+            self.fallback_reason = err or "a peer rank could not map this rank's memory"
 
     def _tensor(self, ptr: int, words: int):
         import torch
