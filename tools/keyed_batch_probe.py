@@ -10,7 +10,7 @@ d = eng.gen_stream(lh.STREAM_U, nmax, lh.DEFAULT_SEED)
 ns = eng.gen_stream(lh.STREAM_TIMER_NS, nmax // 4, lh.DEFAULT_SEED)
 ids = eng.gen_ids_u16(0, nmax, H, lh.DEFAULT_SEED)
 eng.tune("keyed_mode", 2)
-for shape in (4, 3):
+for shape in (6, 4):
     eng.tune("wc_spt", shape)
     for n in (8_000_000, 25_000_000, 50_000_000, 75_000_000, 100_000_000, 200_000_000, 400_000_000):
         t = []
