@@ -1479,9 +1479,9 @@ extern "C" lh_status lh_snapshot_allreduce(lh_ctx *ctx, uint32_t include_counter
     const size_t items = (size_t)ctx->H * (65536u / K5_CHUNK);
     int grid = (int)std::min<size_t>(items, ctx->H == 1 ? 5 : 16);
     if (p.two_shot) {
-        // as many CTAs (2 x 1024 threads per SM) as fit on the SMs the ingest kernels leave free: the write-combining
-        // kernel is cooperative, a wider all-reduce would hold its CTAs back and serialise the two (measured at N = 2)
-        const int room = ctx->k1_reserve_sms > 0 ? 2 * ctx->k1_reserve_sms : 16;
+        // one CTA (1024 threads, 64 registers) per SM the ingest kernels leave free: the write-combining kernel is
+        // cooperative, a wider all-reduce would hold its CTAs back and serialise the two (measured at N = 2)
+        const int room = ctx->k1_reserve_sms > 0 ? ctx->k1_reserve_sms : 8;
         grid = (int)std::min<size_t>((ctx->H + ctx->comm_world - 1) / ctx->comm_world, (size_t)room);
     }
     LH_CUDA(ctx, cudaEventRecord(ctx->comm_t0[ring], s));

@@ -1474,7 +1474,7 @@ __device__ __forceinline__ bool wait_token(const unsigned long long *slot, unsig
     }
 }
 
-__global__ void __launch_bounds__(K5_THREADS)
+__global__ void __launch_bounds__(K5_THREADS, 1)
 k_peer_allreduce(PeerParams p) {
     extern __shared__ unsigned char s_level[];               // [H]: OR over ranks of the histogram's flag
     __shared__ unsigned long long s_cells;
@@ -1543,23 +1543,26 @@ k_peer_allreduce(PeerParams p) {
                 const bool dense = (level & 2u) != 0;
                 const uint32_t ncell = dense ? 65536u : wcells;
                 for (uint32_t base = 0; base < ncell; base += K5_DEEP * K5_THREADS) {
-                    size_t cell[K5_DEEP];
+                    // all loads of a pass before its first store: K5_DEEP cells x world ranks, independent, as many in flight
+                    // per thread as the 64 registers allow (one CTA per SM)
+                    uint32_t cell[K5_DEEP];                  // cell index inside the [H][65536] array (H <= 65535: fits 32 bits)
                     unsigned long long sum[K5_DEEP];
 #pragma unroll
                     for (int k = 0; k < K5_DEEP; k++) {
                         const uint32_t i = base + k * K5_THREADS + t;
-                        cell[k] = i < ncell ? (size_t)h * 65536u + (dense ? i : window_cell(i, p.win)) : (size_t)-1;
+                        cell[k] = i < ncell ? h * 65536u + (dense ? i : window_cell(i, p.win)) : 0xFFFFFFFFu;
                         sum[k] = 0;
                     }
+#pragma unroll 4
                     for (uint32_t r = 0; r < p.world; r++) {
                         const unsigned long long *src = p.buckets[r];
 #pragma unroll
                         for (int k = 0; k < K5_DEEP; k++)
-                            if (cell[k] != (size_t)-1) sum[k] += ld_peer_u64(src + cell[k]);
+                            if (cell[k] != 0xFFFFFFFFu) sum[k] += ld_peer_u64(src + cell[k]);
                     }
 #pragma unroll
                     for (int k = 0; k < K5_DEEP; k++) {
-                        if (cell[k] == (size_t)-1 || sum[k] == 0) continue;
+                        if (cell[k] == 0xFFFFFFFFu || sum[k] == 0) continue;
                         for (uint32_t r = 0; r < p.world; r++) p.out_peer[r][cell[k]] = sum[k];
                     }
                 }
