@@ -191,14 +191,16 @@ void release_thread_shard(ThreadState *ts) {
     ts->shard = nullptr;
     ts->exclusive = false;
 }
+thread_local ThreadState *tl_state = nullptr;
 struct ThreadStateOwner {                        // destroyed at thread exit
     ThreadState *p = nullptr;
     ~ThreadStateOwner() {
         if (p) release_thread_shard(p);
         delete p;
+        p = nullptr;
+        tl_state = nullptr;                      // a later thread-local destructor that still records a sample starts over
     }
 };
-thread_local ThreadState *tl_state = nullptr;
 thread_local ThreadStateOwner tl_owner;
 ThreadState *make_thread_state() {
     tl_owner.p = new ThreadState();
