@@ -449,9 +449,9 @@ def run_b200(a):
         eng.tune("keyed_mode", a.keyed_mode)
     depth = a.pipeline_depth if a.pipeline_depth >= 0 else 2
     peer = world > 1 and a.collective == "peer"
-    # SMs the ingest kernels leave to the snapshot stream.  Peer collective: 1 is enough for one histogram (70 KB per peer);
-    # with 1 024 histograms the two-shot all-reduce moves 2 x 36 MB per rank and needs 4 SMs to finish inside a step
-    # (measured at N = 2: 432 G samples/s with 1 SM, 556 G with 4).  NCCL needs 2 (N <= 4) or 8 SMs.
+    # SMs the ingest kernels leave to the snapshot stream: 1 with the peer collective (its small-payload form needs
+    # one; its large-payload form goes wide for ~0.2 ms between two ingest kernels instead of hiding on a few SMs, where
+    # an SM's ~4 GB/s of NVLink loads would make it slower than the step).  NCCL needs 2 (N <= 4) or 8 SMs.
     if a.reserve_sms >= 0:
         reserve = a.reserve_sms
     elif depth == 0:
@@ -459,7 +459,7 @@ def run_b200(a):
     elif world == 1:
         reserve = 1
     elif peer:
-        reserve = 1 if single else 4
+        reserve = 1
     else:
         reserve = 2 if world <= 4 else 8
     if reserve:

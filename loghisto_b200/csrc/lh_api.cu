@@ -1478,13 +1478,20 @@ extern "C" lh_status lh_snapshot_allreduce(lh_ctx *ctx, uint32_t include_counter
     // CTAs that are not resident yet simply start later (no CTA waits for another CTA of its own grid before the end)
     const size_t items = (size_t)ctx->H * (65536u / K5_CHUNK);
     int grid = (int)std::min<size_t>(items, ctx->H == 1 ? 5 : 16);
-    if (p.two_shot) {
-        // one CTA (1024 threads, 64 registers) per SM the ingest kernels leave free: the write-combining kernel is
-        // cooperative, a wider all-reduce would hold its CTAs back and serialise the two (measured at N = 2)
-        const int room = ctx->k1_reserve_sms > 0 ? ctx->k1_reserve_sms : 8;
-        grid = (int)std::min<size_t>((ctx->H + ctx->comm_world - 1) / ctx->comm_world, (size_t)room);
-    }
     LH_CUDA(ctx, cudaEventRecord(ctx->comm_t0[ring], s));
+    if (p.two_shot) {
+        // An SM sustains only ~4 GB/s of NVLink loads (measured, tools/peer_probe.py: 36 MB take 9.1 / 2.3 / 0.64 / 0.21 ms
+        // on 1 / 4 / 16 / 64 SMs), so the large payload cannot hide on the few SMs the ingest kernels leave free.  It goes
+        // wide and short instead: one small CTA announces this rank and waits for the peers (it may spin for as long as
+        // the ranks are skewed, on one SM), then up to 128 CTAs do the sums in ~0.2 ms; the next ingest kernel's CTAs
+        // start as those finish.
+        PeerParams pa = p;
+        pa.arrive_only = 1;
+        k_peer_allreduce<<<1, K5_THREADS, ctx->H, s>>>(pa);
+        LH_CUDA(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches++;
+        grid = (int)std::min<size_t>((ctx->H + ctx->comm_world - 1) / ctx->comm_world, (size_t)std::max(1, std::min(128, ctx->sm_count - 20)));
+    }
     k_peer_allreduce<<<grid, K5_THREADS, ctx->H, s>>>(p);
     LH_CUDA(ctx, cudaGetLastError());
     LH_CUDA(ctx, cudaEventRecord(ctx->comm_t1[ring], s));

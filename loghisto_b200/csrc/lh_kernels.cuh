@@ -1427,6 +1427,7 @@ struct PeerParams {
     unsigned long long *out_buckets;                      // this rank's reduced arrays (zero outside what is written)
     unsigned long long *out_peer[LH_MAX_RANKS];           // every rank's reduced bucket array (own rank: out_buckets)
     uint32_t two_shot;                                    // 1: each rank sums 1/world of the cells and pushes the sums to every rank
+    uint32_t arrive_only;                                 // 1: announce + wait for every peer, nothing else (one small CTA ahead of a wide launch)
     uint32_t *out_flags;
     unsigned long long *out_counters;
     unsigned int *block_counter;                          // local, zero between launches
@@ -1492,6 +1493,7 @@ k_peer_allreduce(PeerParams p) {
         if (!wait_token(mine + t, token, p.timeout_ns, &seen)) atomicMax(p.status, 1u);
         else if ((seen >> 1) == p.seq && (seen & 1ull) != p.frozen) atomicMax(p.status, 2u);
     }
+    if (p.arrive_only) return;
     if (t == 0) s_cells = 0;
     __syncthreads();
     const bool ok = ld_sys_u32(p.status) == 0;
