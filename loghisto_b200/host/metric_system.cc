@@ -217,7 +217,7 @@ std::atomic<uint64_t> g_system_ids{1};
 // with plain stores.  Threads map onto shards round-robin (one shard per hardware thread by default), so in the
 // steady state a shard has ONE writer and its spinlock is uncontended (an exchange and a store, ~10 ns); the reaper
 // takes it once per interval to commit whatever is open.
-struct MetricSystem::Shard {
+struct alignas(128) MetricSystem::Shard {     // its own cache-line pair: nothing else on the heap shares the lines its owner writes on every call
     // exclusive shards (one owner thread): asymmetric handshake, see asym_available()
     std::atomic<uint32_t> owner_busy{0};     // written by the owner with plain stores
     std::atomic<uint32_t> reaper_wants{0};   // raised by a collecting thread
