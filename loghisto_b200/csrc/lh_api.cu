@@ -179,6 +179,7 @@ struct lh_ctx {
     uint32_t hot_replicas = 1;          // copies of the hot window (all L2-resident); only the vector RED kernel spreads over them
     int keyed_mode = 0;                 // 0 auto, 1 force L2-atomic kernel, 2 force the write-combining owner kernel
     int64_t kp_chunk = 32 << 20;        // samples per chunk of the owner-partitioned kernel
+    uint32_t wc_pf_tiles = 0;           // L2 prefetch distance of that kernel's input, in tiles past the one being loaded (0 = off)
     uint32_t wc_flush_samples = 24576;  // samples a CTA bins between two flushes of its owner buffers
     int wc_spt = 6;                     // tile shape of that kernel (6: 896 threads x 4 samples; 4: 1024 x 4; 3: 768 x 4; 8: 512 x 8)
     // owner-partitioned keyed kernel scratch (allocated on first use)
@@ -393,6 +394,7 @@ lh_status launch_keyed_wc_spt(lh_ctx *ctx, int b, const IdT *ids, const ValT *va
     const double m_max = std::pow((-3.5 + std::sqrt(3.5 * 3.5 + 4.0 * room)) / 2.0, 2.0);
     const uint32_t flush_samples = std::min<uint32_t>(ctx->wc_flush_samples, (uint32_t)(m_max * P));
     prm.flush_tiles = std::max<uint32_t>(1u, flush_samples / S::TILE);
+    prm.pf_tiles = ctx->wc_pf_tiles;
     prm.row_cap = row_cap;
     prm.row_stride = row_cap + WC_ROW_EXTRA;
     prm.slice_tiles = (uint32_t)slice_tiles; prm.queues = ctx->d_kp_queues; prm.q_cnt = ctx->d_kp_cnt;
@@ -1692,6 +1694,11 @@ extern "C" lh_status lh_tune(lh_ctx *ctx, const char *key, int64_t value) {
     if (!strcmp(key, "keyed_mode")) {
         if (value < 0 || value > 2) return fail(ctx, LH_ERR_RANGE, "keyed_mode is 0 (auto), 1 (L2 atomics) or 2 (owner-partitioned, write-combining)");
         ctx->keyed_mode = (int)value;
+        return LH_OK;
+    }
+    if (!strcmp(key, "wc_pf")) {
+        if (value < 0 || value > 8) return fail(ctx, LH_ERR_RANGE, "wc_pf is 0 ... 8 tiles");
+        ctx->wc_pf_tiles = (uint32_t)value;
         return LH_OK;
     }
     if (!strcmp(key, "wc_flush")) {

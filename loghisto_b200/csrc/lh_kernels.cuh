@@ -642,6 +642,7 @@ struct WcParams {
     uint32_t slice_tiles;            // tiles per CTA per chunk
     uint32_t inv_p;                  // floor(2^32 / P) + 1: id / P == __umulhi(id, inv_p) for id < 65536
     uint32_t flush_tiles;            // tiles binned between two flushes of the owner buffers
+    uint32_t pf_tiles;               // the tile this many tiles past the one being loaded is asked of L2 (0 = off)
     uint32_t row_cap;                // records an owner's shared-memory buffer holds (multiple of 64; the host takes what fits)
     uint32_t row_stride;             // row_cap + one spill line + 8 records of padding (bank-conflict-free 128-bit flush)
     unsigned short *queues;          // [2][P owners][P writers][cap]
@@ -716,6 +717,9 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
     // pointers below walk the CTA's slice one tile at a time (no 64-bit multiplies inside the loop).
     const char *vptr = nullptr;                  // this thread's first 32-byte value group of the current tile
     const IdT *iptr = nullptr;                   // ... and its 4 ids
+    // The register pipeline is one tile deep and the first use of a tile (DADD) is the kernel's hottest stall site: the
+    // loads come back late.  A steady L2 prefetch of the tile AFTER the one being loaded turns that load into an L2 hit.
+    const size_t pf_v = (size_t)prm.pf_tiles * S::TILE * 8, pf_i = (size_t)prm.pf_tiles * S::TILE;
     auto load_tile = [&](const char *vp, const IdT *ip, unsigned long long (&raw)[GROUPS][4], IdPack<IdT> (&idp)[GROUPS]) {
 #pragma unroll
         for (int g = 0; g < GROUPS; g++) {
@@ -834,15 +838,26 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
             vptr = reinterpret_cast<const char *>(part == 0 ? prm.vals : prm.vals2) + first * 8;
             iptr = (part == 0 ? ids : reinterpret_cast<const IdT *>(prm.ids2)) + first;
             load_tile(vptr, iptr, cur, cur_id);
+            auto prefetch_ahead = [&](uint32_t tile_loaded) {       // tile_loaded: index (in this part) of the tile vptr points to
+                if (prm.pf_tiles && tile_loaded + prm.pf_tiles < ntile) {
+#pragma unroll
+                    for (int g = 0; g < GROUPS; g++) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(vptr + pf_v + (size_t)g * WC_THREADS * 32));
+                        if ((tid & 3) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(iptr + pf_i + (size_t)g * WC_THREADS * 4));
+                    }
+                }
+            };
             for (uint32_t t = 0; t < ntile; t += 2) {
                 vptr += (size_t)S::TILE * 8;                 // -> tile t + 1
                 iptr += S::TILE;
                 if (t + 1 < ntile) load_tile(vptr, iptr, nxt, nxt_id);
+                prefetch_ahead(t + 1);
                 bin_tile(cur, cur_id, as_i64);
                 if (t + 1 >= ntile) break;
                 vptr += (size_t)S::TILE * 8;                 // -> tile t + 2
                 iptr += S::TILE;
                 if (t + 2 < ntile) load_tile(vptr, iptr, cur, cur_id);
+                prefetch_ahead(t + 2);
                 bin_tile(nxt, nxt_id, as_i64);
             }
         }
