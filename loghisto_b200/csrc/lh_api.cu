@@ -178,7 +178,7 @@ struct lh_ctx {
     int keyed_blocks_per_sm = 8;
     uint32_t hot_replicas = 1;          // copies of the hot window (all L2-resident); only the vector RED kernel spreads over them
     int keyed_mode = 0;                 // 0 auto, 1 force L2-atomic kernel, 2 force the write-combining owner kernel
-    int64_t kp_chunk = 32 << 20;        // samples per chunk of the owner-partitioned kernel
+    int64_t kp_chunk = 64 << 20;        // samples per chunk of the owner-partitioned kernel (16 / 32 / 64 M: 319 / 339 / 354 G samples/s, keyed_pf_probe_r02q.txt)
     uint32_t wc_pf_tiles = 1;           // L2 prefetch distance of that kernel's input, in tiles past the one being loaded (0 = off; 1: +12 %)
     uint32_t wc_flush_samples = 24576;  // samples a CTA bins between two flushes of its owner buffers
     int wc_spt = 6;                     // tile shape of that kernel (6: 896 threads x 4 samples; 4: 1024 x 4; 3: 768 x 4; 8: 512 x 8)
@@ -413,7 +413,7 @@ lh_status launch_keyed_wc(lh_ctx *ctx, int b, const IdT *ids, const ValT *vals, 
                           const IdT *ids2 = nullptr, const long long *vals2 = nullptr, size_t n2 = 0, size_t *taken2 = nullptr) {
 #define LH_WC_SHAPE(code) case code: return launch_keyed_wc_spt<IdT, ValT, code>(ctx, b, ids, vals, n4x4, s, used, taken, ids2, vals2, n2, taken2);
     switch (ctx->wc_spt) {
-        LH_WC_SHAPE(6) LH_WC_SHAPE(4) LH_WC_SHAPE(3) LH_WC_SHAPE(5)
+        LH_WC_SHAPE(6) LH_WC_SHAPE(4) LH_WC_SHAPE(3)
         default: return launch_keyed_wc_spt<IdT, ValT, 8>(ctx, b, ids, vals, n4x4, s, used, taken, ids2, vals2, n2, taken2);
     }
 #undef LH_WC_SHAPE
@@ -1707,7 +1707,7 @@ extern "C" lh_status lh_tune(lh_ctx *ctx, const char *key, int64_t value) {
         return LH_OK;
     }
     if (!strcmp(key, "wc_spt")) {
-        if (value != 4 && value != 6 && value != 3 && value != 8 && value != 5)
+        if (value != 4 && value != 6 && value != 3 && value != 8)
             return fail(ctx, LH_ERR_RANGE, "wc_spt is a shape code: 6 (896 threads x 4 samples), 4 (1024 x 4), 3 (768 x 4) or 8 (512 x 8)");
         ctx->wc_spt = (int)value;
         return LH_OK;

@@ -619,11 +619,10 @@ constexpr int WC_LINE = 64;                   // records per line (128 B)
 
 template <int SPT> struct WcShape {           // shape code -> threads x samples per thread and tile (registers per thread):
                                               // 6: 896 x 4 (72, default), 4: 1024 x 4 (64), 3: 768 x 4 (80), 8: 512 x 8 (128);
-                                              // measured within 3 % of each other, 640 x 4 and 512 x 4 were 3 - 10 % slower.
-                                              // 5: 640 x 4 (96) with a register pipeline THREE tiles deep (experiment)
-    static constexpr int THREADS = SPT == 4 ? 1024 : SPT == 6 ? 896 : SPT == 3 ? 768 : SPT == 5 ? 640 : 512;
+                                              // 640 x 4 and 512 x 4 were 3 - 10 % slower, and a register pipeline three tiles
+                                              // deep (640 x 4, 96 registers) gained nothing over the L2 prefetch below
+    static constexpr int THREADS = SPT == 4 ? 1024 : SPT == 6 ? 896 : SPT == 3 ? 768 : 512;
     static constexpr int PER = SPT == 8 ? 8 : 4;               // samples per thread per tile
-    static constexpr int DEPTH = SPT == 5 ? 3 : 2;             // tile buffers in registers (loads in flight: DEPTH - 1 tiles)
     static constexpr int TILE = THREADS * PER;
 };
 // An owner's shared-memory buffer holds row_cap records (WcParams; 256 when it fits, else 192 or 128): < WC_LINE carried
@@ -712,8 +711,8 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
     const uint32_t row_cap = prm.row_cap, row_stride = prm.row_stride;
 
 
-    unsigned long long cur[GROUPS][4], nxt[GROUPS][4], nx2[GROUPS][4];       // nx2: only with DEPTH 3
-    IdPack<IdT> cur_id[GROUPS], nxt_id[GROUPS], nx2_id[GROUPS];
+    unsigned long long cur[GROUPS][4], nxt[GROUPS][4];
+    IdPack<IdT> cur_id[GROUPS], nxt_id[GROUPS];
     uint32_t since_flush = 0;
     // tile `tile` = TILE consecutive samples; thread tid takes the 4-sample groups tid, tid + THREADS, ... of it.  The
     // pointers below walk the CTA's slice one tile at a time (no 64-bit multiplies inside the loop).
@@ -849,24 +848,6 @@ k_ingest_keyed_wc(WcParams prm, Prec pc) {
                     }
                 }
             };
-            if constexpr (S::DEPTH == 3) {
-                auto adv = [&] { vptr += (size_t)S::TILE * 8; iptr += S::TILE; };
-                adv();                                       // -> tile 1
-                if (1 < ntile) load_tile(vptr, iptr, nxt, nxt_id);
-                for (uint32_t t = 0; t < ntile; t += 3) {
-                    adv();                                   // -> tile t + 2
-                    if (t + 2 < ntile) load_tile(vptr, iptr, nx2, nx2_id);
-                    bin_tile(cur, cur_id, as_i64);
-                    if (t + 1 >= ntile) break;
-                    adv();                                   // -> tile t + 3
-                    if (t + 3 < ntile) load_tile(vptr, iptr, cur, cur_id);
-                    bin_tile(nxt, nxt_id, as_i64);
-                    if (t + 2 >= ntile) break;
-                    adv();                                   // -> tile t + 4
-                    if (t + 4 < ntile) load_tile(vptr, iptr, nxt, nxt_id);
-                    bin_tile(nx2, nx2_id, as_i64);
-                }
-            } else
             for (uint32_t t = 0; t < ntile; t += 2) {
                 vptr += (size_t)S::TILE * 8;                 // -> tile t + 1
                 iptr += S::TILE;
