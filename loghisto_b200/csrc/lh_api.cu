@@ -178,7 +178,7 @@ struct lh_ctx {
     int keyed_blocks_per_sm = 8;
     uint32_t hot_replicas = 1;          // copies of the hot window (all L2-resident); only the vector RED kernel spreads over them
     int keyed_mode = 0;                 // 0 auto, 1 force L2-atomic kernel, 2 force the write-combining owner kernel
-    int64_t kp_chunk = 64 << 20;        // samples per chunk of the owner-partitioned kernel (16 / 32 / 64 M: 319 / 339 / 354 G samples/s, keyed_pf_probe_r02q.txt)
+    int64_t kp_chunk = 256 << 20;       // samples per chunk of the owner-partitioned kernel (16 / 32 / 64 / 128 / 256 M: 319 / 339 / 354 / 363 / 368 G samples/s, keyed_pf_probe_r02q/r.txt)
     uint32_t wc_pf_tiles = 1;           // L2 prefetch distance of that kernel's input, in tiles past the one being loaded (0 = off; 1: +12 %)
     uint32_t wc_flush_samples = 24576;  // samples a CTA bins between two flushes of its owner buffers
     int wc_spt = 6;                     // tile shape of that kernel (6: 896 threads x 4 samples; 4: 1024 x 4; 3: 768 x 4; 8: 512 x 8)
