@@ -86,22 +86,42 @@ size_t next_thread_slot() {
 // Here the steady-state lookup touches only thread-local memory: a direct-mapped cache keyed by the hash of the
 // name's bytes, verified byte for byte (a collision can never send a sample to the wrong histogram).  A miss falls
 // back to the shared intern table (the reference's RLock / double-checked Lock idiom, metrics.go:275-294).
+// Fixed-size loads only: a memcpy of a run-time length is a library call, and it was most of the cost of a lookup.
+inline uint64_t load8(const char *p) { uint64_t w; memcpy(&w, p, 8); return w; }
+inline uint64_t load_1to7(const char *p, size_t n) {        // n in 1..7, reads only p[0..n)
+    if (n >= 4) {
+        uint32_t a, b;
+        memcpy(&a, p, 4);
+        memcpy(&b, p + n - 4, 4);
+        return (uint64_t)a | ((uint64_t)b << 32);
+    }
+    return (uint64_t)(uint8_t)p[0] | ((uint64_t)(uint8_t)p[n >> 1] << 8) | ((uint64_t)(uint8_t)p[n - 1] << 16);
+}
+// the (at most) 16 bytes of a short name as two words that determine them given the length
+inline void short_words(const char *p, size_t n, uint64_t *w0, uint64_t *w1) {
+    if (n >= 8) { *w0 = load8(p); *w1 = load8(p + n - 8); }
+    else { *w0 = n ? load_1to7(p, n) : 0; *w1 = 0; }
+}
 inline uint64_t hash_bytes(const char *p, size_t n) {
     uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xFF51AFD7ED558CCDull);
-    while (n >= 8) {
-        uint64_t w;
-        memcpy(&w, p, 8);
+    const char *q = p;
+    size_t m = n;
+    while (m >= 8) {
+        h = (h ^ load8(q)) * 0xC2B2AE3D27D4EB4Full;
+        h ^= h >> 29;
+        q += 8; m -= 8;
+    }
+    if (m) {                                                 // the tail: an overlapping 8-byte load when the name allows it
+        const uint64_t w = n >= 8 ? load8(p + n - 8) : load_1to7(q, m);
         h = (h ^ w) * 0xC2B2AE3D27D4EB4Full;
         h ^= h >> 29;
-        p += 8; n -= 8;
     }
-    if (n) {
-        uint64_t w = 0;
-        memcpy(&w, p, n);
-        h = (h ^ w) * 0xC2B2AE3D27D4EB4Full;
-        h ^= h >> 29;
-    }
-    return h ^ (h >> 32);
+    // full avalanche: the table index is the LOW bits, and the bytes that tell "histogram7" from "histogram1023" sit in
+    // the high half of the overlapping tail word
+    h ^= h >> 33;
+    h *= 0xFF51AFD7ED558CCDull;
+    h ^= h >> 33;
+    return h;
 }
 
 struct NameCache {
@@ -110,15 +130,13 @@ struct NameCache {
     // bytes; the names' bytes live in an append-only arena owned by the cache.
     struct Entry {                               // id_plus1 == 0: empty
         uint64_t hash; const char *name; uint32_t len; uint32_t id_plus1;
-        char head[16];                           // the first 16 bytes of the name, zero padded: short names never touch the arena
+        uint64_t w0, w1;                         // short_words() of a name of at most 16 bytes: it never touches the arena
         bool matches(uint64_t h, const char *p, size_t n) const {
             if (hash != h || len != n) return false;
             if (n <= 16) {
-                uint64_t a[2] = {0, 0};
-                memcpy(a, p, n);
-                uint64_t b[2];
-                memcpy(b, head, 16);
-                return a[0] == b[0] && a[1] == b[1];
+                uint64_t a0, a1;
+                short_words(p, n, &a0, &a1);
+                return a0 == w0 && a1 == w1;
             }
             return memcmp(name, p, n) == 0;
         }
@@ -131,7 +149,12 @@ struct NameCache {
     const Entry *last = nullptr;                 // most recently found entry: a thread that repeats one name skips the hash
     bool find_last(const char *p, size_t n, uint32_t *id) const {
         const Entry *x = last;
-        if (x && x->len == n && memcmp(x->name, p, n) == 0) { *id = x->id_plus1 - 1; return true; }
+        if (x && x->len == n) {
+            bool same;
+            if (n <= 16) { uint64_t a0, a1; short_words(p, n, &a0, &a1); same = a0 == x->w0 && a1 == x->w1; }
+            else same = memcmp(x->name, p, n) == 0;
+            if (same) { *id = x->id_plus1 - 1; return true; }
+        }
         return false;
     }
     bool find(uint64_t h, const char *p, size_t n, uint32_t *id) {
@@ -166,7 +189,7 @@ struct NameCache {
         memcpy(arena_next, p, n);
         Entry en{};
         en.hash = h; en.name = arena_next; en.len = (uint32_t)n; en.id_plus1 = id + 1;
-        memcpy(en.head, p, std::min<size_t>(n, 16));
+        if (n <= 16) short_words(p, n, &en.w0, &en.w1);
         insert_raw(en);
         arena_next += n; arena_left -= n;
         count++;
