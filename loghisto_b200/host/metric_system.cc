@@ -497,9 +497,13 @@ void MetricSystem::Histogram(const char *name, size_t len, double value) noexcep
 }
 
 void MetricSystem::Counter(const std::string &name, uint64_t amount) noexcept {
+    ThreadState *ts = thread_state(*this, system_id_);
     uint32_t id;
-    if (!lookup_counter(name.data(), name.size(), &id)) return;
-    Shard &s = *static_cast<Shard *>(thread_state(*this, system_id_)->shard);
+    if (!ts->c.find_last(name.data(), name.size(), &id) &&
+        __builtin_expect(!ts->c.find(hash_bytes(name.data(), name.size()), name.data(), name.size(), &id), 0)) {
+        if (!lookup_counter(name.data(), name.size(), &id)) return;  // name table full: dropped and counted
+    }
+    Shard &s = *static_cast<Shard *>(ts->shard);
     ShardGuard g(s);
     s.c_touched[id] = 1;                    // Counter(name, 0) still makes the name appear in Rates (metrics.go:430-433)
     s.c_any_touched = true;
