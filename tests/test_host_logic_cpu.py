@@ -159,3 +159,29 @@ def test_collects_race_with_per_call_ingest(MS, monkeypatch, shard_lock):
     assert ms.dropped() == 0
     assert int(total.sum()) == 2 * n
     assert (total == want).all()
+
+
+def test_name_lengths_around_the_cache_word_boundaries(MS):
+    """The per-thread name cache compares names of up to 16 bytes as two (overlapping) 8-byte words and hashes tails with
+    overlapping loads: names of every length 0..40, some differing only in one byte at either end, must stay distinct."""
+    names = []
+    for n in range(0, 41):
+        base = ("abcdefghijklmnopqrstuvwxyz0123456789ABCDEFGH")[:n]
+        names.append(base)
+        if n:
+            names.append(base[:-1] + "#")            # differs in the last byte
+            names.append("#" + base[1:])             # differs in the first byte
+        if n >= 9:
+            names.append(base[:4] + "#" + base[5:])  # differs in the middle of the first word
+    names = list(dict.fromkeys(names))
+    ms = MS(interval_s=3600.0, max_histograms=len(names) + 4, max_counters=len(names) + 4)
+    for rnd in range(3):                                 # the second and third rounds hit the caches
+        for i, nm in enumerate(names):
+            for _ in range(i % 5 + 1):
+                ms.Histogram(nm, float(i))
+            ms.Counter(nm, i + 1)
+    raw, _ = ms.collect_and_process()
+    assert len(raw["Histograms"]) == len(names) and len(raw["Rates"]) == len(names)
+    for i, nm in enumerate(names):
+        assert sum(raw["Histograms"][nm].values()) == 3 * (i % 5 + 1), (i, nm)
+        assert raw["Rates"][nm] == 3 * (i + 1), (i, nm)
