@@ -298,8 +298,10 @@ LH_API lh_status lh_memcpy_d2h(lh_ctx *ctx, void *h_dst, const void *d_src, size
 /* kernel-variant selection for profiling: key "k1" -> variant number,
  * "k1_grid_mult", "k1_reserve_sms" (SMs the ingest kernels leave free so that a concurrent
  * snapshot / all-reduce kernel can run beside them), "keyed_blocks_per_sm", "keyed_mode" (0 auto, 1 L2-atomic
- * kernel, 2 owner-partitioned write-combining kernel whatever the batch size), "kp_chunk" (samples per chunk of the
- * owner-partitioned kernel) */
+ * kernel, 2 owner-partitioned write-combining kernel whatever the batch size), and that kernel's knobs: "kp_chunk"
+ * (samples per chunk, default 256 M), "wc_spt" (tile shape code: 6 = 896 threads x 4 samples (default), 4 = 1024 x 4,
+ * 3 = 768 x 4, 8 = 512 x 8), "wc_flush" (samples a CTA bins between two flushes of its owner buffers, default 24576),
+ * "wc_pf" (L2 prefetch distance of its input in tiles, default 1, 0 = off) */
 LH_API lh_status lh_tune(lh_ctx *ctx, const char *key, int64_t value);
 LH_API int32_t lh_k1_variant_count(void);
 LH_API int32_t lh_k1_variant_current(lh_ctx *ctx);
